@@ -1,0 +1,210 @@
+"""ctypes binding of libbuctd_b200.so (the C ABI declared in include/buctd_b200.h).
+
+The product path fails loudly when the CUDA library is missing or cannot be loaded: there is no
+CPU or PyTorch fallback anywhere in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbuctd_b200.so")
+
+ABI_VERSION = 1
+F16, BF16 = 0, 1
+TG_FLAT, TG_PATCH = 0, 1
+OUT_ACT16, OUT_ROWS16, OUT_NCHW32 = 0, 1, 2
+(OP_TAPGEMM, OP_STEM, OP_FUSE, OP_RESIZE, OP_CHAN_ATT, OP_POS_ATT, OP_DA_COMBINE, OP_PRENET, OP_DECODE,
+ OP_RASTER) = range(1, 11)
+
+i32, i64, vp, fp = C.c_int32, C.c_int64, C.c_void_p, C.c_void_p
+
+
+class TapGemmArgs(C.Structure):
+    _fields_ = [("dtype", i32), ("mode", i32), ("ntaps", i32), ("stride", i32), ("batch", i32),
+                ("out_h", i32), ("out_w", i32), ("in_h", i32), ("in_w", i32), ("m_rows", i64),
+                ("k", i32), ("a_cs", i32), ("n", i32), ("n_alloc", i32), ("w_cs", i32), ("out_cs", i32),
+                ("res_cs", i32), ("relu", i32), ("out_mode", i32), ("reserved", i32),
+                ("a", vp), ("w", vp), ("bias", fp), ("residual", vp), ("out", vp)]
+
+
+class StemArgs(C.Structure):
+    _fields_ = [("dtype", i32), ("batch", i32), ("x_channels", i32), ("h", i32), ("w", i32), ("out_cs", i32),
+                ("x", fp), ("weight", fp), ("bias", fp), ("out", vp)]
+
+
+class FuseArgs(C.Structure):
+    _fields_ = [("dtype", i32), ("batch", i32), ("h", i32), ("w", i32), ("c", i32), ("out_cs", i32),
+                ("nterms", i32), ("relu", i32), ("term", vp * 4), ("term_cs", i32 * 4), ("term_shift", i32 * 4),
+                ("out", vp)]
+
+
+class ResizeArgs(C.Structure):
+    _fields_ = [("dtype", i32), ("batch", i32), ("x_channels", i32), ("c_off", i32), ("cc", i32), ("h", i32),
+                ("w", i32), ("oh", i32), ("ow", i32), ("out_cs", i32), ("antialias", i32), ("reserved", i32),
+                ("x", fp), ("out", vp)]
+
+
+class ChanAttArgs(C.Structure):
+    _fields_ = [("dtype", i32), ("batch", i32), ("h", i32), ("w", i32), ("c", i32), ("y_cs", i32), ("yc_cs", i32),
+                ("reserved", i32), ("y", vp), ("yc", vp), ("scratch", fp), ("out", vp)]
+
+
+class PosAttArgs(C.Structure):
+    _fields_ = [("dtype", i32), ("batch", i32), ("h", i32), ("w", i32), ("c", i32), ("q_cs", i32), ("k_cs", i32),
+                ("v_cs", i32), ("o_cs", i32), ("reserved", i32), ("q", vp), ("k", vp), ("v", vp), ("o", vp)]
+
+
+class DaCombineArgs(C.Structure):
+    _fields_ = [("dtype", i32), ("batch", i32), ("h", i32), ("w", i32), ("c", i32), ("x_cs", i32), ("p_cs", i32),
+                ("out_cs", i32), ("channel_only", i32), ("reserved", i32),
+                ("x", vp), ("p_out", vp), ("c_out", vp), ("out", vp)]
+
+
+class PrenetArgs(C.Structure):
+    _fields_ = [("batch", i32), ("x_channels", i32), ("h", i32), ("w", i32),
+                ("x", fp), ("w_eff", fp), ("b_eff", fp), ("wc", fp), ("out", fp)]
+
+
+class DecodeArgs(C.Structure):
+    _fields_ = [("batch", i32), ("k", i32), ("h", i32), ("w", i32), ("post_process", i32), ("reserved", i32),
+                ("heatmaps", fp), ("center", fp), ("scale", fp), ("preds", fp), ("maxvals", fp), ("coords", fp),
+                ("idx", vp)]
+
+
+class RasterArgs(C.Structure):
+    _fields_ = [("batch", i32), ("k", i32), ("kstride", i32), ("h", i32), ("w", i32), ("mode", i32),
+                ("out_channels", i32), ("c_off", i32), ("kpts", fp), ("colors", fp), ("out", fp), ("scratch", vp)]
+
+
+OP_STRUCT = {OP_TAPGEMM: TapGemmArgs, OP_STEM: StemArgs, OP_FUSE: FuseArgs, OP_RESIZE: ResizeArgs,
+             OP_CHAN_ATT: ChanAttArgs, OP_POS_ATT: PosAttArgs, OP_DA_COMBINE: DaCombineArgs, OP_PRENET: PrenetArgs,
+             OP_DECODE: DecodeArgs, OP_RASTER: RasterArgs}
+
+# every symbol include/buctd_b200.h declares (tests/test_abi.py checks the header against this list)
+EXPORTS = ["buctd_abi_version", "buctd_last_error", "buctd_create", "buctd_destroy", "buctd_launch_count",
+           "buctd_tapgemm", "buctd_stem_conv", "buctd_hr_fuse", "buctd_cond_resize", "buctd_coam_channel_att",
+           "buctd_coam_position_att", "buctd_da_combine", "buctd_prenet", "buctd_decode_heatmaps",
+           "buctd_rasterize_condition", "buctd_act16_to_nchw32", "buctd_nchw32_to_act16", "buctd_plan_create",
+           "buctd_plan_destroy", "buctd_plan_add", "buctd_plan_size", "buctd_plan_run", "buctd_plan_run_range"]
+
+_IMMEDIATE = {OP_TAPGEMM: "buctd_tapgemm", OP_STEM: "buctd_stem_conv", OP_FUSE: "buctd_hr_fuse",
+              OP_RESIZE: "buctd_cond_resize", OP_CHAN_ATT: "buctd_coam_channel_att",
+              OP_POS_ATT: "buctd_coam_position_att", OP_DA_COMBINE: "buctd_da_combine", OP_PRENET: "buctd_prenet",
+              OP_DECODE: "buctd_decode_heatmaps", OP_RASTER: "buctd_rasterize_condition"}
+
+
+class BuctdError(RuntimeError):
+    pass
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """dlopen the library (once).  Raises BuctdError if it has not been built."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise BuctdError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                             "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        lib.buctd_last_error.restype = C.c_char_p
+        lib.buctd_launch_count.restype = C.c_longlong
+        lib.buctd_launch_count.argtypes = [vp]
+        lib.buctd_create.argtypes = [C.c_int, C.POINTER(vp)]
+        lib.buctd_destroy.argtypes = [vp]
+        for name in _IMMEDIATE.values():
+            getattr(lib, name).argtypes = [vp, vp, vp]
+        lib.buctd_act16_to_nchw32.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
+        lib.buctd_nchw32_to_act16.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                              C.c_int, vp, vp]
+        lib.buctd_plan_create.argtypes = [vp, C.POINTER(vp)]
+        lib.buctd_plan_destroy.argtypes = [vp]
+        lib.buctd_plan_add.argtypes = [vp, C.c_int, vp, C.c_size_t]
+        lib.buctd_plan_size.argtypes = [vp]
+        lib.buctd_plan_run.argtypes = [vp, vp]
+        lib.buctd_plan_run_range.argtypes = [vp, C.c_int, C.c_int, vp]
+        if lib.buctd_abi_version() != ABI_VERSION:
+            raise BuctdError("libbuctd_b200.so ABI %d != binding ABI %d: rebuild" % (lib.buctd_abi_version(), ABI_VERSION))
+        _lib = lib
+        return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().buctd_last_error().decode("utf-8", "replace")
+        raise BuctdError("%s failed (%d): %s" % (what or "buctd call", rc, msg))
+
+
+class Context:
+    """Per-device handle (buctd_create / buctd_destroy)."""
+    _by_device = {}
+
+    def __init__(self, device: int):
+        self.lib = load()
+        h = vp()
+        check(self.lib.buctd_create(int(device), C.byref(h)), "buctd_create(%d)" % device)
+        self.handle = h
+        self.device = int(device)
+
+    @classmethod
+    def get(cls, device: int) -> "Context":
+        with _lock:
+            ctx = cls._by_device.get(device)
+        if ctx is None:
+            ctx = cls(device)
+            with _lock:
+                cls._by_device[device] = ctx
+        return ctx
+
+    def launch_count(self) -> int:
+        return int(self.lib.buctd_launch_count(self.handle))
+
+    def run(self, kind: int, args: C.Structure, stream: int):
+        fn = getattr(self.lib, _IMMEDIATE[kind])
+        check(fn(self.handle, C.byref(args), vp(stream)), _IMMEDIATE[kind])
+
+    def act16_to_nchw32(self, dtype, act_ptr, b, h, w, c, cs, out_ptr, stream):
+        check(self.lib.buctd_act16_to_nchw32(self.handle, dtype, vp(act_ptr), b, h, w, c, cs, vp(out_ptr), vp(stream)),
+              "buctd_act16_to_nchw32")
+
+    def nchw32_to_act16(self, dtype, x_ptr, b, xc, c_off, c, h, w, cs, out_ptr, stream):
+        check(self.lib.buctd_nchw32_to_act16(self.handle, dtype, vp(x_ptr), b, xc, c_off, c, h, w, cs, vp(out_ptr),
+                                             vp(stream)), "buctd_nchw32_to_act16")
+
+
+class Plan:
+    """Recorded launch sequence (buctd_plan_*)."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        h = vp()
+        check(ctx.lib.buctd_plan_create(ctx.handle, C.byref(h)), "buctd_plan_create")
+        self.handle = h
+        self.labels = []
+
+    def add(self, kind: int, args: C.Structure, label: str = ""):
+        check(self.ctx.lib.buctd_plan_add(self.handle, kind, C.byref(args), C.sizeof(args)),
+              "buctd_plan_add(%s)" % (label or kind))
+        self.labels.append(label)
+
+    def __len__(self):
+        return int(self.ctx.lib.buctd_plan_size(self.handle))
+
+    def run(self, stream: int, first: int = 0, last: int | None = None):
+        last = len(self) if last is None else last
+        check(self.ctx.lib.buctd_plan_run_range(self.handle, first, last, vp(stream)), "buctd_plan_run")
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.ctx.lib.buctd_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass

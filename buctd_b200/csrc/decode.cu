@@ -1,0 +1,254 @@
+// Heat-map decode (argmax + quarter-pixel refine + inverse crop transform) and the condition
+// rasteriser.  Both are HBM-bound: decode reads each heat-map exactly once, the rasteriser writes
+// each condition plane exactly once.
+#include "common.cuh"
+#include "internal.h"
+
+namespace buctd {
+
+// =================================================================================================
+// decode: get_max_preds + get_final_preds, lib/core/inference.py:19-87; transform_preds,
+// lib/utils/transforms.py:78-118 (inv=1, rot=0: a similarity with factor 200*scale[0]/W).
+// One block per (b,k).  Ties: the FIRST flat index wins (np.argmax).  NaN inputs are not defined.
+// =================================================================================================
+__global__ void __launch_bounds__(256) decode_kernel(buctd_decode_args a) {
+  const int bk = blockIdx.x;
+  const int hw = a.h * a.w;
+  const float* hm = a.heatmaps + (long long)bk * hw;
+  float best = -INFINITY;
+  int bidx = 0x7fffffff;
+  // 128-bit loads when the plane is 16-byte aligned
+  if ((hw & 3) == 0 && ((reinterpret_cast<uintptr_t>(hm) & 15) == 0)) {
+    const float4* h4 = reinterpret_cast<const float4*>(hm);
+    for (int i = threadIdx.x; i < hw / 4; i += blockDim.x) {
+      const float4 v = h4[i];
+      const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (e[j] > best) { best = e[j]; bidx = 4 * i + j; }   // strict >: first index within the thread's ascending scan
+    }
+  } else {
+    for (int i = threadIdx.x; i < hw; i += blockDim.x) {
+      const float v = hm[i];
+      if (v > best) { best = v; bidx = i; }
+    }
+  }
+  // warp then block reduction on (value desc, index asc)
+  for (int o = 16; o; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffff, best, o);
+    const int oi = __shfl_xor_sync(0xffffffff, bidx, o);
+    if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+  }
+  __shared__ float s_v[8];
+  __shared__ int s_i[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_v[warp] = best; s_i[warp] = bidx; }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+    if (s_v[w] > best || (s_v[w] == best && s_i[w] < bidx)) { best = s_v[w]; bidx = s_i[w]; }
+  if (bidx == 0x7fffffff) bidx = 0;      // all -inf / NaN plane: np.argmax gives 0
+
+  float cx = (float)(bidx % a.w);
+  float cy = floorf((float)bidx / (float)a.w);
+  if (!(best > 0.0f)) { cx = 0.f; cy = 0.f; }             // pred_mask = maxvals > 0
+  if (a.idx) a.idx[bk] = bidx;
+  if (a.coords) { a.coords[2 * bk] = cx; a.coords[2 * bk + 1] = cy; }
+  a.maxvals[bk] = best;
+  if (a.post_process) {
+    const int px = (int)floorf(cx + 0.5f), py = (int)floorf(cy + 0.5f);
+    if (1 < px && px < a.w - 1 && 1 < py && py < a.h - 1) {
+      const float dx = hm[py * a.w + px + 1] - hm[py * a.w + px - 1];
+      const float dy = hm[(py + 1) * a.w + px] - hm[(py - 1) * a.w + px];
+      cx += (dx > 0.f ? 0.25f : (dx < 0.f ? -0.25f : 0.f));
+      cy += (dy > 0.f ? 0.25f : (dy < 0.f ? -0.25f : 0.f));
+    }
+  }
+  if (a.center != nullptr && a.scale != nullptr) {
+    const int b = bk / a.k;
+    // the reference builds the 2x3 matrix in float64 from float32 points, applies it in float64,
+    // then stores float32
+    const double f = (double)(a.scale[2 * b] * 200.0f) / (double)a.w;
+    const double tx = (double)a.center[2 * b] - f * (double)a.w * 0.5;
+    const double ty = (double)a.center[2 * b + 1] - f * (double)a.h * 0.5;
+    a.preds[2 * bk] = (float)(f * (double)cx + tx);
+    a.preds[2 * bk + 1] = (float)(f * (double)cy + ty);
+  } else {
+    a.preds[2 * bk] = cx;
+    a.preds[2 * bk + 1] = cy;
+  }
+}
+
+int launch_decode(const buctd_decode_args& a, cudaStream_t st) {
+  BUCTD_CHECK(a.heatmaps && a.preds && a.maxvals, BUCTD_ERR_INVALID, "decode: null pointer");
+  BUCTD_CHECK(a.batch >= 0 && a.k > 0 && a.h > 0 && a.w > 0, BUCTD_ERR_INVALID, "decode: bad shape");
+  BUCTD_CHECK((a.center == nullptr) == (a.scale == nullptr), BUCTD_ERR_INVALID, "decode: center and scale go together");
+  if (a.batch == 0) return BUCTD_OK;
+  decode_kernel<<<a.batch * a.k, 256, 0, st>>>(a);
+  BUCTD_CUDA(cudaGetLastError());
+  return BUCTD_OK;
+}
+
+// =================================================================================================
+// rasteriser: lib/dataset/JointsDataset.py:457-543.  cv2.GaussianBlur(15x15, sigma 0 -> 2.6,
+// BORDER_REFLECT_101) of an impulse image is separable; with reflection the 1-D response of an
+// impulse at p is  g_p[x] = sum_t k[t] * [reflect101(x + t - 7) == p].  Arithmetic in float64 like
+// the reference (np.zeros is float64), stored as float32.
+// =================================================================================================
+__device__ __forceinline__ int reflect101(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+__device__ void gauss15(double* k) {
+  const double sigma = 0.3 * ((15 - 1) * 0.5 - 1) + 0.8;
+  double s = 0;
+  for (int i = 0; i < 15; ++i) {
+    const double r = i - 7;
+    k[i] = exp(-(r * r) / (2.0 * sigma * sigma));
+    s += k[i];
+  }
+  for (int i = 0; i < 15; ++i) k[i] /= s;
+}
+
+__device__ __forceinline__ double folded(const double* k, int x, int p, int n) {
+  double v = 0;
+  for (int t = 0; t < 15; ++t)
+    if (reflect101(x + t - 7, n) == p) v += k[t];
+  return v;
+}
+
+__device__ __forceinline__ bool kpt_pixel(const float* kp, int w, int h, int* px, int* py) {
+  const int x = (int)kp[0], y = (int)kp[1];       // .astype(int): truncation toward zero
+  if (0 < x && x < w && 0 < y && y < h) { *px = x - 1; *py = y - 1; return true; }
+  return false;
+}
+
+// mode 0 (stacked): grid (ceil(H/32), K, B); each block writes 32 rows of one plane.
+__global__ void __launch_bounds__(256) raster_stacked_kernel(buctd_raster_args a) {
+  __shared__ double s_k[15];
+  __shared__ double s_gx[512];
+  __shared__ double s_gy[32];
+  __shared__ double s_mx, s_my;
+  const int k = blockIdx.y, b = blockIdx.z;
+  const int y0 = blockIdx.x * 32;
+  float* out = a.out + (((long long)b * a.out_channels + a.c_off + k) * a.h) * a.w;
+  int px, py;
+  const bool on = kpt_pixel(a.kpts + ((long long)b * a.k + k) * a.kstride, a.w, a.h, &px, &py);
+  if (threadIdx.x == 0) gauss15(s_k);
+  __syncthreads();
+  if (on) {
+    for (int x = threadIdx.x; x < a.w; x += blockDim.x) s_gx[x] = folded(s_k, x, px, a.w);
+    if (threadIdx.x < 32) s_gy[threadIdx.x] = (y0 + threadIdx.x < a.h) ? folded(s_k, y0 + threadIdx.x, py, a.h) : 0.0;
+    if (threadIdx.x == 0) {
+      // peak of the blurred impulse = max_x gx * max_y gy, attained inside the 15-tap window
+      double mx = 0, my = 0;
+      for (int t = -7; t <= 7; ++t) {
+        if (px + t >= 0 && px + t < a.w) mx = fmax(mx, folded(s_k, px + t, px, a.w));
+        if (py + t >= 0 && py + t < a.h) my = fmax(my, folded(s_k, py + t, py, a.h));
+      }
+      s_mx = mx; s_my = my;
+    }
+  }
+  __syncthreads();
+  const double am = on ? (s_my * (s_mx * 255.0)) : 0.0;
+  const double den = am / 255.0;
+  for (int i = threadIdx.x; i < 32 * a.w; i += blockDim.x) {
+    const int yy = i / a.w, x = i % a.w;
+    if (y0 + yy >= a.h) break;
+    float v = 0.f;
+    if (on) {
+      const double g = s_gy[yy] * (s_gx[x] * 255.0);     // column pass of (row pass of the impulse)
+      v = (float)(g / den);
+    }
+    out[(long long)(y0 + yy) * a.w + x] = v;
+  }
+}
+
+// modes 1/2: pass 1 accumulates the un-normalised image maximum per crop (as ordered int64 bits of
+// a non-negative double) into scratch; pass 2 recomputes and normalises.
+template <bool WRITE>
+__global__ void __launch_bounds__(256) raster_sum_kernel(buctd_raster_args a, unsigned long long* scratch) {
+  __shared__ double s_k[15];
+  __shared__ int s_px[64], s_py[64];
+  __shared__ float s_amp[64][3];
+  __shared__ int s_n;
+  const int b = blockIdx.z;
+  const int y = blockIdx.x;
+  if (threadIdx.x == 0) {
+    gauss15(s_k);
+    int n = 0;
+    for (int k = 0; k < a.k && k < 64; ++k) {
+      int px, py;
+      if (!kpt_pixel(a.kpts + ((long long)b * a.k + k) * a.kstride, a.w, a.h, &px, &py)) continue;
+      // later keypoints overwrite earlier ones at the same pixel
+      int slot = n;
+      for (int j = 0; j < n; ++j)
+        if (s_px[j] == px && s_py[j] == py) slot = j;
+      s_px[slot] = px; s_py[slot] = py;
+      for (int c = 0; c < 3; ++c) s_amp[slot][c] = a.mode == 1 ? a.colors[k * 3 + c] : 255.f;
+      if (slot == n) ++n;
+    }
+    s_n = n;
+  }
+  __syncthreads();
+  const int nch = a.mode == 1 ? 3 : 1;
+  double lmax = 0;
+  double den = 1.0;
+  if (WRITE) {
+    const double am = __longlong_as_double((long long)scratch[b]);
+    den = am / 255.0;
+  }
+  for (int x = threadIdx.x; x < a.w; x += blockDim.x) {
+    double v[3] = {0, 0, 0};
+    for (int j = 0; j < s_n; ++j) {
+      if (abs(y - s_py[j]) > 14 || abs(x - s_px[j]) > 14) continue;
+      const double gy = folded(s_k, y, s_py[j], a.h);
+      if (gy == 0) continue;
+      const double gx = folded(s_k, x, s_px[j], a.w);
+      for (int c = 0; c < nch; ++c) v[c] += gy * (gx * (double)s_amp[j][c]);
+    }
+    if (!WRITE) {
+      for (int c = 0; c < nch; ++c) lmax = fmax(lmax, v[c]);
+    } else {
+      for (int c = 0; c < 3; ++c) {
+        double r = v[a.mode == 1 ? c : 0];
+        if (den != 0) r = r / den;
+        float f = (float)r;
+        if (a.mode == 2) f = (float)(long long)r;           // .astype(int)
+        a.out[(((long long)b * a.out_channels + a.c_off + c) * a.h + y) * a.w + x] = f;
+      }
+    }
+  }
+  if (!WRITE) {
+    for (int o = 16; o; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(0xffffffff, lmax, o));
+    if ((threadIdx.x & 31) == 0 && lmax > 0)
+      atomicMax(reinterpret_cast<unsigned long long*>(&scratch[b]), (unsigned long long)__double_as_longlong(lmax));
+  }
+}
+
+int launch_raster(const buctd_raster_args& a, cudaStream_t st, int* nlaunch) {
+  BUCTD_CHECK(a.kpts && a.out, BUCTD_ERR_INVALID, "raster: null pointer");
+  BUCTD_CHECK(a.kstride >= 2 && a.w <= 512 && a.k >= 1, BUCTD_ERR_INVALID, "raster: bad kstride/width/k");
+  BUCTD_CHECK(a.mode >= 0 && a.mode <= 2, BUCTD_ERR_INVALID, "raster: bad mode %d", a.mode);
+  if (nlaunch) *nlaunch = 1;
+  if (a.batch == 0) return BUCTD_OK;
+  if (a.mode == 0) {
+    BUCTD_CHECK(a.c_off + a.k <= a.out_channels, BUCTD_ERR_INVALID, "raster: channels out of range");
+    raster_stacked_kernel<<<dim3(ceil_div(a.h, 32), a.k, a.batch), 256, 0, st>>>(a);
+  } else {
+    BUCTD_CHECK(a.c_off + 3 <= a.out_channels && a.k <= 64, BUCTD_ERR_INVALID, "raster: channels out of range / K > 64");
+    BUCTD_CHECK(a.mode != 1 || a.colors != nullptr, BUCTD_ERR_INVALID, "raster: coloured mode needs colors");
+    BUCTD_CHECK(a.scratch != nullptr, BUCTD_ERR_INVALID, "raster: modes 1/2 need 8*B bytes of scratch");
+    unsigned long long* d_scratch = reinterpret_cast<unsigned long long*>(a.scratch);
+    BUCTD_CUDA(cudaMemsetAsync(d_scratch, 0, sizeof(unsigned long long) * a.batch, st));
+    raster_sum_kernel<false><<<dim3(a.h, 1, a.batch), 128, 0, st>>>(a, d_scratch);
+    raster_sum_kernel<true><<<dim3(a.h, 1, a.batch), 128, 0, st>>>(a, d_scratch);
+    if (nlaunch) *nlaunch = 2;
+  }
+  BUCTD_CUDA(cudaGetLastError());
+  return BUCTD_OK;
+}
+
+}  // namespace buctd

@@ -1,0 +1,61 @@
+// Internal (non-ABI) declarations shared by the translation units of libbuctd_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <vector>
+
+#include "../../include/buctd_b200.h"
+
+struct buctd_ctx {
+  int device = 0;
+  int sm_count = 0;
+  std::atomic<long long> launches{0};
+};
+
+namespace buctd {
+
+struct TapGemmKParams {
+  int mode, ntaps, stride, num_kc, k16, wp;
+  long long m_rows;
+  int B, H, W;
+  int tw, th, tiles_x, tiles_y;
+  int n, n_alloc;
+  int out_cs, res_cs, relu, out_mode;
+  uint32_t a_tile_bytes;
+  const float* bias;
+  const void* residual;
+  void* out;
+};
+
+// everything a tap-GEMM launch needs, computed (tensor maps encoded) once
+struct TapGemmLaunch {
+  alignas(64) CUtensorMap map_a;
+  alignas(64) CUtensorMap map_b;
+  TapGemmKParams kp;
+  dim3 grid;
+  int bn;
+  int dtype;
+};
+
+int tapgemm_prepare(const buctd_tapgemm_args& a, TapGemmLaunch* L);
+int tapgemm_launch(const TapGemmLaunch& L, cudaStream_t st);
+int tapgemm_init_device();
+
+// immediate launchers of the CUDA-core kernels (each returns a BUCTD_* code)
+int launch_stem(const buctd_stem_args& a, cudaStream_t st);
+int launch_fuse(const buctd_fuse_args& a, cudaStream_t st);
+int launch_resize(const buctd_resize_args& a, cudaStream_t st);
+int launch_chan_att(const buctd_chan_att_args& a, cudaStream_t st, int* nlaunch);
+int launch_pos_att(const buctd_pos_att_args& a, cudaStream_t st);
+int launch_da_combine(const buctd_da_combine_args& a, cudaStream_t st);
+int launch_prenet(const buctd_prenet_args& a, cudaStream_t st);
+int launch_decode(const buctd_decode_args& a, cudaStream_t st);
+int launch_raster(const buctd_raster_args& a, cudaStream_t st, int* nlaunch);
+int launch_act16_to_nchw32(int dtype, const void* act, int B, int H, int W, int C, int cs, float* out, cudaStream_t st);
+int launch_nchw32_to_act16(int dtype, const float* x, int B, int xc, int c_off, int C, int H, int W, int cs, void* out,
+                           cudaStream_t st);
+int pos_att_init_device();
+
+}  // namespace buctd

@@ -1,0 +1,518 @@
+// CUDA-core kernels of the path: everything that is HBM-bound or too small for tensor cores.
+// stem conv1, exchange/fuse sum, antialiased condition resize, CoAM channel attention, DAModule
+// combine, layout converters.  (Decode + rasteriser live in decode.cu, attention in posatt.cu.)
+#include "common.cuh"
+#include "internal.h"
+
+namespace buctd {
+
+// =================================================================================================
+// Stem conv1: 3x3 s2, 3 -> 64, folded BN + ReLU; nchw32 in, act16 out.
+// lib/models/pose_hrnet_coam.py:505-507.  One thread = one output pixel x 64 channels.
+// =================================================================================================
+constexpr int kStemTile = 16;   // 16x16 output pixels per block
+
+template <typename T>
+__global__ void __launch_bounds__(256) stem_kernel(buctd_stem_args a) {
+  __shared__ float s_w[27][64];
+  __shared__ float s_b[64];
+  __shared__ float s_in[3][2 * kStemTile + 1][2 * kStemTile + 2];
+  const int oh = a.h / 2, ow = a.w / 2;
+  const int b = blockIdx.z;
+  const int oy0 = blockIdx.y * kStemTile, ox0 = blockIdx.x * kStemTile;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 27 * 64; i += 256) {
+    int co = i / 27, t = i % 27;          // weight [co][ci*9 + ky*3 + kx]
+    s_w[t][co] = a.weight[i];
+  }
+  if (tid < 64) s_b[tid] = a.bias[tid];
+  const int iy0 = 2 * oy0 - 1, ix0 = 2 * ox0 - 1;
+  constexpr int PH = 2 * kStemTile + 1, PW = 2 * kStemTile + 1;
+  for (int i = tid; i < 3 * PH * PW; i += 256) {
+    int c = i / (PH * PW), r = i % (PH * PW);
+    int yy = r / PW, xx = r % PW;
+    int iy = iy0 + yy, ix = ix0 + xx;
+    float v = 0.f;
+    if (iy >= 0 && iy < a.h && ix >= 0 && ix < a.w)
+      v = a.x[(((long long)b * a.x_channels + c) * a.h + iy) * a.w + ix];
+    s_in[c][yy][xx] = v;
+  }
+  __syncthreads();
+  const int ty = tid / kStemTile, tx = tid % kStemTile;
+  const int oy = oy0 + ty, ox = ox0 + tx;
+  if (oy >= oh || ox >= ow) return;
+  float in[27];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) in[c * 9 + ky * 3 + kx] = s_in[c][2 * ty + ky][2 * tx + kx];
+  T* o = reinterpret_cast<T*>(a.out) + (((long long)b * (oh + 1) + oy) * (ow + 1) + ox) * a.out_cs;
+#pragma unroll 1
+  for (int c0 = 0; c0 < 64; c0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = s_b[c0 + j];
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {
+      const float4 w0 = *reinterpret_cast<const float4*>(&s_w[t][c0]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&s_w[t][c0 + 4]);
+      acc[0] = fmaf(in[t], w0.x, acc[0]); acc[1] = fmaf(in[t], w0.y, acc[1]);
+      acc[2] = fmaf(in[t], w0.z, acc[2]); acc[3] = fmaf(in[t], w0.w, acc[3]);
+      acc[4] = fmaf(in[t], w1.x, acc[4]); acc[5] = fmaf(in[t], w1.y, acc[5]);
+      acc[6] = fmaf(in[t], w1.z, acc[6]); acc[7] = fmaf(in[t], w1.w, acc[7]);
+    }
+    uint4 u;
+    u.x = T16<T>::pack2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f));
+    u.y = T16<T>::pack2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
+    u.z = T16<T>::pack2(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f));
+    u.w = T16<T>::pack2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
+    *reinterpret_cast<uint4*>(o + c0) = u;
+  }
+}
+
+int launch_stem(const buctd_stem_args& a, cudaStream_t st) {
+  BUCTD_CHECK(a.h % 2 == 0 && a.w % 2 == 0 && a.out_cs >= 64 && a.out_cs % 8 == 0, BUCTD_ERR_INVALID,
+              "stem: need even H,W and out_cs>=64 (got %dx%d, cs %d)", a.h, a.w, a.out_cs);
+  BUCTD_CHECK(a.x && a.weight && a.bias && a.out && a.x_channels >= 3, BUCTD_ERR_INVALID, "stem: bad pointers/channels");
+  dim3 grid(ceil_div(a.w / 2, kStemTile), ceil_div(a.h / 2, kStemTile), a.batch);
+  if (a.dtype == BUCTD_F16) stem_kernel<__half><<<grid, 256, 0, st>>>(a);
+  else stem_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a);
+  BUCTD_CUDA(cudaGetLastError());
+  return BUCTD_OK;
+}
+
+// =================================================================================================
+// Exchange/fuse: out = ReLU(sum_j nearest_up(term_j)), 8 channels (16 B) per thread.
+// lib/models/pose_hrnet_coam.py:257-266.
+// =================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) fuse_kernel(buctd_fuse_args a) {
+  const int cv = a.c / 8;
+  const int Hp = a.h + 1, Wp = a.w + 1;
+  const long long total = (long long)a.batch * Hp * Wp * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    const long long r = i / cv;
+    const int x = (int)(r % Wp);
+    const long long ry = r / Wp;
+    const int y = (int)(ry % Hp);
+    const int b = (int)(ry / Hp);
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (x < a.w && y < a.h) {
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j >= a.nterms) break;
+        const int sh = a.term_shift[j];
+        const int sw = (a.w >> sh) + 1, shh = (a.h >> sh) + 1;
+        const long long sr = ((long long)b * shh + (y >> sh)) * sw + (x >> sh);
+        const uint4 t = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.term[j]) + sr * a.term_cs[j] + c8 * 8);
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float2 f = T16<T>::unpack2(w[q]);
+          acc[2 * q] += f.x;
+          acc[2 * q + 1] += f.y;
+        }
+      }
+      if (a.relu) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = fmaxf(acc[q], 0.f);
+      }
+      u.x = T16<T>::pack2(acc[0], acc[1]); u.y = T16<T>::pack2(acc[2], acc[3]);
+      u.z = T16<T>::pack2(acc[4], acc[5]); u.w = T16<T>::pack2(acc[6], acc[7]);
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.out) + r * a.out_cs + c8 * 8) = u;
+  }
+}
+
+int launch_fuse(const buctd_fuse_args& a, cudaStream_t st) {
+  BUCTD_CHECK(a.nterms >= 1 && a.nterms <= 4, BUCTD_ERR_INVALID, "fuse: nterms %d out of range", a.nterms);
+  BUCTD_CHECK(a.c % 8 == 0 && a.out_cs % 8 == 0, BUCTD_ERR_INVALID, "fuse: channels must be a multiple of 8");
+  for (int j = 0; j < a.nterms; ++j) {
+    BUCTD_CHECK(a.term[j] != nullptr && a.term_cs[j] % 8 == 0, BUCTD_ERR_INVALID, "fuse: bad term %d", j);
+    BUCTD_CHECK((a.h % (1 << a.term_shift[j])) == 0 && (a.w % (1 << a.term_shift[j])) == 0, BUCTD_ERR_INVALID,
+                "fuse: %dx%d not divisible by 2^%d", a.h, a.w, a.term_shift[j]);
+  }
+  const long long total = (long long)a.batch * (a.h + 1) * (a.w + 1) * (a.c / 8);
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  if (a.dtype == BUCTD_F16) fuse_kernel<__half><<<blocks, 256, 0, st>>>(a);
+  else fuse_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(a);
+  BUCTD_CUDA(cudaGetLastError());
+  return BUCTD_OK;
+}
+
+// =================================================================================================
+// Condition resize (antialiased bilinear = triangle filter of support `scale`), nchw32 -> act16.
+// TF.resize(cond_hm, (H_i, W_i)), lib/models/pose_hrnet_coam.py:755; closed form SURVEY.md App. B:
+// centre = scale*(o+0.5); taps j in [max(0,int(centre-scale+0.5)), min(in,int(centre+scale+0.5)));
+// weight max(0, 1-|j-centre+0.5|/scale), normalised.  antialias=0: support 1 (2-tap bilinear).
+// Horizontal pass first, then vertical, both in fp32 (ATen's separable order).
+// =================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(128) resize_kernel(buctd_resize_args a) {
+  // one block = one output row (b, c, oy); thread = ox.  Row weights staged in shared memory.
+  __shared__ float s_wy[64];
+  __shared__ int s_ylo, s_yn;
+  const int oy = blockIdx.x, c = blockIdx.y, b = blockIdx.z;
+  const float sy = (float)a.h / a.oh, sx = (float)a.w / a.ow;
+  const float supy = (a.antialias && sy > 1.f) ? sy : 1.f, supx = (a.antialias && sx > 1.f) ? sx : 1.f;
+  const float invy = (a.antialias && sy > 1.f) ? 1.f / sy : 1.f, invx = (a.antialias && sx > 1.f) ? 1.f / sx : 1.f;
+  if (threadIdx.x == 0) {
+    const float center = sy * (oy + 0.5f);
+    int lo = max(0, (int)(center - supy + 0.5f)), hi = min(a.h, (int)(center + supy + 0.5f));
+    float tot = 0.f;
+    for (int j = lo; j < hi; ++j) {
+      float w = fmaxf(0.f, 1.f - fabsf((j - center + 0.5f) * invy));
+      s_wy[j - lo] = w;
+      tot += w;
+    }
+    for (int j = lo; j < hi; ++j) s_wy[j - lo] /= tot;
+    s_ylo = lo; s_yn = hi - lo;
+  }
+  __syncthreads();
+  const float* src = a.x + (((long long)b * a.x_channels + a.c_off + c) * a.h) * a.w;
+  for (int ox = threadIdx.x; ox < a.ow; ox += blockDim.x) {
+    const float center = sx * (ox + 0.5f);
+    const int lo = max(0, (int)(center - supx + 0.5f)), hi = min(a.w, (int)(center + supx + 0.5f));
+    float wx[64];
+    float tot = 0.f;
+    const int n = hi - lo;
+#pragma unroll 1
+    for (int j = 0; j < n; ++j) {
+      float w = fmaxf(0.f, 1.f - fabsf((lo + j - center + 0.5f) * invx));
+      wx[j] = w;
+      tot += w;
+    }
+    const float rt = 1.f / tot;
+    float acc = 0.f;
+    for (int iy = 0; iy < s_yn; ++iy) {
+      const float* row = src + (long long)(s_ylo + iy) * a.w + lo;
+      float h = 0.f;
+#pragma unroll 1
+      for (int j = 0; j < n; ++j) h = fmaf(wx[j] * rt, row[j], h);
+      acc = fmaf(s_wy[iy], h, acc);
+    }
+    T* o = reinterpret_cast<T*>(a.out) + (((long long)b * (a.oh + 1) + oy) * (a.ow + 1) + ox) * a.out_cs + c;
+    *o = T16<T>::from_f(acc);
+  }
+}
+
+int launch_resize(const buctd_resize_args& a, cudaStream_t st) {
+  BUCTD_CHECK(a.cc > 0 && a.cc <= a.out_cs, BUCTD_ERR_INVALID, "resize: cc %d vs out_cs %d", a.cc, a.out_cs);
+  const float sy = (float)a.h / a.oh, sx = (float)a.w / a.ow;
+  BUCTD_CHECK(2 * sy + 2 <= 64 && 2 * sx + 2 <= 64, BUCTD_ERR_INVALID, "resize: scale %.2f x %.2f too large (max 31)", sy, sx);
+  dim3 grid(a.oh, a.cc, a.batch);
+  if (a.dtype == BUCTD_F16) resize_kernel<__half><<<grid, 128, 0, st>>>(a);
+  else resize_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(a);
+  BUCTD_CUDA(cudaGetLastError());
+  return BUCTD_OK;
+}
+
+// =================================================================================================
+// CoAM channel attention (SimplifiedScaledDotProductAttention, h = 1):
+//   S[c1][c2] = sum_p yc[p][c1] * y[p][c2] / sqrt(HW)   (pad rows are zero in both, so the sum runs
+//   over all (H+1)(W+1) rows), att = softmax_c2(S), out[c1][p] = sum_c2 att[c1][c2] * y[p][c2].
+// lib/models/self_attention.py:146-158; lib/models/pose_hrnet_coam.py:673-689.
+// =================================================================================================
+// S is computed in kCaTile x kCaTile output tiles per block (16x16 threads x PER x PER); kCaTile is 48
+// for the W48 family (C = 48/96/192) and 32 for W32 (C = 32/64/128).
+constexpr int kCaRows = 32;      // rows staged per step
+
+template <typename T, int kCaTile>
+__global__ void __launch_bounds__(256) chan_scores_kernel(buctd_chan_att_args a, int rows_per_chunk) {
+  constexpr int PER = kCaTile / 16;
+  __shared__ float s_q[kCaRows][kCaTile + 1];
+  __shared__ float s_k[kCaRows][kCaTile + 1];
+  const int b = blockIdx.z;
+  const int tiles = a.c / kCaTile;
+  const int t1 = blockIdx.y / tiles, t2 = blockIdx.y % tiles;
+  const long long rows = (long long)(a.h + 1) * (a.w + 1);
+  const long long r0 = (long long)blockIdx.x * rows_per_chunk;
+  const long long r1 = min(rows, r0 + rows_per_chunk);
+  const T* yc = reinterpret_cast<const T*>(a.yc) + (long long)b * rows * a.yc_cs + t1 * kCaTile;
+  const T* y = reinterpret_cast<const T*>(a.y) + (long long)b * rows * a.y_cs + t2 * kCaTile;
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  float acc[PER][PER] = {};
+  for (long long r = r0; r < r1; r += kCaRows) {
+    for (int i = threadIdx.x; i < kCaRows * kCaTile; i += 256) {
+      int rr = i / kCaTile, cc = i % kCaTile;
+      bool ok = r + rr < r1;
+      s_q[rr][cc] = ok ? T16<T>::to_f(yc[(r + rr) * a.yc_cs + cc]) : 0.f;
+      s_k[rr][cc] = ok ? T16<T>::to_f(y[(r + rr) * a.y_cs + cc]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int rr = 0; rr < kCaRows; ++rr) {
+      float q[PER], k[PER];
+#pragma unroll
+      for (int i = 0; i < PER; ++i) { q[i] = s_q[rr][ty * PER + i]; k[i] = s_k[rr][tx * PER + i]; }
+#pragma unroll
+      for (int i = 0; i < PER; ++i)
+#pragma unroll
+        for (int j = 0; j < PER; ++j) acc[i][j] = fmaf(q[i], k[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* S = a.scratch + (long long)b * a.c * a.c;
+#pragma unroll
+  for (int i = 0; i < PER; ++i)
+#pragma unroll
+    for (int j = 0; j < PER; ++j)
+      atomicAdd(&S[(long long)(t1 * kCaTile + ty * PER + i) * a.c + t2 * kCaTile + tx * PER + j], acc[i][j]);
+}
+
+__global__ void chan_softmax_kernel(float* S, int c, float scale, int nrows) {
+  // one warp per row of S
+  const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x & 31;
+  if (row >= nrows) return;
+  float* p = S + (long long)row * c;
+  float m = -INFINITY;
+  for (int i = lane; i < c; i += 32) m = fmaxf(m, p[i] * scale);
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffff, m, o));
+  float s = 0.f;
+  for (int i = lane; i < c; i += 32) s += expf(p[i] * scale - m);
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffff, s, o);
+  const float inv = 1.f / s;
+  for (int i = lane; i < c; i += 32) p[i] = expf(p[i] * scale - m) * inv;
+}
+
+constexpr int kCaPix = 64;
+template <typename T, int kCaTile>
+__global__ void __launch_bounds__(256) chan_apply_kernel(buctd_chan_att_args a) {
+  // block: 64 valid pixels x kCaTile output channels (c1 tile); dynamic smem: att[tile][C] f32, y[64][C+1] f32
+  constexpr int G = kCaTile / 4;   // channels per thread group
+  extern __shared__ float s_dyn[];
+  float* s_att = s_dyn;                         // [48][C]
+  float* s_y = s_dyn + kCaTile * a.c;           // [64][C+1]
+  const int b = blockIdx.z, t1 = blockIdx.y;
+  const int hw = a.h * a.w;
+  const int p0 = blockIdx.x * kCaPix;
+  const int cs1 = a.c + 1;
+  const float* att = a.scratch + ((long long)b * a.c + t1 * kCaTile) * a.c;
+  for (int i = threadIdx.x; i < kCaTile * a.c; i += 256) s_att[i] = att[i];
+  const T* y = reinterpret_cast<const T*>(a.y) + (long long)b * (a.h + 1) * (a.w + 1) * a.y_cs;
+  for (int i = threadIdx.x; i < kCaPix * a.c; i += 256) {
+    int pp = i / a.c, cc = i % a.c;
+    int p = p0 + pp;
+    float v = 0.f;
+    if (p < hw) {
+      int py = p / a.w, px = p % a.w;
+      v = T16<T>::to_f(y[((long long)py * (a.w + 1) + px) * a.y_cs + cc]);
+    }
+    s_y[pp * cs1 + cc] = v;
+  }
+  __syncthreads();
+  const int pp = threadIdx.x % kCaPix, g = threadIdx.x / kCaPix;   // 4 groups x G channels
+  float acc[G] = {};
+  for (int c2 = 0; c2 < a.c; ++c2) {
+    const float yv = s_y[pp * cs1 + c2];
+#pragma unroll
+    for (int i = 0; i < G; ++i) acc[i] = fmaf(s_att[(g * G + i) * a.c + c2], yv, acc[i]);
+  }
+  const int p = p0 + pp;
+  if (p < hw) {
+    T* o = reinterpret_cast<T*>(a.out) + ((long long)b * a.c + t1 * kCaTile + g * G) * hw + p;
+#pragma unroll
+    for (int i = 0; i < G; ++i) o[(long long)i * hw] = T16<T>::from_f(acc[i]);
+  }
+}
+
+template <typename T, int TILE>
+static int chan_att_run(const buctd_chan_att_args& a, cudaStream_t st) {
+  const long long rows = (long long)(a.h + 1) * (a.w + 1);
+  const int tiles = a.c / TILE;
+  const int chunk = 512;
+  dim3 g1((unsigned)((rows + chunk - 1) / chunk), tiles * tiles, a.batch);
+  const size_t smem = sizeof(float) * ((size_t)TILE * a.c + (size_t)kCaPix * (a.c + 1));
+  dim3 g3(ceil_div(a.h * a.w, kCaPix), tiles, a.batch);
+  const float scale = 1.f / sqrtf((float)(a.h * a.w));
+  chan_scores_kernel<T, TILE><<<g1, 256, 0, st>>>(a, chunk);
+  chan_softmax_kernel<<<ceil_div(a.batch * a.c, 8), 256, 0, st>>>(a.scratch, a.c, scale, a.batch * a.c);
+  BUCTD_CUDA(cudaFuncSetAttribute(chan_apply_kernel<T, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  chan_apply_kernel<T, TILE><<<g3, 256, smem, st>>>(a);
+  BUCTD_CUDA(cudaGetLastError());
+  return BUCTD_OK;
+}
+
+int launch_chan_att(const buctd_chan_att_args& a, cudaStream_t st, int* nlaunch) {
+  BUCTD_CHECK(a.c % 48 == 0 || a.c % 32 == 0, BUCTD_ERR_INVALID, "chan_att: C=%d must be a multiple of 48 or 32", a.c);
+  BUCTD_CHECK(a.y && a.yc && a.scratch && a.out, BUCTD_ERR_INVALID, "chan_att: null pointer");
+  BUCTD_CHECK(a.c <= 256, BUCTD_ERR_INVALID, "chan_att: C=%d too large for the shared-memory tile", a.c);
+  BUCTD_CUDA(cudaMemsetAsync(a.scratch, 0, sizeof(float) * (size_t)a.batch * a.c * a.c, st));
+  if (nlaunch) *nlaunch = 3;
+  const bool t48 = a.c % 48 == 0;
+  if (a.dtype == BUCTD_F16) return t48 ? chan_att_run<__half, 48>(a, st) : chan_att_run<__half, 32>(a, st);
+  return t48 ? chan_att_run<__nv_bfloat16, 48>(a, st) : chan_att_run<__nv_bfloat16, 32>(a, st);
+}
+
+// =================================================================================================
+// DAModule combine: out = x + (p_out + c_out)   (channel_only: out = x * c_out)
+// lib/models/pose_hrnet_coam.py:716-724.  c_out is planar [B][C][HW]: 32x32 smem transpose.
+// =================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) da_combine_kernel(buctd_da_combine_args a) {
+  __shared__ float s_c[32][33];
+  const int b = blockIdx.z;
+  const int hw = a.h * a.w;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;   // 32 x 8
+  const T* cout = reinterpret_cast<const T*>(a.c_out) + (long long)b * a.c * hw;
+  for (int cc = ty; cc < 32; cc += 8) {
+    int c = c0 + cc, p = p0 + tx;
+    s_c[cc][tx] = (c < a.c && p < hw) ? T16<T>::to_f(cout[(long long)c * hw + p]) : 0.f;
+  }
+  __syncthreads();
+  for (int pp = ty; pp < 32; pp += 8) {
+    const int p = p0 + pp, c = c0 + tx;
+    if (p >= hw || c >= a.c) continue;
+    const int py = p / a.w, px = p % a.w;
+    const long long r = ((long long)b * (a.h + 1) + py) * (a.w + 1) + px;
+    const float xv = T16<T>::to_f(reinterpret_cast<const T*>(a.x)[r * a.x_cs + c]);
+    float v;
+    if (a.channel_only) v = xv * s_c[tx][pp];
+    else v = xv + (T16<T>::to_f(reinterpret_cast<const T*>(a.p_out)[r * a.p_cs + c]) + s_c[tx][pp]);
+    reinterpret_cast<T*>(a.out)[r * a.out_cs + c] = T16<T>::from_f(v);
+  }
+}
+
+int launch_da_combine(const buctd_da_combine_args& a, cudaStream_t st) {
+  BUCTD_CHECK(a.x && a.c_out && a.out && (a.channel_only || a.p_out), BUCTD_ERR_INVALID, "da_combine: null pointer");
+  dim3 grid(ceil_div(a.h * a.w, 32), ceil_div(a.c, 32), a.batch);
+  if (a.dtype == BUCTD_F16) da_combine_kernel<__half><<<grid, 256, 0, st>>>(a);
+  else da_combine_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a);
+  BUCTD_CUDA(cudaGetLastError());
+  return BUCTD_OK;
+}
+
+// =================================================================================================
+// Layout converters (tests, and the nchw32 -> act16 entry of tensors produced outside the plan)
+// =================================================================================================
+template <typename T>
+__global__ void act16_to_nchw32_kernel(const T* act, int B, int H, int W, int C, int cs, float* out) {
+  const long long total = (long long)B * C * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int x = (int)(i % W);
+    long long t = i / W;
+    int y = (int)(t % H); t /= H;
+    int c = (int)(t % C);
+    int b = (int)(t / C);
+    out[i] = T16<T>::to_f(act[(((long long)b * (H + 1) + y) * (W + 1) + x) * cs + c]);
+  }
+}
+template <typename T>
+__global__ void nchw32_to_act16_kernel(const float* x, int B, int xc, int c_off, int C, int H, int W, int cs, T* out) {
+  const long long total = (long long)B * (H + 1) * (W + 1) * cs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % cs);
+    long long t = i / cs;
+    int xx = (int)(t % (W + 1)); t /= (W + 1);
+    int y = (int)(t % (H + 1));
+    int b = (int)(t / (H + 1));
+    float v = 0.f;
+    if (c < C && xx < W && y < H) v = x[(((long long)b * xc + c_off + c) * H + y) * W + xx];
+    out[i] = T16<T>::from_f(v);
+  }
+}
+
+int launch_act16_to_nchw32(int dtype, const void* act, int B, int H, int W, int C, int cs, float* out, cudaStream_t st) {
+  BUCTD_CHECK(act && out, BUCTD_ERR_INVALID, "act16_to_nchw32: null pointer");
+  const long long total = (long long)B * C * H * W;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  if (dtype == BUCTD_F16) act16_to_nchw32_kernel<<<blocks, 256, 0, st>>>((const __half*)act, B, H, W, C, cs, out);
+  else act16_to_nchw32_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)act, B, H, W, C, cs, out);
+  BUCTD_CUDA(cudaGetLastError());
+  return BUCTD_OK;
+}
+int launch_nchw32_to_act16(int dtype, const float* x, int B, int xc, int c_off, int C, int H, int W, int cs, void* out,
+                           cudaStream_t st) {
+  BUCTD_CHECK(x && out && C <= cs, BUCTD_ERR_INVALID, "nchw32_to_act16: bad args");
+  const long long total = (long long)B * (H + 1) * (W + 1) * cs;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  if (dtype == BUCTD_F16) nchw32_to_act16_kernel<<<blocks, 256, 0, st>>>(x, B, xc, c_off, C, H, W, cs, (__half*)out);
+  else nchw32_to_act16_kernel<<<blocks, 256, 0, st>>>(x, B, xc, c_off, C, H, W, cs, (__nv_bfloat16*)out);
+  BUCTD_CUDA(cudaGetLastError());
+  return BUCTD_OK;
+}
+
+}  // namespace buctd
+
+namespace buctd {
+// =================================================================================================
+// preNet (lib/models/pose_hrnet.py:431-442, 452-458): composed 9x9 (rgb) + 7x7 (cond) 3->3 convs.
+// Block = 32x8 output pixels; rgb/cond halo tiles in shared memory; the (warp-uniform almost
+// everywhere) weight variant is read through the read-only cache.
+// =================================================================================================
+__device__ __forceinline__ int prenet_variant(int p, int n) {
+  const int lo = 3 - p;             // rows cut at the top/left
+  if (lo > 0) return lo;
+  const int hi = p + 3 - (n - 1);   // rows cut at the bottom/right
+  if (hi > 0) return 3 + hi;
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) prenet_kernel(buctd_prenet_args a) {
+  constexpr int TW = 32, TH = 8;
+  __shared__ float s_rgb[3][TH + 8][TW + 8];
+  __shared__ float s_cond[3][TH + 6][TW + 6 + 2];
+  const int b = blockIdx.z;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  const float* xb = a.x + (long long)b * a.x_channels * a.h * a.w;
+  for (int i = threadIdx.x; i < 3 * (TH + 8) * (TW + 8); i += 256) {
+    const int c = i / ((TH + 8) * (TW + 8)), r = i % ((TH + 8) * (TW + 8));
+    const int yy = r / (TW + 8), xx = r % (TW + 8);
+    const int gy = y0 + yy - 4, gx = x0 + xx - 4;
+    s_rgb[c][yy][xx] = (gy >= 0 && gy < a.h && gx >= 0 && gx < a.w) ? xb[((long long)c * a.h + gy) * a.w + gx] : 0.f;
+  }
+  for (int i = threadIdx.x; i < 3 * (TH + 6) * (TW + 6); i += 256) {
+    const int c = i / ((TH + 6) * (TW + 6)), r = i % ((TH + 6) * (TW + 6));
+    const int yy = r / (TW + 6), xx = r % (TW + 6);
+    const int gy = y0 + yy - 3, gx = x0 + xx - 3;
+    s_cond[c][yy][xx] = (gy >= 0 && gy < a.h && gx >= 0 && gx < a.w) ? xb[((long long)(3 + c) * a.h + gy) * a.w + gx] : 0.f;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x % TW, ty = threadIdx.x / TW;
+  const int x = x0 + tx, y = y0 + ty;
+  if (x >= a.w || y >= a.h) return;
+  const int v = prenet_variant(y, a.h) * 7 + prenet_variant(x, a.w);
+  const float* we = a.w_eff + (long long)v * 3 * 3 * 81;
+  float acc[3];
+#pragma unroll
+  for (int co = 0; co < 3; ++co) acc[co] = __ldg(a.b_eff + v * 3 + co);
+  for (int ci = 0; ci < 3; ++ci)
+    for (int ky = 0; ky < 9; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 9; ++kx) {
+        const float in = s_rgb[ci][ty + ky][tx + kx];
+        const int o = ci * 81 + ky * 9 + kx;
+        acc[0] = fmaf(in, __ldg(we + o), acc[0]);
+        acc[1] = fmaf(in, __ldg(we + 243 + o), acc[1]);
+        acc[2] = fmaf(in, __ldg(we + 486 + o), acc[2]);
+      }
+  for (int ci = 0; ci < 3; ++ci)
+    for (int ky = 0; ky < 7; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) {
+        const float in = s_cond[ci][ty + ky][tx + kx];
+        const int o = ci * 49 + ky * 7 + kx;
+        acc[0] = fmaf(in, __ldg(a.wc + o), acc[0]);
+        acc[1] = fmaf(in, __ldg(a.wc + 147 + o), acc[1]);
+        acc[2] = fmaf(in, __ldg(a.wc + 294 + o), acc[2]);
+      }
+#pragma unroll
+  for (int co = 0; co < 3; ++co) a.out[(((long long)b * 3 + co) * a.h + y) * a.w + x] = acc[co];
+}
+
+int launch_prenet(const buctd_prenet_args& a, cudaStream_t st) {
+  BUCTD_CHECK(a.x && a.w_eff && a.b_eff && a.wc && a.out, BUCTD_ERR_INVALID, "prenet: null pointer");
+  BUCTD_CHECK(a.x_channels >= 6 && a.h >= 7 && a.w >= 7, BUCTD_ERR_INVALID, "prenet: need >= 6 input channels and H,W >= 7");
+  if (a.batch == 0) return BUCTD_OK;
+  prenet_kernel<<<dim3(ceil_div(a.w, 32), ceil_div(a.h, 8), a.batch), 256, 0, st>>>(a);
+  BUCTD_CUDA(cudaGetLastError());
+  return BUCTD_OK;
+}
+}  // namespace buctd

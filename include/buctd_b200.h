@@ -1,0 +1,234 @@
+/* buctd_b200 -- C ABI of the B200 (sm_100a) implementation of the BUCTD conditional top-down
+ * pose path.  Plain pointers and sizes only; no torch / C++ types.  Every entry point returns
+ * 0 on success or a negative BUCTD_ERR_* code; buctd_last_error() returns the message of the
+ * last failure on the calling thread.  All device work is enqueued on the caller's stream
+ * (stream-ordered, no implicit device synchronisation, no hidden allocation): the caller owns
+ * every buffer, the library never frees caller memory.  Handles are per device; calls on
+ * different handles may run concurrently from different host threads (the reference's
+ * torch.nn.DataParallel drives one host thread per GPU, tools/test.py:134).
+ *
+ * The reference (amathislab/BUCTD) is pure Python on top of cuDNN/cuBLAS/ATen/NumPy, so there
+ * is no existing FFI to mirror; each entry point below names the reference function it replaces
+ * (paths relative to the reference root), and INTEGRATION.md shows the ctypes stubs a reference
+ * maintainer would add.
+ *
+ * Data layouts
+ *   "act16"  : padded NHWC 16-bit activation  [B][H+1][W+1][Cs]  (fp16 or bf16, see buctd_dtype);
+ *              row y==H and column x==W are zero ("shared pad": a 3x3 tap that leaves the image
+ *              lands on a zero).  Flat row index r = (b*(H+1) + y)*(W+1) + x; Cs = channel stride
+ *              in elements (multiple of 8).
+ *   "planar" : [B][C][H*W] 16-bit, unpadded (the layout of the CoAM channel attention and of its
+ *              HW x HW projection).
+ *   "nchw32" : [B][C][H][W] float32, unpadded: the reference's own tensors (model input, heat-maps).
+ */
+#ifndef BUCTD_B200_H_
+#define BUCTD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BUCTD_ABI_VERSION 1
+
+#define BUCTD_OK 0
+#define BUCTD_ERR_INVALID (-1)   /* bad argument / unsupported shape */
+#define BUCTD_ERR_CUDA (-2)      /* a CUDA runtime / driver call failed */
+#define BUCTD_ERR_NO_DEVICE (-3) /* no sm_100 device, or driver entry point missing */
+
+typedef enum { BUCTD_F16 = 0, BUCTD_BF16 = 1 } buctd_dtype;
+
+typedef struct buctd_ctx buctd_ctx;   /* per-device handle */
+typedef struct buctd_plan buctd_plan; /* recorded sequence of launches with pre-encoded tensor maps */
+typedef void* buctd_stream;           /* cudaStream_t */
+
+int buctd_abi_version(void);
+const char* buctd_last_error(void);
+int buctd_create(int device, buctd_ctx** out);
+int buctd_destroy(buctd_ctx* ctx);
+/* number of kernels launched through this handle since creation (bench.py's gpu_launches) */
+long long buctd_launch_count(const buctd_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------
+ * Tap-GEMM: every dense contraction of the path on the tcgen05 tensor cores.
+ *   out[m, n] = act( sum_t sum_k A[m (+) tap t, k] * Wt[t][n][k] + bias[n] + residual[m, n] )
+ * mode FLAT : A is an act16 tensor seen as a 2-D matrix [rows, Cs]; tap t of a 3x3 stride-1
+ *             convolution is the same matrix shifted by dy*(W+1)+dx rows (zero pads make the shift
+ *             exact), ntaps = 9; ntaps = 1 is a 1x1 convolution / nn.Linear.
+ * mode PATCH: stride-2 3x3 convolution; M-tile = th x tw output pixels of one image, A tiles are
+ *             loaded with a strided 4-D TMA box.
+ * Replaces nn.Conv2d + nn.BatchNorm2d(eval) + ReLU (+ residual) in
+ *   lib/models/pose_hrnet_coam.py:44-60 (BasicBlock), :81-101 (Bottleneck), :200-242 (fuse convs),
+ *   :405-432 (transitions), :565 (final_layer), :635-641,666-670 (CoAM convs) and nn.Linear in
+ *   lib/models/self_attention.py:74-76,87,159.
+ * Weights are packed by the caller: BN folded in fp32, cast to 16 bit, layout [ntaps][n_alloc][k_cs]
+ * (K contiguous); bias is the folded BN shift / conv bias in fp32.
+ * ------------------------------------------------------------------------------------------ */
+enum { BUCTD_TG_FLAT = 0, BUCTD_TG_PATCH = 1 };
+enum { BUCTD_OUT_ACT16 = 0,   /* act16 with pad rows/cols written as zero */
+       BUCTD_OUT_ROWS16 = 1,  /* plain [rows][out_cs] 16-bit, no pad handling (linear layers) */
+       BUCTD_OUT_NCHW32 = 2   /* float32 [B][N][H][W] unpadded (the returned heat-maps) */ };
+
+typedef struct {
+  int32_t dtype;        /* buctd_dtype of A, W, residual and 16-bit outputs */
+  int32_t mode;         /* BUCTD_TG_FLAT | BUCTD_TG_PATCH */
+  int32_t ntaps;        /* 1 or 9 */
+  int32_t stride;       /* PATCH: 2 (1 allowed); FLAT: 1 */
+  int32_t batch;        /* geometry of the OUTPUT image grid (B, H, W); for ROWS16 only m_rows is used */
+  int32_t out_h, out_w;
+  int32_t in_h, in_w;   /* PATCH: input image size (in_h = stride*out_h) */
+  int64_t m_rows;       /* FLAT: number of A/out rows (act16: B*(H+1)*(W+1)) */
+  int32_t k;            /* valid input channels (cin) */
+  int32_t a_cs;         /* A channel stride (elements) */
+  int32_t n;            /* valid output channels (cout) */
+  int32_t n_alloc;      /* rows per tap in W (>= n, multiple of 16) */
+  int32_t w_cs;         /* W row stride in elements (>= k, multiple of 8) */
+  int32_t out_cs;       /* out channel stride (ACT16/ROWS16) */
+  int32_t res_cs;       /* residual channel stride */
+  int32_t relu;
+  int32_t out_mode;
+  int32_t reserved;
+  const void* a;
+  const void* w;
+  const float* bias;    /* [n] or NULL */
+  const void* residual; /* same row indexing as out, or NULL */
+  void* out;
+} buctd_tapgemm_args;
+int buctd_tapgemm(buctd_ctx* ctx, const buctd_tapgemm_args* args, buctd_stream stream);
+
+/* Stem conv1: 3x3 stride 2, 3 -> 64, BN folded, ReLU, reading the nchw32 model input directly
+ * (channels [0,3) of x[B][x_channels][H][W]) and writing act16 [B][H/2+1][W/2+1][64].
+ * Replaces conv1/bn1/relu, lib/models/pose_hrnet_coam.py:505-507.  w: float32 [64][27] (ci,ky,kx). */
+typedef struct {
+  int32_t dtype, batch, x_channels, h, w, out_cs;
+  const float* x; const float* weight; const float* bias; void* out;
+} buctd_stem_args;
+int buctd_stem_conv(buctd_ctx* ctx, const buctd_stem_args* args, buctd_stream stream);
+
+/* Exchange/fuse sum: out = ReLU(sum_j term_j), term_j an act16 tensor at the output resolution or
+ * 2^shift times coarser (nearest up-sampling).  Replaces the sum + nn.Upsample + ReLU of
+ * HighResolutionModule.forward, lib/models/pose_hrnet_coam.py:257-266 (the 1x1 / 3x3 convs of
+ * the terms are tap-GEMMs). */
+typedef struct {
+  int32_t dtype, batch, h, w, c, out_cs, nterms, relu;
+  const void* term[4]; int32_t term_cs[4]; int32_t term_shift[4];
+  void* out;
+} buctd_fuse_args;
+int buctd_hr_fuse(buctd_ctx* ctx, const buctd_fuse_args* args, buctd_stream stream);
+
+/* Condition resize: antialiased bilinear (triangle filter, support = scale) from channels
+ * [c_off, c_off+cc) of the nchw32 model input to act16 [B][oh+1][ow+1][out_cs] (channels >= cc
+ * zero).  Replaces TF.resize(cond_hm, (H_i, W_i)), lib/models/pose_hrnet_coam.py:755 as
+ * torchvision >= 0.17 computes it (antialias=True); antialias=0 gives the 2-tap legacy form. */
+typedef struct {
+  int32_t dtype, batch, x_channels, c_off, cc, h, w, oh, ow, out_cs, antialias, reserved;
+  const float* x; void* out;
+} buctd_resize_args;
+int buctd_cond_resize(buctd_ctx* ctx, const buctd_resize_args* args, buctd_stream stream);
+
+/* CoAM channel attention core: att = softmax_c2( yc^T y / sqrt(HW) ) [C x C] per crop, then
+ * out[c1][p] = sum_c2 att[c1][c2] y[p][c2], written planar [B][C][HW] (the A operand of the
+ * HW x HW fc_o tap-GEMM).  y, yc: act16 [B][H+1][W+1][cs].  scratch: float32 [B][C][C].
+ * Replaces SimplifiedScaledDotProductAttention.forward up to fc_o,
+ * lib/models/self_attention.py:146-158 as called from ChannelAttentionModule.forward,
+ * lib/models/pose_hrnet_coam.py:673-689. */
+typedef struct {
+  int32_t dtype, batch, h, w, c, y_cs, yc_cs, reserved;
+  const void* y; const void* yc; float* scratch; void* out;
+} buctd_chan_att_args;
+int buctd_coam_channel_att(buctd_ctx* ctx, const buctd_chan_att_args* args, buctd_stream stream);
+
+/* CoAM position attention core (flash style, the [HW x HW] score matrix never leaves the SM):
+ * o[t] = softmax_s( q[t].k[s] / sqrt(C) ) v[s] over the H*W valid pixels of each crop.
+ * q, k, v, o: act16 [B][H+1][W+1][cs] with C valid channels (q/k/v may be slices of one tensor).
+ * Replaces ScaledDotProductAttention.forward between the projections,
+ * lib/models/self_attention.py:78-86 (eval mode: dropout is the identity). */
+typedef struct {
+  int32_t dtype, batch, h, w, c, q_cs, k_cs, v_cs, o_cs, reserved;
+  const void* q; const void* k; const void* v; void* o;
+} buctd_pos_att_args;
+int buctd_coam_position_att(buctd_ctx* ctx, const buctd_pos_att_args* args, buctd_stream stream);
+
+/* DAModule output: out = x + (p_out + c_out), p_out act16, c_out planar [B][C][HW]; with
+ * channel_only: out = x * c_out.  Replaces DAModule.forward, lib/models/pose_hrnet_coam.py:716-724. */
+typedef struct {
+  int32_t dtype, batch, h, w, c, x_cs, p_cs, out_cs, channel_only, reserved;
+  const void* x; const void* p_out; const void* c_out; void* out;
+} buctd_da_combine_args;
+int buctd_da_combine(buctd_ctx* ctx, const buctd_da_combine_args* args, buctd_stream stream);
+
+/* preNet: x' = BN(conv7x7(BN(conv3x3(rgb)))) + BN(conv7x7(cond)) at full resolution; nchw32 in
+ * (rgb = channels [0,3), cond = channels [3,6) of x), nchw32 3-channel out.  There is no
+ * non-linearity between the 3x3 and the 7x7 convolution, so the caller composes them (with both
+ * BatchNorms folded) into one 9x9 3->3 kernel.  The 64-channel intermediate is zero-padded by the
+ * 7x7 convolution, so near the border the composition only includes the taps that fall inside the
+ * image: w_eff holds the 7x7 = 49 variants [vy*7+vx][co][ci][9*9], vy/vx = 0 (interior), 1..3 (that
+ * many rows/cols cut at the top/left), 4..6 (1..3 cut at the bottom/right); b_eff [49][3] is the
+ * matching constant (b2 + bc + sum of w2*b1 over the included taps).  wc [3][3][7*7] is the
+ * BN-folded cond kernel.  Replaces rgb_preNet / cond_preNet, lib/models/pose_hrnet.py:431-442,452-458. */
+typedef struct {
+  int32_t batch, x_channels, h, w;
+  const float* x; const float* w_eff; const float* b_eff; const float* wc; float* out;
+} buctd_prenet_args;
+int buctd_prenet(buctd_ctx* ctx, const buctd_prenet_args* args, buctd_stream stream);
+
+/* Heat-map decode: per (b,k) flat argmax (first maximum), max value, quarter-pixel offset from
+ * the sign of the neighbour differences (strict 1<px<W-1, 1<py<H-1), zeroing when maxval<=0, and
+ * the inverse crop transform x_img = cx + (x - W/2) * 200*scale[0]/W (likewise y with H/2).
+ * heatmaps nchw32 [B][K][H][W]; center, scale float32 [B][2] (may be NULL: then preds = heat-map
+ * coordinates); outputs preds [B][K][2], maxvals [B][K], optional coords [B][K][2] (the
+ * get_max_preds result before the offset) and idx [B][K] (int32 flat argmax).
+ * Replaces get_max_preds / get_final_preds, lib/core/inference.py:19-87 and transform_preds,
+ * lib/utils/transforms.py:78-118. */
+typedef struct {
+  int32_t batch, k, h, w, post_process, reserved;
+  const float* heatmaps; const float* center; const float* scale;
+  float* preds; float* maxvals; float* coords; int32_t* idx;
+} buctd_decode_args;
+int buctd_decode_heatmaps(buctd_ctx* ctx, const buctd_decode_args* args, buctd_stream stream);
+
+/* Condition rasteriser: keypoint proposals -> blurred impulse maps written into channels
+ * [c_off, c_off+Cc) of an nchw32 tensor out[B][out_channels][H][W].
+ *  mode 0 stacked: Cc = K, one channel per keypoint, each scaled to peak 255;
+ *  mode 1 coloured: Cc = 3, impulses carry colors[k][3], later keypoints overwrite, one global scale;
+ *  mode 2 plain:   Cc = 3, one map of all keypoints, repeated, truncated to integer values.
+ * kpts float32 [B][K][kstride] (x, y first; truncated toward zero like .astype(int)); a keypoint
+ * is drawn only if 0 < x < W and 0 < y < H, at pixel (y-1, x-1); 15x15 Gaussian, sigma 2.6,
+ * BORDER_REFLECT_101.  Replaces get_stacked_condition / get_condition_image_colored /
+ * get_condition_image + generate_heatmap, lib/dataset/JointsDataset.py:457-543. */
+typedef struct {
+  int32_t batch, k, kstride, h, w, mode, out_channels, c_off;
+  const float* kpts; const float* colors; /* [K][3] for mode 1, else NULL */
+  float* out;
+  void* scratch;        /* modes 1/2: >= 8*B bytes of device scratch (per-crop maximum); mode 0: unused */
+} buctd_raster_args;
+int buctd_rasterize_condition(buctd_ctx* ctx, const buctd_raster_args* args, buctd_stream stream);
+
+/* Utility kernels used by the host mirror: zero-fill, and act16 -> nchw32 export for tests. */
+int buctd_act16_to_nchw32(buctd_ctx* ctx, int dtype, const void* act, int batch, int h, int w, int c, int cs,
+                          float* out, buctd_stream stream);
+int buctd_nchw32_to_act16(buctd_ctx* ctx, int dtype, const float* x, int batch, int x_channels, int c_off, int c,
+                          int h, int w, int cs, void* out, buctd_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Plans: the host mirror records one forward pass (a few hundred launches) once per (config,
+ * batch) and replays it with a single call; tensor maps are encoded at record time.
+ * kind = one of BUCTD_OP_*, args = the matching struct above (copied).
+ * ------------------------------------------------------------------------------------------ */
+enum { BUCTD_OP_TAPGEMM = 1, BUCTD_OP_STEM = 2, BUCTD_OP_FUSE = 3, BUCTD_OP_RESIZE = 4, BUCTD_OP_CHAN_ATT = 5,
+       BUCTD_OP_POS_ATT = 6, BUCTD_OP_DA_COMBINE = 7, BUCTD_OP_PRENET = 8, BUCTD_OP_DECODE = 9,
+       BUCTD_OP_RASTER = 10 };
+int buctd_plan_create(buctd_ctx* ctx, buctd_plan** out);
+int buctd_plan_destroy(buctd_plan* plan);
+int buctd_plan_add(buctd_plan* plan, int kind, const void* args, size_t args_size);
+int buctd_plan_size(const buctd_plan* plan);
+int buctd_plan_run(buctd_plan* plan, buctd_stream stream);
+/* run ops [first, last) only (stage-boundary parity tests) */
+int buctd_plan_run_range(buctd_plan* plan, int first, int last, buctd_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BUCTD_B200_H_ */

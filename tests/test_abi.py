@@ -1,0 +1,58 @@
+"""not gpu: the C-ABI library loads and exports every symbol include/buctd_b200.h declares; the ctypes
+structs match the header field for field (no compute calls: there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from buctd_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "buctd_b200.h")
+
+
+def _header():
+    with open(HEADER) as f:
+        return f.read()
+
+
+def test_header_symbols_match_binding_list():
+    declared = set(re.findall(r"^(?:int|long long|const char\*)\s+(buctd_\w+)\s*\(", _header(), re.M))
+    assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
+
+
+@pytest.mark.skipif(not os.path.exists(L.LIB_PATH), reason="library not built (run __graft_entry__.build())")
+def test_library_exports_every_symbol():
+    lib = ctypes.CDLL(L.LIB_PATH)
+    for name in L.EXPORTS:
+        assert hasattr(lib, name), name
+    assert lib.buctd_abi_version() == L.ABI_VERSION
+
+
+def test_struct_fields_match_header():
+    h = _header()
+    pairs = {"buctd_tapgemm_args": L.TapGemmArgs, "buctd_stem_args": L.StemArgs, "buctd_fuse_args": L.FuseArgs,
+             "buctd_resize_args": L.ResizeArgs, "buctd_chan_att_args": L.ChanAttArgs, "buctd_pos_att_args": L.PosAttArgs,
+             "buctd_da_combine_args": L.DaCombineArgs, "buctd_prenet_args": L.PrenetArgs, "buctd_decode_args": L.DecodeArgs,
+             "buctd_raster_args": L.RasterArgs}
+    for cname, st in pairs.items():
+        body = re.search(r"typedef struct \{([^}]*)\}\s*%s;" % cname, h).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            # "int32_t a, b, c" / "const void* term[4]" / "const float* x"
+            decl = re.sub(r"^(const\s+)?(int32_t|int64_t|float|void|double)\s*\**", "", decl)
+            for part in decl.split(","):
+                names.append(re.sub(r"\[.*\]", "", part).replace("*", "").strip())
+        assert names == [f[0] for f in st._fields_], (cname, names, [f[0] for f in st._fields_])
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(L.BuctdError, match="no CPU fallback"):
+        L.load()

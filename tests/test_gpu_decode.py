@@ -1,0 +1,107 @@
+"""-m gpu: decode + rasteriser kernels through the reference-facing Python API (which calls the C
+ABI) against the oracle and the committed reference outputs (tests/golden)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from buctd_b200 import condition, inference
+from buctd_b200.config import make_cfg
+from oracle import condition_oracle as C
+from oracle import decode_oracle as D
+from oracle import make_golden as G
+
+pytestmark = pytest.mark.gpu
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+@pytest.mark.parametrize("name", list(G.CASES) + ["decode_edge_cases"])
+def test_decode_matches_reference_golden(golden_dir, name):
+    g = _load(golden_dir, name)
+    cfg = make_cfg("plain", 32, (72, 96))
+    coords, maxvals = inference.get_max_preds(g["heatmaps"])
+    assert np.array_equal(coords, g["coords"])              # integer index work: bit exact
+    assert np.array_equal(maxvals, g["maxvals"])
+    for pp in (False, True):
+        key = "preds_pp%d" % pp if name == "decode_edge_cases" else ("preds" if pp else None)
+        if key is None:
+            continue
+        cfg.TEST.POST_PROCESS = pp
+        preds, mv = inference.get_final_preds(cfg, g["heatmaps"], g["center"], g["scale"])
+        assert np.array_equal(mv, g["maxvals"])
+        assert np.abs(preds - g[key]).max() <= 1e-4         # float64 affine stored as float32
+
+
+def test_decode_device_indices_and_offsets_vs_oracle():
+    g = np.random.default_rng(5)
+    B, K, H, W = 64, 17, 96, 72                              # BASELINE.json full size
+    hm = g.standard_normal((B, K, H, W)).astype(np.float32)
+    hm[3, 2] = hm[3, 2].round(1)                             # many exact ties
+    hm[4, :] = -np.abs(hm[4, :])                             # all negative
+    center = g.uniform(100, 200, (B, 2)).astype(np.float32)
+    scale = g.uniform(1, 2, (B, 2)).astype(np.float32)
+    t = torch.from_numpy(hm).cuda()
+    preds, maxvals, coords, idx = inference.decode_device(t, torch.from_numpy(center).cuda(), torch.from_numpy(scale).cuda(),
+                                                          post_process=True, want_coords=True)
+    oc, om = D.get_max_preds(hm)
+    op, _ = D.get_final_preds(True, hm, center, scale)
+    assert np.array_equal(idx.cpu().numpy(), hm.reshape(B, K, -1).argmax(-1).astype(np.int32))
+    assert np.array_equal(coords.cpu().numpy(), oc)
+    assert np.array_equal(maxvals.cpu().numpy(), om)
+    assert np.abs(preds.cpu().numpy() - op).max() <= 1e-4
+    # heat-map-space result (no center/scale): quarter offsets are exact in float32
+    p2, _ = inference.decode_device(t, None, None, post_process=True)
+    ident_c = np.tile(np.array([[W / 2.0, H / 2.0]], np.float32), (B, 1))
+    ident_s = np.tile(np.array([[W / 200.0, H / 200.0]], np.float32), (B, 1))
+    op2, _ = D.get_final_preds(True, hm, ident_c, ident_s)
+    assert np.abs(p2.cpu().numpy() - op2).max() <= 1e-4
+
+
+def test_decode_empty_batch_and_asserts():
+    cfg = make_cfg("plain", 32, (72, 96))
+    p, m = inference.get_final_preds(cfg, np.zeros((0, 17, 8, 6), np.float32), np.zeros((0, 2)), np.zeros((0, 2)))
+    assert p.shape == (0, 17, 2) and m.shape == (0, 17, 1)
+    with pytest.raises(AssertionError):
+        inference.get_max_preds(np.zeros((17, 8, 6), np.float32))
+    with pytest.raises(AssertionError):
+        inference.get_max_preds([[1.0]])
+
+
+@pytest.mark.parametrize("mode", ["stacked", "colored", "plain"])
+def test_rasteriser_vs_oracle(mode):
+    g = np.random.default_rng(9)
+    B, K, H, W = 3, 17, 384, 288
+    kp = np.stack([g.uniform(-10, W + 10, (B, K)), g.uniform(-10, H + 10, (B, K)), g.uniform(0, 1, (B, K))], -1).astype(np.float32)
+    kp[0, 0] = (1.2, 1.7, 1)          # -> pixel (0,0): reflect-101 corner
+    kp[0, 1] = (W - 0.5, H - 0.5, 1)  # -> last valid pixel (W-2,H-2)
+    kp[0, 2] = (0.5, 30, 1)           # x<1: skipped
+    kp[0, 3] = kp[0, 4]               # duplicate position: later keypoint overwrites
+    kp[1, :] = 0                      # no keypoint at all: all-zero image, no division by zero
+    out = condition.rasterize_condition(torch.from_numpy(kp).cuda(), H, W, mode).cpu().numpy()
+    for b in range(B):
+        if mode == "stacked":
+            ref = C.stacked_condition(kp[b], H, W)
+        elif mode == "colored":
+            ref = C.colored_condition(kp[b], H, W, C.default_colors(K))
+        else:
+            ref = C.plain_condition(kp[b], H, W)
+        ref = ref.astype(np.float32)
+        if mode == "plain":
+            # .astype(int) truncation: a value within 1e-9 of an integer may land on either side
+            bad = np.abs(out[b] - ref) > 0
+            assert bad.mean() < 1e-4 and np.abs(out[b] - ref).max() <= 1.0
+        else:
+            assert np.abs(out[b] - ref).max() <= 2e-4, (mode, b, np.abs(out[b] - ref).max())
+    assert out[1].max() == 0
+
+
+def test_rasteriser_writes_into_model_input_channels():
+    B, K, H, W = 2, 17, 128, 96
+    kp = torch.tensor(np.random.default_rng(1).uniform(5, 90, (B, K, 2)), dtype=torch.float32).cuda()
+    x = torch.full((B, 3 + K, H, W), -1.0, device="cuda")
+    condition.rasterize_condition(kp, H, W, "stacked", out=x, c_off=3)
+    assert (x[:, :3] == -1).all() and x[:, 3:].max() > 254.9 and x[:, 3:].min() >= 0

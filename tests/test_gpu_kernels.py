@@ -1,0 +1,260 @@
+"""-m gpu: every CUDA kernel of the path against a plain torch fp32 reference of the same op on
+the same 16-bit-rounded operands (the oracle for whole-network parity is in test_gpu_model.py).
+All calls go through the C ABI (ctypes -> libbuctd_b200.so)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from buctd_b200 import _lib as L
+
+from gpu_utils import (TDT, assert_close, ctx, from_act16, pack_w, pads_are_zero, q16, rup, stream, tapgemm, to_act16)
+
+pytestmark = pytest.mark.gpu
+DTS = [L.F16, L.BF16]
+TOL = {L.F16: 3e-3, L.BF16: 2e-2}      # output rounding of the 16-bit type (2^-11 / 2^-8) + fp32 accumulation order
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("cin,cout,h,w,relu,res", [
+    (48, 48, 24, 18, True, True), (96, 96, 12, 9, True, False), (192, 192, 12, 9, False, True),
+    (384, 384, 12, 9, True, True), (256, 48, 24, 18, True, False), (64, 64, 10, 7, True, False),
+    (17, 48, 24, 18, False, False), (17, 17, 12, 9, False, False), (3, 96, 8, 6, False, False),
+])
+def test_tapgemm_conv3x3_flat(dt, cin, cout, h, w, relu, res):
+    B = 3
+    x = q16(_rand(B, cin, h, w, seed=1), dt)
+    wt = q16(_rand(cout, cin, 3, 3, seed=2, scale=1.0 / math.sqrt(9 * cin)), dt)
+    bias = _rand(cout, seed=3, scale=0.1)
+    r = q16(_rand(B, cout, h, w, seed=4), dt) if res else None
+    a16 = to_act16(x, dt, cs=rup(cin, 16) if cin % 8 else None)
+    out = torch.full((B, h + 1, w + 1, rup(cout, 16)), 7.0, dtype=TDT[dt], device="cuda")
+    r16 = to_act16(r, dt, cs=out.shape[-1]) if res else None
+    tapgemm(dt, a16, wt, bias, out, H=h, W=w, relu=relu, residual=r16, k=cin)
+    ref = F.conv2d(x, wt, bias, padding=1)
+    if res:
+        ref = ref + r
+    if relu:
+        ref = F.relu(ref)
+    assert_close(from_act16(out, cout), ref, TOL[dt], "conv3x3 %d->%d" % (cin, cout))
+    assert pads_are_zero(out)
+    if out.shape[-1] > cout:
+        assert out[..., cout:].float().abs().max() == 0
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("cin,cout,h,w", [(64, 256, 12, 9), (256, 64, 12, 9), (96, 48, 6, 4), (384, 192, 3, 2), (48, 96, 24, 18)])
+def test_tapgemm_conv1x1(dt, cin, cout, h, w):
+    B = 2
+    x = q16(_rand(B, cin, h, w, seed=5), dt)
+    wt = q16(_rand(cout, cin, 1, 1, seed=6, scale=1.0 / math.sqrt(cin)), dt)
+    bias = _rand(cout, seed=7, scale=0.1)
+    out = torch.zeros(B, h + 1, w + 1, cout, dtype=TDT[dt], device="cuda")
+    tapgemm(dt, to_act16(x, dt), wt, bias, out, H=h, W=w)
+    assert_close(from_act16(out, cout), F.conv2d(x, wt, bias), TOL[dt], "conv1x1")
+    assert pads_are_zero(out)
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("cin,cout,h,w,relu", [(48, 96, 24, 18, False), (64, 64, 48, 36, True), (96, 192, 12, 10, True),
+                                               (192, 384, 24, 18, True), (48, 48, 96, 72, True), (256, 96, 24, 18, True)])
+def test_tapgemm_conv3x3_stride2_patch(dt, cin, cout, h, w, relu):
+    B = 2
+    x = q16(_rand(B, cin, h, w, seed=8), dt)
+    wt = q16(_rand(cout, cin, 3, 3, seed=9, scale=1.0 / math.sqrt(9 * cin)), dt)
+    bias = _rand(cout, seed=10, scale=0.1)
+    oh, ow = h // 2, w // 2
+    out = torch.zeros(B, oh + 1, ow + 1, cout, dtype=TDT[dt], device="cuda")
+    tapgemm(dt, to_act16(x, dt), wt, bias, out, H=oh, W=ow, stride=2, relu=relu, in_hw=(h, w))
+    ref = F.conv2d(x, wt, bias, stride=2, padding=1)
+    if relu:
+        ref = F.relu(ref)
+    assert_close(from_act16(out, cout), ref, TOL[dt], "conv3x3s2 %d->%d" % (cin, cout))
+    assert pads_are_zero(out)
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_tapgemm_head_nchw32(dt):
+    B, cin, K, h, w = 2, 48, 17, 24, 18
+    x = q16(_rand(B, cin, h, w, seed=11), dt)
+    wt = q16(_rand(K, cin, 1, 1, seed=12, scale=0.2), dt)
+    bias = _rand(K, seed=13, scale=0.1)
+    out = torch.full((B, K, h, w), 9.0, dtype=torch.float32, device="cuda")
+    tapgemm(dt, to_act16(x, dt), wt, bias, out, H=h, W=w, out_mode=L.OUT_NCHW32)
+    assert_close(out, F.conv2d(x, wt, bias), 1e-4 if dt == L.F16 else 1e-4, "head")   # fp32 output: no 16-bit rounding
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("rows,k,n", [(96, 432, 432), (200, 768, 768), (130, 1728, 1728)])
+def test_tapgemm_linear_rows(dt, rows, k, n):
+    x = q16(_rand(rows, k, seed=14), dt)
+    wt = q16(_rand(n, k, seed=15, scale=1.0 / math.sqrt(k)), dt)
+    bias = _rand(n, seed=16, scale=0.1)
+    a16 = x.to(TDT[dt]).contiguous()
+    out = torch.zeros(rows, n, dtype=TDT[dt], device="cuda")
+    tapgemm(dt, a16, wt.view(n, k, 1, 1), bias, out, H=0, W=0, out_mode=L.OUT_ROWS16, m_rows=rows, batch=1)
+    assert_close(out, F.linear(x, wt, bias), TOL[dt], "linear")
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_stem_conv(dt):
+    B, h, w = 2, 32, 24
+    x = _rand(B, 5, h, w, seed=17)
+    wt = _rand(64, 3, 3, 3, seed=18, scale=0.3)
+    bias = _rand(64, seed=19, scale=0.1)
+    out = torch.zeros(B, h // 2 + 1, w // 2 + 1, 64, dtype=TDT[dt], device="cuda")
+    a = L.StemArgs()
+    a.dtype, a.batch, a.x_channels, a.h, a.w, a.out_cs = dt, B, 5, h, w, 64
+    wf = wt.reshape(64, 27).contiguous()
+    a.x, a.weight, a.bias, a.out = x.data_ptr(), wf.data_ptr(), bias.data_ptr(), out.data_ptr()
+    ctx().run(L.OP_STEM, a, stream())
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(x[:, :3], wt, bias, stride=2, padding=1))
+    assert_close(from_act16(out, 64), ref, TOL[dt], "stem")
+    assert pads_are_zero(out)
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_hr_fuse(dt):
+    B, C, h, w = 2, 48, 24, 16
+    t0 = q16(_rand(B, C, h, w, seed=20), dt)
+    t1 = q16(_rand(B, C, h // 2, w // 2, seed=21), dt)
+    t2 = q16(_rand(B, C, h // 4, w // 4, seed=22), dt)
+    t3 = q16(_rand(B, C, h // 8, w // 8, seed=23), dt)
+    terms = [to_act16(t, dt) for t in (t0, t1, t2, t3)]
+    out = torch.full((B, h + 1, w + 1, C), 3.0, dtype=TDT[dt], device="cuda")
+    a = L.FuseArgs()
+    a.dtype, a.batch, a.h, a.w, a.c, a.out_cs, a.nterms, a.relu = dt, B, h, w, C, C, 4, 1
+    for j, t in enumerate(terms):
+        a.term[j], a.term_cs[j], a.term_shift[j] = t.data_ptr(), C, j
+    a.out = out.data_ptr()
+    ctx().run(L.OP_FUSE, a, stream())
+    torch.cuda.synchronize()
+    ref = t0 + sum(F.interpolate(t, scale_factor=2 ** (j + 1), mode="nearest") for j, t in enumerate((t1, t2, t3)))
+    assert_close(from_act16(out, C), F.relu(ref), TOL[dt], "fuse")
+    assert pads_are_zero(out)
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("aa", [1, 0])
+def test_cond_resize(dt, aa):
+    B, cc, H, W = 2, 17, 128, 96
+    x = _rand(B, 3 + cc, H, W, seed=24).abs() * 100
+    for s in (4, 8, 16):
+        oh, ow = H // s, W // s
+        out = torch.zeros(B, oh + 1, ow + 1, 32, dtype=TDT[dt], device="cuda")
+        a = L.ResizeArgs()
+        a.dtype, a.batch, a.x_channels, a.c_off, a.cc = dt, B, 3 + cc, 3, cc
+        a.h, a.w, a.oh, a.ow, a.out_cs, a.antialias = H, W, oh, ow, 32, aa
+        a.x, a.out = x.data_ptr(), out.data_ptr()
+        ctx().run(L.OP_RESIZE, a, stream())
+        torch.cuda.synchronize()
+        ref = F.interpolate(x[:, 3:].cpu(), size=(oh, ow), mode="bilinear", align_corners=False, antialias=bool(aa))
+        assert_close(from_act16(out, cc), ref, TOL[dt], "resize x%d aa=%d" % (s, aa))
+        assert out[..., cc:].float().abs().max() == 0 and pads_are_zero(out)
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("C,h,w", [(48, 24, 18), (96, 12, 9), (192, 6, 5), (32, 8, 6), (64, 4, 3)])
+def test_channel_attention(dt, C, h, w):
+    B = 2
+    y = q16(_rand(B, C, h, w, seed=25), dt)
+    yc = q16(_rand(B, C, h, w, seed=26), dt)
+    out = torch.zeros(B, C, h * w, dtype=TDT[dt], device="cuda")
+    scratch = torch.zeros(B, C, C, dtype=torch.float32, device="cuda")
+    ya, yca = to_act16(y, dt), to_act16(yc, dt)
+    a = L.ChanAttArgs()
+    a.dtype, a.batch, a.h, a.w, a.c, a.y_cs, a.yc_cs = dt, B, h, w, C, C, C
+    a.y, a.yc, a.scratch, a.out = ya.data_ptr(), yca.data_ptr(), scratch.data_ptr(), out.data_ptr()
+    ctx().run(L.OP_CHAN_ATT, a, stream())
+    torch.cuda.synchronize()
+    yf, ycf = y.view(B, C, -1), yc.view(B, C, -1)
+    att = torch.softmax(torch.matmul(ycf, yf.transpose(1, 2)) / math.sqrt(h * w), -1)
+    assert_close(scratch, att, 1e-4, "chan att probs")
+    assert_close(out, torch.matmul(att, yf), TOL[dt], "chan att out")
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("C,h,w", [(48, 24, 18), (96, 12, 9), (192, 7, 5), (32, 16, 12), (64, 8, 6), (128, 4, 3)])
+def test_position_attention(dt, C, h, w):
+    B = 2
+    q = q16(_rand(B, C, h, w, seed=27, scale=1.5), dt)
+    k = q16(_rand(B, C, h, w, seed=28), dt)
+    v = q16(_rand(B, C, h, w, seed=29), dt)
+    qa = to_act16(q, dt)
+    kv = to_act16(torch.cat([k, v], 1), dt)
+    # poison the pad rows of k/v: they must be masked out, not merely zero
+    kv[:, -1] = 50.0
+    kv[:, :, -1] = 50.0
+    o = torch.zeros(B, h + 1, w + 1, C, dtype=TDT[dt], device="cuda")
+    a = L.PosAttArgs()
+    a.dtype, a.batch, a.h, a.w, a.c = dt, B, h, w, C
+    a.q_cs, a.k_cs, a.v_cs, a.o_cs = C, 2 * C, 2 * C, C
+    a.q, a.k, a.v, a.o = qa.data_ptr(), kv.data_ptr(), kv.data_ptr() + 2 * C, o.data_ptr()
+    ctx().run(L.OP_POS_ATT, a, stream())
+    torch.cuda.synchronize()
+    qt, kt, vt = [t.view(B, C, -1).transpose(1, 2) for t in (q, k, v)]
+    att = torch.softmax(torch.matmul(qt, kt.transpose(1, 2)) / math.sqrt(C), -1)
+    ref = torch.matmul(att, vt).transpose(1, 2).reshape(B, C, h, w)
+    assert_close(from_act16(o, C), ref, 2.5 * TOL[dt], "pos att")     # P is rounded to 16 bit before P.V
+    assert pads_are_zero(o)
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("channel_only", [0, 1])
+def test_da_combine(dt, channel_only):
+    B, C, h, w = 2, 48, 11, 7
+    x = q16(_rand(B, C, h, w, seed=30), dt)
+    p = q16(_rand(B, C, h, w, seed=31), dt)
+    c = q16(_rand(B, C, h, w, seed=32), dt)
+    out = torch.zeros(B, h + 1, w + 1, C, dtype=TDT[dt], device="cuda")
+    xa, pa, cp = to_act16(x, dt), to_act16(p, dt), c.view(B, C, -1).to(TDT[dt]).contiguous()
+    a = L.DaCombineArgs()
+    a.dtype, a.batch, a.h, a.w, a.c, a.x_cs, a.p_cs, a.out_cs, a.channel_only = dt, B, h, w, C, C, C, C, channel_only
+    a.x, a.p_out, a.c_out, a.out = xa.data_ptr(), pa.data_ptr(), cp.data_ptr(), out.data_ptr()
+    ctx().run(L.OP_DA_COMBINE, a, stream())
+    torch.cuda.synchronize()
+    ref = x * c if channel_only else x + (p + c)
+    assert_close(from_act16(out, C), ref, TOL[dt], "da_combine")
+    assert pads_are_zero(out)
+
+
+def test_prenet_composed():
+    """composed 9x9 + border variants == conv7x7(BN(conv3x3(rgb))) + conv7x7(cond) in fp32"""
+    from buctd_b200 import pose_hrnet
+    from buctd_b200.config import make_cfg
+    from buctd_b200.synth import synth_state_dict
+    cfg = make_cfg("prenet", 32, (24, 40), cond="colored")
+    net = pose_hrnet.get_pose_net(cfg, is_train=False)
+    sd = synth_state_dict(net.arch, 3)
+    net.load_state_dict(sd)
+    f = {k: v.cuda() for k, v in net._compose_prenet().items()}
+    B, H, W = 2, 40, 24
+    x = _rand(B, 6, H, W, seed=33)
+    out = torch.zeros(B, 3, H, W, device="cuda")
+    a = L.PrenetArgs()
+    a.batch, a.x_channels, a.h, a.w = B, 6, H, W
+    a.x, a.w_eff, a.b_eff, a.wc, a.out = x.data_ptr(), f["prenet.w_eff"].data_ptr(), f["prenet.b_eff"].data_ptr(), f["prenet.wc"].data_ptr(), out.data_ptr()
+    ctx().run(L.OP_PRENET, a, stream())
+    torch.cuda.synchronize()
+    sdc = {k: v.cuda() for k, v in sd.items()}
+
+    def bn(p, t):
+        return F.batch_norm(t, sdc[p + ".running_mean"], sdc[p + ".running_var"], sdc[p + ".weight"], sdc[p + ".bias"], False, 0.0, 1e-5)
+    t = bn("rgb_preNet.1", F.conv2d(x[:, :3], sdc["rgb_preNet.0.weight"], sdc["rgb_preNet.0.bias"], padding=1))
+    x0 = bn("rgb_preNet.3", F.conv2d(t, sdc["rgb_preNet.2.weight"], sdc["rgb_preNet.2.bias"], padding=3))
+    x1 = bn("cond_preNet.1", F.conv2d(x[:, 3:], sdc["cond_preNet.0.weight"], sdc["cond_preNet.0.bias"], padding=3))
+    assert_close(out, x0 + x1, 2e-5, "prenet")
