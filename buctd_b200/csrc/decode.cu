@@ -80,10 +80,10 @@ __global__ void __launch_bounds__(256) decode_kernel(buctd_decode_args a) {
 }
 
 int launch_decode(const buctd_decode_args& a, cudaStream_t st) {
-  BUCTD_CHECK(a.heatmaps && a.preds && a.maxvals, BUCTD_ERR_INVALID, "decode: null pointer");
   BUCTD_CHECK(a.batch >= 0 && a.k > 0 && a.h > 0 && a.w > 0, BUCTD_ERR_INVALID, "decode: bad shape");
+  if (a.batch == 0) return BUCTD_OK;      // empty batch: nothing to do (pointers may be null)
+  BUCTD_CHECK(a.heatmaps && a.preds && a.maxvals, BUCTD_ERR_INVALID, "decode: null pointer");
   BUCTD_CHECK((a.center == nullptr) == (a.scale == nullptr), BUCTD_ERR_INVALID, "decode: center and scale go together");
-  if (a.batch == 0) return BUCTD_OK;
   decode_kernel<<<a.batch * a.k, 256, 0, st>>>(a);
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;
