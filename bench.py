@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""Benchmark of the BUCTD conditional top-down hot path (BASELINE.json: crops/sec at 384x288
+BUCTD-CoAM-W48, stacked 17-channel condition, batch 64 per GPU, inference forward + decode).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port)
+
+One step = one forward of the network over one batch of synthetic crops + the fused decode.
+`value`   : crops/s with the inputs already resident in HBM (whole job, all ranks).
+`e2e`     : the same metric through the reference-facing call `model(x_host)` + decode with HOST
+            buffers: the pinned-host -> device copy of every step's input and the device -> host
+            read of the decoded keypoints are inside the timed region.
+`roofline`: fraction of the 3x3-conv tensor-core roofline: achieved =
+            crops/s/GPU x 70.34 GFLOP (all 3x3 convolutions of CoAM-W48 per crop) against the MEASURED
+            dense bf16/fp16 tensor peak in MEASURED_PEAKS.json (sustained figure: the kernels are timed
+            inside a long step), plus the dominant launch class timed alone with CUDA events.
+`cpu_baseline`: the oracle port of the reference forward + decode on the host cores (bounded sample).
+Only the cpu_baseline / --impl reference legs import oracle/.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+F3X3_GFLOP = {"coam": 70.34, "prenet": 68.78}      # BASELINE.md section 2 (3x3 convs, per crop)
+FTOTAL_GFLOP = {"coam": 88.75, "prenet": 73.17}
+METRIC = "crops/sec at 384x288 CoAM-W48"
+WORKLOAD = "BUCTD-CoAM-W48 384x288, 17 kpts, stacked condition, batch=%d/GPU, inference forward + decode"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"tflops_burst": d["bf16_tflops"], "tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "hbm_gbs": d["hbm_gbs"], "source": "measured"}
+    return {"tflops_burst": 1590.0, "tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(torch, cfg, batch, device, seed):
+    """Synthetic crops on the device: RGB ~ N(0,1); condition = rasterised random proposals (0..255)."""
+    from buctd_b200 import condition
+    w, h = cfg.MODEL.IMAGE_SIZE
+    k = cfg.MODEL.NUM_JOINTS
+    g = torch.Generator(device=device).manual_seed(seed)
+    x = torch.empty(batch, 3 + k, h, w, dtype=torch.float32, device=device)
+    x[:, :3] = torch.randn(batch, 3, h, w, generator=g, device=device)
+    kp = torch.rand(batch, k, 2, generator=g, device=device) * torch.tensor([w - 16.0, h - 16.0], device=device) + 8.0
+    kp[torch.rand(batch, k, generator=g, device=device) < 0.1] = 0.0
+    condition.rasterize_condition(kp, h, w, "stacked", out=x, c_off=3)
+    c = torch.tensor([w / 2.0, h / 2.0], device=device) + (torch.rand(batch, 2, generator=g, device=device) * 40 - 20)
+    s = torch.tensor([w / 200.0, h / 200.0], device=device) * (0.8 + 0.45 * torch.rand(batch, 1, generator=g, device=device))
+    return x, c.contiguous(), s.contiguous()
+
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    from buctd_b200 import inference, pose_hrnet_coam, synth
+    from buctd_b200.config import make_cfg
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("WORLD_SIZE %d != --gpus %d" % (world, args.gpus))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    B = args.batch
+    cfg = make_cfg("coam", 48, (288, 384), cond="stacked")
+    net = pose_hrnet_coam.get_pose_net(cfg, is_train=False, dtype=args.dtype)
+    net.load_state_dict(synth.synth_state_dict(net.arch, 0), strict=True)     # random-init weights of the architecture
+    net = net.cuda().eval()
+    x, center, scale = make_inputs(torch, cfg, B, device, 1234 + rank)
+    K = cfg.MODEL.NUM_JOINTS
+    gathered = [torch.empty(B, K, 3, device=device) for _ in range(world)] if world > 1 else None
+
+    def step(xin):
+        hm = net(xin)
+        preds, maxvals = inference.decode_device(hm, center, scale, post_process=True)
+        res = torch.cat([preds, maxvals], -1)                 # [B,K,3] = 204 B per crop
+        if world > 1:                                          # the ONE collective: decoded keypoints only
+            dist.all_gather(gathered, res)
+        return res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            step(x)
+        barrier()
+        ctx = net._plans[(B, local)]["ctx"]
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        l0 = ctx.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step(x)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = ctx.launch_count() - l0
+        clocks = sampler.stop() if rank == 0 else None
+
+        # ---- end to end: host buffers, H2D of every step's input + D2H of the decoded result ----------
+        xh = [x.cpu().pin_memory() for _ in range(1)][0]
+        out_h = torch.empty(B, K, 3).pin_memory()
+        copy_stream = torch.cuda.Stream(device)
+        xd = [torch.empty_like(x) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+
+        def e2e_loop(n):
+            main = torch.cuda.current_stream(device)
+            for i in range(n):
+                b = i & 1
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(freed[b]) if i >= 2 else None
+                    xd[b].copy_(xh, non_blocking=True)          # 566 MB pinned host -> device
+                    ready[b].record(copy_stream)
+                main.wait_event(ready[b])
+                res = step(xd[b])
+                freed[b].record(main)
+                out_h.copy_(res, non_blocking=True)             # 13 KB device -> host
+            main.synchronize()
+
+        e2e_loop(2)
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        e2e_loop(args.steps)
+        t1.record()
+        barrier()
+        ms_e2e = t0.elapsed_time(t1)
+
+        # ---- dominant launch class alone: BasicBlock conv 48->48 3x3 @96x72 (64 launches / forward) ---
+        kern = time_dominant_conv(torch, net, B, local)
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    crops = B * world * args.steps
+    value = crops / (ms / 1e3)
+    per_gpu = value / world
+    ach = per_gpu * F3X3_GFLOP["coam"] / 1e3
+    out = {
+        "metric": METRIC, "value": round(value, 2), "unit": "crops/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": WORKLOAD % B, "global_batch": B * world, "parallelism": "crops sharded, dp%d" % world,
+                   "weights": "random-init (buctd_b200.synth, seed 0)", "l2": "per-step input 566 MB > 126 MB L2",
+                   "collective": "one NCCL all_gather of decoded [B,17,3] per step" if world > 1 else "none"},
+        "roofline": {"bound": "tensor", "achieved": round(ach, 2), "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": round(ach / peaks["tflops_sustained"], 4), "traffic": None,
+                     "peak_source": peaks["source"] + " (sustained bf16/fp16 dense)",
+                     "what": "crops/s/GPU x 70.34 GFLOP of 3x3 convs per crop (BASELINE.md)",
+                     "all_contractions_tflops": round(per_gpu * FTOTAL_GFLOP["coam"] / 1e3, 2),
+                     "dominant_kernel": kern},
+        "e2e": {"value": round(crops / (ms_e2e / 1e3), 2), "unit": "crops/s",
+                "h2d_bytes_per_step": int(x.numel() * 4), "d2h_bytes_per_step": int(B * K * 3 * 4),
+                "ms_per_step": round(ms_e2e / args.steps, 4), "api": "model(x_host) + decode_device + .cpu()"},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(sample_crops=4, iters=2)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def time_dominant_conv(torch, net, B, local):
+    """The single most expensive launch class, timed alone with CUDA events: 3x3 s1 48->48 at 96x72
+    (BasicBlock, branch 0).  Algorithmic FLOPs per launch = 2 * B*96*72 * 48*48*9."""
+    st = net._plans[(B, local)]
+    plan = st["plan"]
+    idx = [i for i, l in enumerate(plan.labels) if l.startswith("stage3.0.branches.0.") and l.endswith("conv1")]
+    if not idx:
+        return None
+    i = idx[0]
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(5):
+        plan.run(stream, i, i + 1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 50
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n):
+        plan.run(stream, i, i + 1)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / n
+    flops = 2.0 * B * 96 * 72 * 48 * 48 * 9
+    peaks = load_peaks()
+    # per-launch HBM minimum: read in + write out (+ residual on conv2), 16-bit padded NHWC
+    return {"name": "tapgemm 3x3 s1 48->48 @96x72 (BasicBlock conv1)", "us_per_launch": round(us, 2),
+            "tflops": round(flops / us / 1e6, 2), "frac_of_burst_peak": round(flops / us / 1e6 / peaks["tflops_burst"], 4),
+            "hbm_bytes_min": int(2 * B * 97 * 73 * 48 * 2), "note": "back-to-back launches: input stays in L2 (43 MB)"}
+
+
+def cpu_baseline(sample_crops=4, iters=2):
+    """The oracle port of the reference forward + get_final_preds on the host cores (reported baseline only)."""
+    import torch
+    from buctd_b200 import synth
+    from buctd_b200.arch import HRNetArch
+    from buctd_b200.config import make_cfg
+    from oracle import condition_oracle, decode_oracle, hrnet_oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = make_cfg("coam", 48, (288, 384), cond="stacked")
+    sd = synth.synth_state_dict(HRNetArch(cfg), 0)
+    rgb = synth.synth_rgb(sample_crops, 288, 384)
+    kp = synth.synth_keypoints(sample_crops, 17, 288, 384)
+    cond = np.stack([condition_oracle.stacked_condition(kp[b], 384, 288) for b in range(sample_crops)]).astype(np.float32)
+    x = torch.from_numpy(np.concatenate([rgb, cond], 1))
+    c, s = synth.synth_center_scale(sample_crops, 288, 384)
+    with torch.no_grad():
+        hrnet_oracle.forward(sd, cfg, x)                       # warm-up
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            hm = hrnet_oracle.forward(sd, cfg, x).numpy()
+            decode_oracle.get_final_preds(True, hm, c, s)
+        dt = (time.perf_counter() - t0) / iters
+    return {"value": round(sample_crops / dt, 3), "unit": "crops/s", "cores": cores, "kind": "port",
+            "sample": "%d crops x %d iterations of the same workload (fp32 oracle port of the reference forward + decode, "
+                      "torch CPU threads=%d)" % (sample_crops, iters, cores)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU algorithm (oracle port; /root/reference does not exist on the
+    GPU box and the reference has no native code to compile).  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    from buctd_b200 import synth
+    from buctd_b200.arch import HRNetArch
+    from buctd_b200.config import make_cfg
+    from oracle import condition_oracle, decode_oracle, hrnet_oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n = args.ref_crops
+    cfg = make_cfg("coam", 48, (288, 384), cond="stacked")
+    sd = synth.synth_state_dict(HRNetArch(cfg), 0)
+    rgb = synth.synth_rgb(n, 288, 384)
+    kp = synth.synth_keypoints(n, 17, 288, 384)
+    cond = np.stack([condition_oracle.stacked_condition(kp[b], 384, 288) for b in range(n)]).astype(np.float32)
+    x = torch.from_numpy(np.concatenate([rgb, cond], 1))
+    c, s = synth.synth_center_scale(n, 288, 384)
+
+    def step():
+        hm = hrnet_oracle.forward(sd, cfg, x).numpy()
+        decode_oracle.get_final_preds(True, hm, c, s)
+
+    # bound the whole run to a few minutes whatever K the driver passes
+    with torch.no_grad():
+        step()
+        t0 = time.perf_counter(); step(); per = time.perf_counter() - t0
+        steps = max(1, min(args.steps, int(150.0 / max(per, 1e-3))))
+        warm = max(0, min(args.warmup, 3) - 2)
+        for _ in range(warm):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        dt = time.perf_counter() - t0
+    v = round(n * steps / dt, 3)
+    sample = "%d crops per step x %d timed steps (fp32 oracle port of the reference forward + decode, %d CPU threads)" % (n, steps, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "crops/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm + 2, "ms_per_step": round(dt / steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD % args.batch, "sample_crops_per_step": n},
+        "cpu_baseline": {"value": v, "unit": "crops/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--dtype", default=os.environ.get("BUCTD_DTYPE", "fp16"), choices=["fp16", "bf16"])
+    ap.add_argument("--batch", type=int, default=64, help="crops per GPU")
+    ap.add_argument("--ref-crops", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -72,14 +72,14 @@ static int copy_args(A* dst, const void* src, size_t size, const char* name) {
   return BUCTD_OK;
 }
 
-static int make_op(int kind, const void* args, size_t size, PlanOp* op) {
+static int make_op(int kind, const void* args, size_t size, PlanOp* op, int sm_count) {
   BUCTD_CHECK(args != nullptr, BUCTD_ERR_INVALID, "null args");
   op->kind = kind;
   switch (kind) {
     case BUCTD_OP_TAPGEMM: {
       buctd_tapgemm_args a;
       int rc = copy_args(&a, args, size, "tapgemm");
-      return rc ? rc : tapgemm_prepare(a, &op->tg);
+      return rc ? rc : tapgemm_prepare(a, &op->tg, sm_count);
     }
     case BUCTD_OP_STEM: return copy_args(&op->u.stem, args, size, "stem");
     case BUCTD_OP_FUSE: return copy_args(&op->u.fuse, args, size, "fuse");
@@ -151,7 +151,7 @@ BUCTD_API long long buctd_launch_count(const buctd_ctx* ctx) { return ctx ? ctx-
 static int immediate(buctd_ctx* ctx, int kind, const void* args, size_t size, buctd_stream stream) {
   BUCTD_CHECK(ctx != nullptr, BUCTD_ERR_INVALID, "null ctx");
   PlanOp op;
-  int rc = make_op(kind, args, size, &op);
+  int rc = make_op(kind, args, size, &op, ctx->sm_count);
   if (rc) return rc;
   rc = run_op(op, static_cast<cudaStream_t>(stream));
   if (!rc) ctx->launches += op.nlaunch;
@@ -217,7 +217,7 @@ BUCTD_API int buctd_plan_destroy(buctd_plan* plan) {
 BUCTD_API int buctd_plan_add(buctd_plan* plan, int kind, const void* args, size_t size) {
   BUCTD_CHECK(plan != nullptr, BUCTD_ERR_INVALID, "buctd_plan_add: null plan");
   PlanOp op;
-  int rc = make_op(kind, args, size, &op);
+  int rc = make_op(kind, args, size, &op, plan->ctx->sm_count);
   if (rc) return rc;
   plan->ops.push_back(op);
   return BUCTD_OK;

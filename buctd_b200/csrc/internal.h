@@ -29,17 +29,30 @@ struct TapGemmKParams {
   void* out;
 };
 
+// slab (FLAT-mode) kernel plan: super-tile, rings and shared-memory carve-up
+struct SlabParams {
+  int msub;          // 128-row sub-tiles per super-tile
+  int halo;          // slab rows loaded before/after the super-tile (W+2 for 3x3, 0 for 1x1)
+  int nboxes, box_rows, slab_bytes;
+  int sa, sw;        // slab ring / weight ring depth
+  int w_resident, w_tiles;
+  int num_super, num_items;
+  int tmem_cols, smem_bytes;
+  int desc_mode;
+};
+
 // everything a tap-GEMM launch needs, computed (tensor maps encoded) once
 struct TapGemmLaunch {
   alignas(64) CUtensorMap map_a;
   alignas(64) CUtensorMap map_b;
   TapGemmKParams kp;
+  SlabParams sp;
   dim3 grid;
   int bn;
   int dtype;
 };
 
-int tapgemm_prepare(const buctd_tapgemm_args& a, TapGemmLaunch* L);
+int tapgemm_prepare(const buctd_tapgemm_args& a, TapGemmLaunch* L, int sm_count);
 int tapgemm_launch(const TapGemmLaunch& L, cudaStream_t st);
 int tapgemm_init_device();
 

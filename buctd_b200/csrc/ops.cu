@@ -152,62 +152,68 @@ int launch_fuse(const buctd_fuse_args& a, cudaStream_t st) {
 // weight max(0, 1-|j-centre+0.5|/scale), normalised.  antialias=0: support 1 (2-tap bilinear).
 // Horizontal pass first, then vertical, both in fp32 (ATen's separable order).
 // =================================================================================================
+constexpr int kRzRows = 4;      // output rows per block
+constexpr int kRzMaxW = 512;
+
+__device__ __forceinline__ void aa_span(float scale, float support, int o, int n_in, int* lo, int* hi, float* center) {
+  *center = scale * (o + 0.5f);
+  *lo = max(0, (int)(*center - support + 0.5f));
+  *hi = min(n_in, (int)(*center + support + 0.5f));
+}
+
 template <typename T>
-__global__ void __launch_bounds__(128) resize_kernel(buctd_resize_args a) {
-  // one block = one output row (b, c, oy); thread = ox.  Row weights staged in shared memory.
-  __shared__ float s_wy[64];
-  __shared__ int s_ylo, s_yn;
-  const int oy = blockIdx.x, c = blockIdx.y, b = blockIdx.z;
+__global__ void __launch_bounds__(256) resize_kernel(buctd_resize_args a) {
+  // block = kRzRows output rows of one (b, c) plane.  Pass 1 (threads over input columns, coalesced):
+  // vertical triangle filter into shared memory; pass 2: horizontal filter + 16-bit store.
+  __shared__ float s_v[kRzRows][kRzMaxW];
+  const int c = blockIdx.y, b = blockIdx.z;
+  const int oy0 = blockIdx.x * kRzRows;
   const float sy = (float)a.h / a.oh, sx = (float)a.w / a.ow;
-  const float supy = (a.antialias && sy > 1.f) ? sy : 1.f, supx = (a.antialias && sx > 1.f) ? sx : 1.f;
-  const float invy = (a.antialias && sy > 1.f) ? 1.f / sy : 1.f, invx = (a.antialias && sx > 1.f) ? 1.f / sx : 1.f;
-  if (threadIdx.x == 0) {
-    const float center = sy * (oy + 0.5f);
-    int lo = max(0, (int)(center - supy + 0.5f)), hi = min(a.h, (int)(center + supy + 0.5f));
+  const bool aay = a.antialias && sy > 1.f, aax = a.antialias && sx > 1.f;
+  const float supy = aay ? sy : 1.f, supx = aax ? sx : 1.f;
+  const float invy = aay ? 1.f / sy : 1.f, invx = aax ? 1.f / sx : 1.f;
+  const float* src = a.x + (((long long)b * a.x_channels + a.c_off + c) * a.h) * a.w;
+  for (int g = 0; g < kRzRows; ++g) {
+    const int oy = oy0 + g;
+    if (oy >= a.oh) break;
+    int lo, hi; float center;
+    aa_span(sy, supy, oy, a.h, &lo, &hi, &center);
     float tot = 0.f;
-    for (int j = lo; j < hi; ++j) {
-      float w = fmaxf(0.f, 1.f - fabsf((j - center + 0.5f) * invy));
-      s_wy[j - lo] = w;
-      tot += w;
+    for (int j = lo; j < hi; ++j) tot += fmaxf(0.f, 1.f - fabsf((j - center + 0.5f) * invy));
+    const float rt = 1.f / tot;
+    for (int x = threadIdx.x; x < a.w; x += blockDim.x) {
+      float acc = 0.f;
+      for (int j = lo; j < hi; ++j)
+        acc = fmaf(fmaxf(0.f, 1.f - fabsf((j - center + 0.5f) * invy)) * rt, __ldg(src + (long long)j * a.w + x), acc);
+      s_v[g][x] = acc;
     }
-    for (int j = lo; j < hi; ++j) s_wy[j - lo] /= tot;
-    s_ylo = lo; s_yn = hi - lo;
   }
   __syncthreads();
-  const float* src = a.x + (((long long)b * a.x_channels + a.c_off + c) * a.h) * a.w;
-  for (int ox = threadIdx.x; ox < a.ow; ox += blockDim.x) {
-    const float center = sx * (ox + 0.5f);
-    const int lo = max(0, (int)(center - supx + 0.5f)), hi = min(a.w, (int)(center + supx + 0.5f));
-    float wx[64];
-    float tot = 0.f;
-    const int n = hi - lo;
-#pragma unroll 1
-    for (int j = 0; j < n; ++j) {
-      float w = fmaxf(0.f, 1.f - fabsf((lo + j - center + 0.5f) * invx));
-      wx[j] = w;
+  for (int i = threadIdx.x; i < kRzRows * a.ow; i += blockDim.x) {
+    const int g = i / a.ow, ox = i - g * a.ow;
+    const int oy = oy0 + g;
+    if (oy >= a.oh) break;
+    int lo, hi; float center;
+    aa_span(sx, supx, ox, a.w, &lo, &hi, &center);
+    float tot = 0.f, acc = 0.f;
+    for (int j = lo; j < hi; ++j) {
+      const float w = fmaxf(0.f, 1.f - fabsf((j - center + 0.5f) * invx));
       tot += w;
-    }
-    const float rt = 1.f / tot;
-    float acc = 0.f;
-    for (int iy = 0; iy < s_yn; ++iy) {
-      const float* row = src + (long long)(s_ylo + iy) * a.w + lo;
-      float h = 0.f;
-#pragma unroll 1
-      for (int j = 0; j < n; ++j) h = fmaf(wx[j] * rt, row[j], h);
-      acc = fmaf(s_wy[iy], h, acc);
+      acc = fmaf(w, s_v[g][j], acc);
     }
     T* o = reinterpret_cast<T*>(a.out) + (((long long)b * (a.oh + 1) + oy) * (a.ow + 1) + ox) * a.out_cs + c;
-    *o = T16<T>::from_f(acc);
+    *o = T16<T>::from_f(acc / tot);
   }
 }
 
 int launch_resize(const buctd_resize_args& a, cudaStream_t st) {
   BUCTD_CHECK(a.cc > 0 && a.cc <= a.out_cs, BUCTD_ERR_INVALID, "resize: cc %d vs out_cs %d", a.cc, a.out_cs);
-  const float sy = (float)a.h / a.oh, sx = (float)a.w / a.ow;
-  BUCTD_CHECK(2 * sy + 2 <= 64 && 2 * sx + 2 <= 64, BUCTD_ERR_INVALID, "resize: scale %.2f x %.2f too large (max 31)", sy, sx);
-  dim3 grid(a.oh, a.cc, a.batch);
-  if (a.dtype == BUCTD_F16) resize_kernel<__half><<<grid, 128, 0, st>>>(a);
-  else resize_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(a);
+  BUCTD_CHECK(a.w <= kRzMaxW, BUCTD_ERR_INVALID, "resize: input width %d > %d", a.w, kRzMaxW);
+  BUCTD_CHECK(a.x && a.out, BUCTD_ERR_INVALID, "resize: null pointer");
+  if (a.batch == 0) return BUCTD_OK;
+  dim3 grid(ceil_div(a.oh, kRzRows), a.cc, a.batch);
+  if (a.dtype == BUCTD_F16) resize_kernel<__half><<<grid, 256, 0, st>>>(a);
+  else resize_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a);
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;
 }

@@ -44,15 +44,46 @@ def test_tapgemm_conv3x3_flat(dt, cin, cout, h, w, relu, res):
     out = torch.full((B, h + 1, w + 1, rup(cout, 16)), 7.0, dtype=TDT[dt], device="cuda")
     r16 = to_act16(r, dt, cs=out.shape[-1]) if res else None
     tapgemm(dt, a16, wt, bias, out, H=h, W=w, relu=relu, residual=r16, k=cin)
-    ref = F.conv2d(x, wt, bias, padding=1)
+    ref = F.conv2d(x.cpu(), wt.cpu(), bias.cpu(), padding=1)
     if res:
-        ref = ref + r
+        ref = ref + r.cpu()
     if relu:
         ref = F.relu(ref)
     assert_close(from_act16(out, cout), ref, TOL[dt], "conv3x3 %d->%d" % (cin, cout))
     assert pads_are_zero(out)
     if out.shape[-1] > cout:
         assert out[..., cout:].float().abs().max() == 0
+
+
+@pytest.mark.parametrize("msub", [1, 2, 3, 4])
+@pytest.mark.parametrize("cin,cout", [(48, 48), (96, 96), (64, 64), (256, 48), (192, 192)])
+def test_tapgemm_slab_supertiles(monkeypatch, msub, cin, cout):
+    """slab kernel: every super-tile size (row-shifted tap views across sub-tiles), resident and ring weights"""
+    monkeypatch.setenv("BUCTD_FORCE_MSUB", str(msub))
+    dt, B, h, w = L.F16, 7, 24, 18
+    x = q16(_rand(B, cin, h, w, seed=41), dt)
+    wt = q16(_rand(cout, cin, 3, 3, seed=42, scale=1.0 / math.sqrt(9 * cin)), dt)
+    bias = _rand(cout, seed=43, scale=0.1)
+    r = q16(_rand(B, cout, h, w, seed=44), dt)
+    out = torch.full((B, h + 1, w + 1, cout), 7.0, dtype=TDT[dt], device="cuda")
+    tapgemm(dt, to_act16(x, dt), wt, bias, out, H=h, W=w, relu=True, residual=to_act16(r, dt))
+    ref = F.relu(F.conv2d(x.cpu(), wt.cpu(), bias.cpu(), padding=1) + r.cpu())
+    assert_close(from_act16(out, cout), ref, TOL[dt], "slab msub=%d %d->%d" % (msub, cin, cout))
+    assert pads_are_zero(out)
+
+
+@pytest.mark.parametrize("cin,cout,B,h,w", [(48, 48, 10, 96, 72), (96, 96, 24, 48, 36), (384, 384, 40, 12, 9)])
+def test_tapgemm_slab_persistent_many_items(cin, cout, B, h, w):
+    """more work items than SMs: every CTA loops, both TMEM accumulator sets and the slab ring wrap"""
+    dt = L.F16
+    x = q16(_rand(B, cin, h, w, seed=45), dt)
+    wt = q16(_rand(cout, cin, 3, 3, seed=46, scale=1.0 / math.sqrt(9 * cin)), dt)
+    bias = _rand(cout, seed=47, scale=0.1)
+    out = torch.zeros(B, h + 1, w + 1, cout, dtype=TDT[dt], device="cuda")
+    tapgemm(dt, to_act16(x, dt), wt, bias, out, H=h, W=w, relu=True)
+    ref = F.relu(F.conv2d(x.cpu(), wt.cpu(), bias.cpu(), padding=1))
+    assert_close(from_act16(out, cout), ref, TOL[dt], "slab persistent")
+    assert pads_are_zero(out)
 
 
 @pytest.mark.parametrize("dt", DTS)
@@ -64,7 +95,7 @@ def test_tapgemm_conv1x1(dt, cin, cout, h, w):
     bias = _rand(cout, seed=7, scale=0.1)
     out = torch.zeros(B, h + 1, w + 1, cout, dtype=TDT[dt], device="cuda")
     tapgemm(dt, to_act16(x, dt), wt, bias, out, H=h, W=w)
-    assert_close(from_act16(out, cout), F.conv2d(x, wt, bias), TOL[dt], "conv1x1")
+    assert_close(from_act16(out, cout), F.conv2d(x.cpu(), wt.cpu(), bias.cpu()), TOL[dt], "conv1x1")
     assert pads_are_zero(out)
 
 
@@ -79,7 +110,7 @@ def test_tapgemm_conv3x3_stride2_patch(dt, cin, cout, h, w, relu):
     oh, ow = h // 2, w // 2
     out = torch.zeros(B, oh + 1, ow + 1, cout, dtype=TDT[dt], device="cuda")
     tapgemm(dt, to_act16(x, dt), wt, bias, out, H=oh, W=ow, stride=2, relu=relu, in_hw=(h, w))
-    ref = F.conv2d(x, wt, bias, stride=2, padding=1)
+    ref = F.conv2d(x.cpu(), wt.cpu(), bias.cpu(), stride=2, padding=1)
     if relu:
         ref = F.relu(ref)
     assert_close(from_act16(out, cout), ref, TOL[dt], "conv3x3s2 %d->%d" % (cin, cout))
@@ -94,7 +125,7 @@ def test_tapgemm_head_nchw32(dt):
     bias = _rand(K, seed=13, scale=0.1)
     out = torch.full((B, K, h, w), 9.0, dtype=torch.float32, device="cuda")
     tapgemm(dt, to_act16(x, dt), wt, bias, out, H=h, W=w, out_mode=L.OUT_NCHW32)
-    assert_close(out, F.conv2d(x, wt, bias), 1e-4 if dt == L.F16 else 1e-4, "head")   # fp32 output: no 16-bit rounding
+    assert_close(out, F.conv2d(x.cpu(), wt.cpu(), bias.cpu()), 1e-4, "head")   # fp32 output: no 16-bit rounding
 
 
 @pytest.mark.parametrize("dt", DTS)
@@ -106,7 +137,7 @@ def test_tapgemm_linear_rows(dt, rows, k, n):
     a16 = x.to(TDT[dt]).contiguous()
     out = torch.zeros(rows, n, dtype=TDT[dt], device="cuda")
     tapgemm(dt, a16, wt.view(n, k, 1, 1), bias, out, H=0, W=0, out_mode=L.OUT_ROWS16, m_rows=rows, batch=1)
-    assert_close(out, F.linear(x, wt, bias), TOL[dt], "linear")
+    assert_close(out, F.linear(x.cpu(), wt.cpu(), bias.cpu()), TOL[dt], "linear")
 
 
 @pytest.mark.parametrize("dt", DTS)
@@ -122,7 +153,7 @@ def test_stem_conv(dt):
     a.x, a.weight, a.bias, a.out = x.data_ptr(), wf.data_ptr(), bias.data_ptr(), out.data_ptr()
     ctx().run(L.OP_STEM, a, stream())
     torch.cuda.synchronize()
-    ref = F.relu(F.conv2d(x[:, :3], wt, bias, stride=2, padding=1))
+    ref = F.relu(F.conv2d(x[:, :3].cpu(), wt.cpu(), bias.cpu(), stride=2, padding=1))
     assert_close(from_act16(out, 64), ref, TOL[dt], "stem")
     assert pads_are_zero(out)
 
