@@ -1,8 +1,11 @@
 // Shared epilogue of the tap-GEMM kernels: TMEM accumulator tile (128 rows x BN fp32 columns)
-//   -> + bias[n] + residual[m,n] -> ReLU -> pad mask -> 16-bit -> global,
-// staged through shared memory so that both the residual read and the output write are fully
-// coalesced 16-byte accesses (a thread owns one accumulator ROW; writing rows straight from
-// registers would scatter 16-byte pieces over 32 different lines per instruction).
+//   -> + bias[n] + residual[m,n] -> ReLU -> pad mask -> 16-bit -> global.
+//
+// The 16-bit tile is staged in shared memory as ceil(BN/64) column blocks of [128 rows][128 B] in the
+// SWIZZLE_128B layout, which is (a) what a TMA tensor load produces -- the residual tile is fetched
+// by TMA ahead of time, so its HBM latency is off the critical path -- (b) bank-conflict free for the
+// one-thread-one-row access pattern that tcgen05.ld imposes, and (c) what a TMA tensor store consumes:
+// the output leaves with cp.async.bulk.tensor stores, which also clip the M and N tails.
 // Runs on the 4 epilogue warps (128 threads); warp w may only touch TMEM lanes [32*(w%4), +32).
 #pragma once
 #include "common.cuh"
@@ -10,36 +13,55 @@
 
 namespace buctd {
 
-constexpr int kEpiThreads = 128;
 constexpr int kEpiBarrier = 1;     // named barrier id used by the epilogue warps
+constexpr int kEpiBlockBytes = 128 * 128;
 
-__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync %0, %1;" ::"n"(kEpiBarrier), "n"(kEpiThreads) : "memory"); }
+// NT = number of epilogue threads (128: one warp per TMEM lane quarter; 256: two warps per quarter,
+// which split the columns of a tile between them)
+template <int NT> __device__ __forceinline__ void epi_sync() {
+  asm volatile("bar.sync %0, %1;" ::"n"(kEpiBarrier), "n"(NT) : "memory");
+}
 
-template <int BN> __host__ __device__ constexpr int epi_pitch() { return BN * 2 + 16; }   // odd number of 16-B chunks
-template <int BN> __host__ __device__ constexpr int epi_stage_bytes() { return 128 * epi_pitch<BN>(); }
+template <int BN> __host__ __device__ constexpr int epi_blocks() { return (BN + 63) / 64; }
+template <int BN> __host__ __device__ constexpr int epi_stage_bytes() { return epi_blocks<BN>() * kEpiBlockBytes; }
+
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m), "r"(smem_u32(src)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(m),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 struct EpiTile {          // where the 128 accumulator rows go
   long long m0;           // FLAT: first row
   int tb, ty0, tx0;       // PATCH: image and patch origin
 };
 
-// row of the tile -> global row index, validity, pad flag and (b,y,x) for NCHW output
 struct EpiRow {
-  long long r;
   bool valid, pad;
   int b, y, x;
 };
 
-__device__ __forceinline__ EpiRow epi_row(const TapGemmKParams& p, const EpiTile& t, int row, bool want_yx) {
+__device__ __forceinline__ EpiRow epi_row(const TapGemmKParams& p, const EpiTile& t, int row) {
   EpiRow o;
   o.pad = false; o.b = o.y = o.x = 0;
   const int Hp = p.H + 1, Wp = p.W + 1;
   if (p.mode == BUCTD_TG_FLAT) {
-    o.r = t.m0 + row;
-    o.valid = o.r < p.m_rows;
-    if (want_yx && o.valid && p.out_mode != BUCTD_OUT_ROWS16) {
-      o.x = (int)(o.r % Wp);
-      const long long ry = o.r / Wp;
+    const long long r = t.m0 + row;
+    o.valid = r < p.m_rows;
+    if (o.valid && p.out_mode != BUCTD_OUT_ROWS16) {
+      o.x = (int)(r % Wp);
+      const long long ry = r / Wp;
       o.y = (int)(ry % Hp);
       o.b = (int)(ry / Hp);
       o.pad = (o.x == p.W) || (o.y == p.H);
@@ -48,114 +70,150 @@ __device__ __forceinline__ EpiRow epi_row(const TapGemmKParams& p, const EpiTile
     const int ty = row / p.tw, tx = row - ty * p.tw;
     o.y = t.ty0 + ty; o.x = t.tx0 + tx; o.b = t.tb;
     o.valid = (row < p.tw * p.th) && o.y < p.H && o.x < p.W;
-    o.r = ((long long)t.tb * Hp + o.y) * Wp + o.x;
   }
   return o;
 }
 
-// etid: 0..127 index among the epilogue threads; q = TMEM lane quarter of this warp; tmem_acc: TMEM
-// address (lane 0, first column) of this tile's accumulator.
+// issue the TMA load of the residual tile into `stage` (one elected thread); completes on `bar`
+template <int BN>
+__device__ __forceinline__ void epi_load_residual(const TapGemmKParams& p, const CUtensorMap* map_res, const EpiTile& t, int n0,
+                                                  uint8_t* stage, uint64_t* bar) {
+  constexpr int NB = epi_blocks<BN>();
+  int nblk = 0;
+  for (int blk = 0; blk < NB; ++blk)
+    if (n0 + blk * 64 < p.res_cs) ++nblk;
+  const uint32_t rows_bytes = (p.mode == BUCTD_TG_FLAT ? 128u : (uint32_t)(p.tw * p.th)) * 128u;
+  mbar_expect_tx(bar, nblk * rows_bytes);
+  for (int blk = 0; blk < nblk; ++blk) {
+    if (p.mode == BUCTD_TG_FLAT) tma_load_2d(stage + blk * kEpiBlockBytes, map_res, bar, n0 + blk * 64, (int)t.m0);
+    else tma_load_4d(stage + blk * kEpiBlockBytes, map_res, bar, n0 + blk * 64, t.tx0, t.ty0, t.tb);
+  }
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+
+template <typename T> __device__ __forceinline__ uint32_t relu2(uint32_t u);
+template <> __device__ __forceinline__ uint32_t relu2<__half>(uint32_t u) {
+  __half2 h = __hmax2(*reinterpret_cast<__half2*>(&u), __float2half2_rn(0.f));
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t relu2<__nv_bfloat16>(uint32_t u) {
+  __nv_bfloat162 h = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&u), __float2bfloat162_rn(0.f));
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// TMEM -> (+bias, +residual from stage, ReLU, mask) -> 16-bit -> stage (in place).  Work unit = 8
+// columns (one 16-byte chunk); warp group `grp` of `ngrp` takes every ngrp-th unit of its rows.  The
+// next unit's tcgen05.ld is issued before the current one is processed.
 template <typename T, int BN>
-__device__ void epilogue_tile(const TapGemmKParams& p, const EpiTile& tile, int n0, uint32_t tmem_acc, uint8_t* stage,
-                              int etid, int q, int lane) {
-  constexpr int PITCH = epi_pitch<BN>();
-  constexpr int CH = BN / 8;                       // 16-byte chunks per row
-  const T* res = reinterpret_cast<const T*>(p.residual);
+__device__ __forceinline__ void epi_compute(const TapGemmKParams& p, const EpiTile& tile, int n0, uint32_t tmem_acc,
+                                            uint8_t* stage, const float* s_bias, bool has_res, int q, int lane, int grp,
+                                            int ngrp) {
   const int row = q * 32 + lane;
-  const EpiRow me = epi_row(p, tile, row, true);
+  const EpiRow me = epi_row(p, tile, row);
+  const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
+  const bool zero = me.pad || !me.valid;
+  const int limit = p.n > p.out_cs ? p.n : p.out_cs;
+  int units = (min(limit - n0, BN) + 7) >> 3;              // 8-column units this tile really has
+  if (units <= grp) return;
+  uint8_t* srow = stage + row * 128;
+  const int sw = row & 7;
+  auto process = [&](int u, const uint32_t (&ac)[8]) {
+    const int c0 = u * 8;
+    uint4* a = reinterpret_cast<uint4*>(srow + (c0 >> 6) * kEpiBlockBytes + ((((c0 & 63) >> 3) ^ sw) << 4));
+    float v[8];
+    const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c0), b1 = *reinterpret_cast<const float4*>(s_bias + c0 + 4);
+    v[0] = __uint_as_float(ac[0]) + b0.x; v[1] = __uint_as_float(ac[1]) + b0.y;
+    v[2] = __uint_as_float(ac[2]) + b0.z; v[3] = __uint_as_float(ac[3]) + b0.w;
+    v[4] = __uint_as_float(ac[4]) + b1.x; v[5] = __uint_as_float(ac[5]) + b1.y;
+    v[6] = __uint_as_float(ac[6]) + b1.z; v[7] = __uint_as_float(ac[7]) + b1.w;
+    if (has_res) {
+      const uint4 r = *a;
+      const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = T16<T>::unpack2(w[j]);
+        v[2 * j] += f.x;
+        v[2 * j + 1] += f.y;
+      }
+    }
+    if (n0 + c0 + 8 > p.n) {                                // N tail (and the zero pad channels of act16)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (n0 + c0 + j >= p.n) v[j] = 0.f;
+    }
+    uint4 o;
+    o.x = T16<T>::pack2(v[0], v[1]); o.y = T16<T>::pack2(v[2], v[3]);
+    o.z = T16<T>::pack2(v[4], v[5]); o.w = T16<T>::pack2(v[6], v[7]);
+    if (p.relu) { o.x = relu2<T>(o.x); o.y = relu2<T>(o.y); o.z = relu2<T>(o.z); o.w = relu2<T>(o.w); }
+    if (zero) o = make_uint4(0, 0, 0, 0);
+    *a = o;
+  };
+  uint32_t acc_a[8], acc_b[8];
+  int u = grp;
+  tmem_ld8(taddr + u * 8, acc_a);
+  while (true) {
+    tmem_ld_wait();
+    if (u + ngrp < units) tmem_ld8(taddr + (u + ngrp) * 8, acc_b);
+    process(u, acc_a);
+    u += ngrp;
+    if (u >= units) break;
+    tmem_ld_wait();
+    if (u + ngrp < units) tmem_ld8(taddr + (u + ngrp) * 8, acc_a);
+    process(u, acc_b);
+    u += ngrp;
+    if (u >= units) break;
+  }
+}
 
-  if (p.out_mode == BUCTD_OUT_NCHW32) {            // small-N head: fp32 planes, coalesced across the warp's pixels
-    const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      const int nb = n0 + c0;
-      if (nb >= p.n) break;
-      uint32_t acc[16];
-      tmem_ld16(taddr + c0, acc);
-      tmem_ld_wait();
-      if (!me.valid || me.pad) continue;
-      float* o = reinterpret_cast<float*>(p.out);
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (nb + j < p.n) {
-          float v = __uint_as_float(acc[j]) + (p.bias ? __ldg(p.bias + nb + j) : 0.f);
-          if (p.relu) v = fmaxf(v, 0.f);
-          o[(((long long)me.b * p.n + nb + j) * p.H + me.y) * p.W + me.x] = v;
-        }
-    }
-    return;
+// one elected thread: TMA-store the staged tile (one bulk group)
+template <int BN>
+__device__ __forceinline__ void epi_store(const TapGemmKParams& p, const CUtensorMap* map_out, const EpiTile& t, int n0,
+                                          const uint8_t* stage) {
+  constexpr int NB = epi_blocks<BN>();
+  for (int blk = 0; blk < NB; ++blk) {
+    if (n0 + blk * 64 >= p.out_cs) break;
+    if (p.mode == BUCTD_TG_FLAT) tma_store_2d(map_out, stage + blk * kEpiBlockBytes, n0 + blk * 64, (int)t.m0);
+    else tma_store_4d(map_out, stage + blk * kEpiBlockBytes, n0 + blk * 64, t.tx0, t.ty0, t.tb);
   }
+  tma_store_commit();
+}
 
-  // ---- 1. residual tile -> stage (coalesced) ------------------------------------------------------
-  if (res != nullptr) {
+// small-N head: fp32 planes [B][N][H][W], written straight from registers (coalesced across the
+// warp's consecutive pixels).  No staging.
+template <int BN>
+__device__ __forceinline__ void epi_head_nchw32(const TapGemmKParams& p, const EpiTile& tile, int n0, uint32_t tmem_acc, int q,
+                                                int lane) {
+  const int row = q * 32 + lane;
+  const EpiRow me = epi_row(p, tile, row);
+  const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-    for (int g = etid; g < 128 * CH; g += kEpiThreads) {
-      const int rr = g / CH, ch = g - rr * CH;
-      const EpiRow er = epi_row(p, tile, rr, false);
-      uint4 v = make_uint4(0, 0, 0, 0);
-      const int col = n0 + ch * 8;
-      if (er.valid && col + 8 <= p.res_cs && col < p.n) v = *reinterpret_cast<const uint4*>(res + er.r * p.res_cs + col);
-      *reinterpret_cast<uint4*>(stage + rr * PITCH + ch * 16) = v;
-    }
-    epi_sync();
-  }
-  // ---- 2. own row: TMEM -> bias/residual/ReLU/mask -> 16 bit -> stage -----------------------------
-  {
-    const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
-    uint8_t* srow = stage + row * PITCH;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      const int nb = n0 + c0;
-      if (nb >= p.n && nb >= p.out_cs) break;       // warp-uniform
-      uint32_t acc[16];
-      tmem_ld16(taddr + c0, acc);
-      tmem_ld_wait();
-      float v[16];
+  for (int c0 = 0; c0 < BN; c0 += 16) {
+    const int nb = n0 + c0;
+    if (nb >= p.n) break;
+    uint32_t acc[16];
+    tmem_ld16(taddr + c0, acc);
+    tmem_ld_wait();
+    if (!me.valid || me.pad) continue;
+    float* o = reinterpret_cast<float*>(p.out);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        v[j] = __uint_as_float(acc[j]);
-        if (p.bias != nullptr && nb + j < p.n) v[j] += __ldg(p.bias + nb + j);
+    for (int j = 0; j < 16; ++j)
+      if (nb + j < p.n) {
+        float v = __uint_as_float(acc[j]) + (p.bias ? __ldg(p.bias + nb + j) : 0.f);
+        if (p.relu) v = fmaxf(v, 0.f);
+        o[(((long long)me.b * p.n + nb + j) * p.H + me.y) * p.W + me.x] = v;
       }
-      if (res != nullptr) {
-        const uint4 u0 = *reinterpret_cast<const uint4*>(srow + c0 * 2);
-        const uint4 u1 = *reinterpret_cast<const uint4*>(srow + c0 * 2 + 16);
-        const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float2 f = T16<T>::unpack2(w[j]);
-          v[2 * j] += f.x;
-          v[2 * j + 1] += f.y;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (p.relu) v[j] = fmaxf(v[j], 0.f);
-        if (me.pad || nb + j >= p.n) v[j] = 0.f;
-      }
-      uint4 u0, u1;
-      u0.x = T16<T>::pack2(v[0], v[1]);   u0.y = T16<T>::pack2(v[2], v[3]);
-      u0.z = T16<T>::pack2(v[4], v[5]);   u0.w = T16<T>::pack2(v[6], v[7]);
-      u1.x = T16<T>::pack2(v[8], v[9]);   u1.y = T16<T>::pack2(v[10], v[11]);
-      u1.z = T16<T>::pack2(v[12], v[13]); u1.w = T16<T>::pack2(v[14], v[15]);
-      *reinterpret_cast<uint4*>(srow + c0 * 2) = u0;
-      *reinterpret_cast<uint4*>(srow + c0 * 2 + 16) = u1;
-    }
   }
-  epi_sync();
-  // ---- 3. stage -> global (coalesced 16-byte stores, rows are contiguous in global memory) ---------
-  {
-    T* out = reinterpret_cast<T*>(p.out);
-#pragma unroll 1
-    for (int g = etid; g < 128 * CH; g += kEpiThreads) {
-      const int rr = g / CH, ch = g - rr * CH;
-      const int col = n0 + ch * 8;
-      if (col + 8 > p.out_cs) continue;
-      const EpiRow er = epi_row(p, tile, rr, false);
-      if (!er.valid) continue;
-      *reinterpret_cast<uint4*>(out + er.r * p.out_cs + col) = *reinterpret_cast<const uint4*>(stage + rr * PITCH + ch * 16);
-    }
-  }
-  epi_sync();      // stage may be reused by the next tile
+}
+
+// bias tile -> shared memory (NT epilogue threads, no sync inside)
+template <int BN, int NT>
+__device__ __forceinline__ void epi_load_bias(const TapGemmKParams& p, int n0, float* s_bias, int etid) {
+  for (int i = etid; i < BN; i += NT) s_bias[i] = (p.bias != nullptr && n0 + i < p.n) ? __ldg(p.bias + n0 + i) : 0.f;
 }
 
 }  // namespace buctd

@@ -35,6 +35,7 @@ struct SlabParams {
   int halo;          // slab rows loaded before/after the super-tile (W+2 for 3x3, 0 for 1x1)
   int nboxes, box_rows, slab_bytes;
   int sa, sw;        // slab ring / weight ring depth
+  int stage_bufs;    // epilogue stage buffers (2: residual prefetch + store overlap)
   int w_resident, w_tiles;
   int num_super, num_items;
   int tmem_cols, smem_bytes;
@@ -45,6 +46,8 @@ struct SlabParams {
 struct TapGemmLaunch {
   alignas(64) CUtensorMap map_a;
   alignas(64) CUtensorMap map_b;
+  alignas(64) CUtensorMap map_out;   // 16-bit output tile store (unused for the fp32 head)
+  alignas(64) CUtensorMap map_res;   // residual tile load (copy of map_out when there is no residual)
   TapGemmKParams kp;
   SlabParams sp;
   dim3 grid;

@@ -27,9 +27,25 @@
 
 namespace buctd {
 
+// Optional role timers (debug builds: -DBUCTD_ROLE_TIMERS): cycles each warp role spends waiting / working,
+// written to a global buffer [grid][8] that tools/role_timers.py reads back.
+#ifdef BUCTD_ROLE_TIMERS
+__device__ unsigned long long g_role_cycles[160 * 8];
+#define RT_DECL(name) long long name = 0
+#define RT_BEGIN(t) const long long t = clock64()
+#define RT_ADD(acc, t) acc += clock64() - t
+#define RT_STORE(slot, v) g_role_cycles[blockIdx.x * 8 + (slot)] = (unsigned long long)(v)
+#else
+#define RT_DECL(name)
+#define RT_BEGIN(t)
+#define RT_ADD(acc, t)
+#define RT_STORE(slot, v)
+#endif
+
 constexpr int kBlockM = 128;
 constexpr int kATileBytes = kBlockM * 128;
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;          // patch kernel: producer + MMA + 4 epilogue warps
+constexpr int kSlabThreads = 320;      // slab kernel: producer + MMA + 8 epilogue warps (2 per TMEM lane quarter)
 constexpr int kSmemBudget = 227 * 1024;
 
 template <int BN> __host__ __device__ constexpr int patch_stages() { return BN <= 128 ? 4 : 3; }
@@ -40,6 +56,7 @@ template <int BN> __host__ __device__ constexpr int patch_stages() { return BN <
 template <typename T, int BN>
 __global__ void __launch_bounds__(kThreads)
 tapgemm_patch_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                     const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
                      const TapGemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -47,16 +64,19 @@ tapgemm_patch_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   constexpr int kBTileBytes = BN * 128;
   constexpr int kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + S * kATileBytes;
+  uint8_t* smem_b = smem + S * kATileBytes;                  // BN*128 is a multiple of 1024 for BN % 8 == 0
   uint8_t* stage = smem_b + S * kBTileBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage + epi_stage_bytes<BN>());
+  float* s_bias = reinterpret_cast<float*>(stage + epi_stage_bytes<BN>());
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_bias + BN);
   uint64_t* empty_bar = full_bar + S;
   uint64_t* tmem_full_bar = empty_bar + S;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* res_bar = tmem_full_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * BN;
+  const bool has_res = p.residual != nullptr;
 
   EpiTile tile;
   tile.m0 = 0;
@@ -72,11 +92,13 @@ tapgemm_patch_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&map_out);
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
+    mbar_init(res_bar, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
@@ -88,6 +110,7 @@ tapgemm_patch_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 
   if (warp == 0) {
     if (lane == 0) {
+      if (has_res) epi_load_residual<BN>(p, &map_res, tile, n0, stage, res_bar);
       for (int it = 0; it < iters; ++it) {
         const int s = it % S;
         const int t = it / p.num_kc;
@@ -102,26 +125,41 @@ tapgemm_patch_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(T16<T>::kFmt, kBlockM, BN);
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % S;
-        const int kc = it % p.num_kc;
-        mbar_wait(&full_bar[s], (it / S) & 1);
-        tc_fence_after();
-        const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + s * kATileBytes));
-        const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + s * kBTileBytes));
-        const int ksteps = min(64, p.k16 - kc * 64) >> 4;
-        for (int k = 0; k < ksteps; ++k)
-          tc_mma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (it | k) != 0);
+    const uint32_t idesc = umma_idesc_f16(T16<T>::kFmt, kBlockM, BN);
+    const uint32_t a_addr = smem_u32(smem_a), b_addr = smem_u32(smem_b);
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % S;
+      const int kc = it % p.num_kc;
+      mbar_wait(&full_bar[s], (it / S) & 1);
+      tc_fence_after();
+      const uint64_t adesc = umma_desc_sw128(a_addr + s * kATileBytes);
+      const uint64_t bdesc = umma_desc_sw128(b_addr + s * kBTileBytes);
+      const int ksteps = min(64, p.k16 - kc * 64) >> 4;
+      if (elect_one()) {
+        tc_mma_f16(tmem_base, adesc, bdesc, idesc, it != 0 ? 1u : 0u);
+        if (ksteps > 1) tc_mma_f16(tmem_base, adesc + 2, bdesc + 2, idesc, 1u);
+        if (ksteps > 2) tc_mma_f16(tmem_base, adesc + 4, bdesc + 4, idesc, 1u);
+        if (ksteps > 3) tc_mma_f16(tmem_base, adesc + 6, bdesc + 6, idesc, 1u);
         tc_commit(&empty_bar[s]);
       }
-      tc_commit(tmem_full_bar);
+      __syncwarp();
     }
+    if (elect_one()) tc_commit(tmem_full_bar);
+    __syncwarp();
   } else {
+    const int etid = threadIdx.x - 64;
+    epi_load_bias<BN, 128>(p, n0, s_bias, etid);
+    epi_sync<128>();
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    epilogue_tile<T, BN>(p, tile, n0, tmem_base, stage, threadIdx.x - 64, warp & 3, lane);
+    if (has_res) mbar_wait(res_bar, 0);
+    epi_compute<T, BN>(p, tile, n0, tmem_base, stage, s_bias, has_res, warp & 3, lane, 0, 1);
+    fence_proxy_async_smem();
+    epi_sync<128>();
+    if (etid == 0) {
+      epi_store<BN>(p, &map_out, tile, n0, stage);
+      tma_store_wait_all();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -131,24 +169,40 @@ tapgemm_patch_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 // =================================================================================================
 // SLAB kernel (FLAT mode): persistent, A-slab + row-shifted tap views, double-buffered accumulators
 // =================================================================================================
-template <typename T, int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+// all MMAs of one (tap, chunk): MSUB sub-tiles x KS k-steps, fully unrolled so every descriptor is
+// adesc0/bdesc plus an immediate (no dependent address arithmetic between tcgen05.mma issues)
+template <int BN, int MSUB, int KS>
+__device__ __forceinline__ void mma_batch(uint32_t d0, uint64_t adesc0, uint64_t bdesc, uint32_t idesc, uint32_t first) {
+#pragma unroll
+  for (int j = 0; j < MSUB; ++j) {
+#pragma unroll
+    for (int k = 0; k < KS; ++k)
+      tc_mma_f16(d0 + j * BN, adesc0 + (uint64_t)(j * (kBlockM * 128 / 16) + 2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                 k == 0 ? first : 1u);
+  }
+}
+
+template <typename T, int BN, int MSUB>
+__global__ void __launch_bounds__(kSlabThreads, 1)
 tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
                     const TapGemmKParams p, const SlabParams sp) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kWTileBytes = BN * 128;
   uint8_t* slabs = smem;                                         // [sa][slab_bytes]
   uint8_t* wbuf = slabs + (size_t)sp.sa * sp.slab_bytes;         // resident: [num_kc*ntaps] tiles; ring: [sw] tiles
-  uint8_t* stage = wbuf + (size_t)sp.w_tiles * kWTileBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage + epi_stage_bytes<BN>());
+  uint8_t* stage = wbuf + (size_t)sp.w_tiles * kWTileBytes;       // [stage_bufs][epi_stage_bytes]
+  float* s_bias = reinterpret_cast<float*>(stage + (size_t)sp.stage_bufs * epi_stage_bytes<BN>());
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + BN);
   uint64_t* slab_full = bars;                 // [sa]
   uint64_t* slab_empty = slab_full + 4;       // [sa]
   uint64_t* w_full = slab_empty + 4;          // [sw] (resident: [0] only)
   uint64_t* w_empty = w_full + 8;             // [sw]
   uint64_t* acc_full = w_empty + 8;           // [2]
   uint64_t* acc_empty = acc_full + 2;         // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* res_bar = acc_empty + 2;          // [2] residual tile landed in stage buffer e
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -158,7 +212,8 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     tma_prefetch_desc(&map_b);
     for (int s = 0; s < 4; ++s) { mbar_init(&slab_full[s], 1); mbar_init(&slab_empty[s], 1); }
     for (int s = 0; s < 8; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); mbar_init(&res_bar[s], 1); }
+    tma_prefetch_desc(&map_out);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, sp.tmem_cols);
@@ -166,7 +221,7 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int R = sp.msub * kBlockM;
+  const int R = MSUB * kBlockM;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -202,70 +257,145 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // One elected lane runs the whole MMA role (elect.sync lets ptxas keep every descriptor in
+    // uniform registers: ~2 SASS instructions per tcgen05.mma).
+    if (elect_one()) {
       const uint32_t idesc = umma_idesc_f16(T16<T>::kFmt, kBlockM, BN);
       uint32_t sa_it = 0, sw_it = 0, it_local = 0;
+      RT_DECL(t_acc); RT_DECL(t_slab); RT_DECL(t_w); RT_DECL(t_total); RT_DECL(t_issue); RT_DECL(t_commit);
+      RT_BEGIN(t_start);
+      const uint32_t slab0_addr = smem_u32(slabs);
+      const uint32_t wbuf_addr = smem_u32(wbuf);
+      int tap_shift[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) tap_shift[t] = sp.halo + (p.ntaps == 9 ? (t / 3 - 1) * p.wp + (t % 3 - 1) : 0);
       if (sp.w_resident) { mbar_wait(&w_full[0], 0); }
       for (int item = blockIdx.x; item < sp.num_items; item += gridDim.x, ++it_local) {
         const uint32_t buf = it_local & 1;
-        mbar_wait(&acc_empty[buf], ((it_local >> 1) & 1) ^ 1);
+        { RT_BEGIN(t0); mbar_wait(&acc_empty[buf], ((it_local >> 1) & 1) ^ 1); RT_ADD(t_acc, t0); }
         tc_fence_after();
+        const uint32_t d0 = tmem_base + buf * MSUB * BN;
         for (int kc = 0; kc < p.num_kc; ++kc) {
           const uint32_t slot = sa_it % sp.sa;
-          mbar_wait(&slab_full[slot], (sa_it / sp.sa) & 1);
+          { RT_BEGIN(t0); mbar_wait(&slab_full[slot], (sa_it / sp.sa) & 1); RT_ADD(t_slab, t0); }
           tc_fence_after();
-          const uint32_t slab_addr = smem_u32(slabs + (size_t)slot * sp.slab_bytes);
+          const uint32_t slab_addr = slab0_addr + slot * (uint32_t)sp.slab_bytes;
           const int ksteps = min(64, p.k16 - kc * 64) >> 4;
-          for (int t = 0; t < p.ntaps; ++t) {
-            uint32_t w_addr;
-            uint32_t ws = 0;
-            if (sp.w_resident) {
-              w_addr = smem_u32(wbuf + (size_t)(kc * p.ntaps + t) * kWTileBytes);
-            } else {
-              ws = sw_it % sp.sw;
-              mbar_wait(&w_full[ws], (sw_it / sp.sw) & 1);
-              tc_fence_after();
-              w_addr = smem_u32(wbuf + (size_t)ws * kWTileBytes);
+          RT_BEGIN(t_i0);
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            if (t < p.ntaps) {
+              uint32_t w_addr;
+              uint32_t ws = 0;
+              if (sp.w_resident) {
+                w_addr = wbuf_addr + (uint32_t)(kc * p.ntaps + t) * kWTileBytes;
+              } else {
+                ws = sw_it % sp.sw;
+                { RT_BEGIN(t0); mbar_wait(&w_full[ws], (sw_it / sp.sw) & 1); RT_ADD(t_w, t0); }
+                tc_fence_after();
+                w_addr = wbuf_addr + ws * kWTileBytes;
+              }
+              const uint64_t bdesc = umma_desc_sw128(w_addr);
+              const uint64_t adesc0 = umma_desc_sw128(slab_addr + (uint32_t)tap_shift[t] * 128);
+              const uint32_t first = (kc | t) == 0 ? 0u : 1u;
+              switch (ksteps) {
+                case 1: mma_batch<BN, MSUB, 1>(d0, adesc0, bdesc, idesc, first); break;
+                case 2: mma_batch<BN, MSUB, 2>(d0, adesc0, bdesc, idesc, first); break;
+                case 3: mma_batch<BN, MSUB, 3>(d0, adesc0, bdesc, idesc, first); break;
+                default: mma_batch<BN, MSUB, 4>(d0, adesc0, bdesc, idesc, first); break;
+              }
+              if (!sp.w_resident) { tc_commit(&w_empty[ws]); ++sw_it; }
             }
-            const uint64_t bdesc = umma_desc_sw128(w_addr);
-            int shift = sp.halo;
-            if (p.ntaps == 9) shift += (t / 3 - 1) * p.wp + (t % 3 - 1);
-            for (int j = 0; j < sp.msub; ++j) {
-              const uint32_t row_off = (uint32_t)(shift + j * kBlockM);
-              uint64_t adesc = umma_desc_sw128(slab_addr + row_off * 128);
-              if (sp.desc_mode == 1) adesc |= (uint64_t)(row_off & 7) << 49;
-              const uint32_t d = tmem_base + (buf * sp.msub + j) * BN;
-              for (int k = 0; k < ksteps; ++k)
-                tc_mma_f16(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | t | k) != 0);
-            }
-            if (!sp.w_resident) { tc_commit(&w_empty[ws]); ++sw_it; }
           }
+          RT_ADD(t_issue, t_i0);
           tc_commit(&slab_empty[slot]);
           ++sa_it;
         }
         tc_commit(&acc_full[buf]);
       }
+      RT_ADD(t_total, t_start);
+      RT_STORE(0, t_total); RT_STORE(1, t_acc); RT_STORE(2, t_slab); RT_STORE(3, t_w); RT_STORE(6, t_issue); RT_STORE(7, t_commit);
     }
+    __syncwarp();
   } else {
     const int etid = threadIdx.x - 64;
+    RT_DECL(e_wait); RT_DECL(e_total);
+    RT_BEGIN(e_start);
     const int q = warp & 3;
-    uint32_t it_local = 0;
-    for (int item = blockIdx.x; item < sp.num_items; item += gridDim.x, ++it_local) {
-      const int s = item % sp.num_super, nt = item / sp.num_super;
-      const uint32_t buf = it_local & 1;
-      mbar_wait(&acc_full[buf], (it_local >> 1) & 1);
-      tc_fence_after();
-      for (int j = 0; j < sp.msub; ++j) {
-        EpiTile tile;
-        tile.m0 = (long long)s * R + (long long)j * kBlockM;
-        tile.tb = tile.ty0 = tile.tx0 = 0;
-        if (tile.m0 >= p.m_rows) break;                                    // uniform
-        epilogue_tile<T, BN>(p, tile, nt * BN, tmem_base + (buf * sp.msub + j) * BN, stage, etid, q, lane);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    const int grp = (warp - 2) >> 2;          // 0: warps 2..5, 1: warps 6..9
+    const bool has_res = p.residual != nullptr;
+    const bool head = p.out_mode == BUCTD_OUT_NCHW32;
+    const int SE = sp.stage_bufs;
+    const int my_items = (sp.num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total_u = my_items * MSUB;
+    // sub-tile u of this CTA -> tile origin and N tile
+    auto sub = [&](int u, EpiTile& t, int& nt) {
+      const int k = u / MSUB, j = u - k * MSUB;
+      const int item = blockIdx.x + k * gridDim.x;
+      const int s = item % sp.num_super;
+      nt = item / sp.num_super;
+      t.m0 = (long long)s * R + (long long)j * kBlockM;
+      t.tb = t.ty0 = t.tx0 = 0;
+    };
+    if (has_res && etid == 0 && total_u > 0) {
+      EpiTile t0; int nt0;
+      sub(0, t0, nt0);
+      epi_load_residual<BN>(p, &map_res, t0, nt0 * BN, stage, &res_bar[0]);
     }
+    int cur_nt = -1;
+    for (int u = 0; u < total_u; ++u) {
+      const int k = u / MSUB, j = u - k * MSUB;
+      const uint32_t buf = k & 1;
+      const int e = SE == 2 ? (u & 1) : 0;
+      uint8_t* st = stage + (size_t)e * epi_stage_bytes<BN>();
+      EpiTile tile; int nt;
+      sub(u, tile, nt);
+      if (nt != cur_nt) {                      // (re)load the bias tile of this N tile
+        epi_sync<256>();
+        epi_load_bias<BN, 256>(p, nt * BN, s_bias, etid);
+        cur_nt = nt;
+        epi_sync<256>();
+      }
+      if (j == 0) {
+        RT_BEGIN(t0); mbar_wait(&acc_full[buf], (k >> 1) & 1); RT_ADD(e_wait, t0);
+        tc_fence_after();
+      }
+      const uint32_t acc = tmem_base + (buf * MSUB + j) * BN;
+      if (head) {
+        if (grp == 0) epi_head_nchw32<BN>(p, tile, nt * BN, acc, q, lane);
+      } else {
+        if (etid == 0) {
+          // stores are committed one group per sub-tile, in order.  SE == 2: store(u-1) (other buffer) must have
+          // been read before the residual of u+1 lands there; SE == 1: store(u-1) used this very buffer.
+          tma_store_wait_read<0>();
+          if (has_res) {
+            if (SE == 2) {
+              if (u + 1 < total_u) {
+                EpiTile tn; int ntn;
+                sub(u + 1, tn, ntn);
+                epi_load_residual<BN>(p, &map_res, tn, ntn * BN, stage + (size_t)(e ^ 1) * epi_stage_bytes<BN>(), &res_bar[e ^ 1]);
+              }
+            } else if (u > 0) {
+              epi_load_residual<BN>(p, &map_res, tile, nt * BN, st, &res_bar[0]);
+            }
+          }
+        }
+        if (SE == 1 && !has_res) epi_sync<256>();   // nobody may overwrite the stage before store(u-1) has been read
+        if (has_res) mbar_wait(&res_bar[e], (SE == 2 ? (u >> 1) : u) & 1);
+        epi_compute<T, BN>(p, tile, nt * BN, acc, st, s_bias, has_res, q, lane, grp, 2);
+        fence_proxy_async_smem();
+        epi_sync<256>();
+        if (etid == 0) epi_store<BN>(p, &map_out, tile, nt * BN, st);
+      }
+      if (j == MSUB - 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      }
+    }
+    if (etid == 0) tma_store_wait_all();
+    RT_ADD(e_total, e_start);
+    if (threadIdx.x == 64) { RT_STORE(4, e_total); RT_STORE(5, e_wait); }
   }
   tc_fence_before();
   __syncthreads();
@@ -273,17 +403,28 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 }
 
 // ---- host side --------------------------------------------------------------------------------
+static int stage_bytes(int bn) { return (bn + 63) / 64 * kEpiBlockBytes; }
 static size_t patch_smem_bytes(int bn) {
   const int s = bn <= 128 ? 4 : 3;
-  return 1024 + (size_t)s * (kATileBytes + bn * 128) + 128 * (bn * 2 + 16) + 256;
+  return 1024 + (size_t)s * (kATileBytes + bn * 128) + stage_bytes(bn) + bn * 4 + 256;
 }
 
+template <typename T, int BN, int MSUB>
+static int set_attr_slab() {
+  if constexpr (2 * MSUB * BN <= 512) {
+    BUCTD_CUDA(cudaFuncSetAttribute(tapgemm_slab_kernel<T, BN, MSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+  }
+  return BUCTD_OK;
+}
 template <typename T, int BN>
 static int set_attr() {
   BUCTD_CUDA(cudaFuncSetAttribute(tapgemm_patch_kernel<T, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)patch_smem_bytes(BN)));
-  BUCTD_CUDA(cudaFuncSetAttribute(tapgemm_slab_kernel<T, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-  return BUCTD_OK;
+  int rc;
+  if ((rc = set_attr_slab<T, BN, 1>())) return rc;
+  if ((rc = set_attr_slab<T, BN, 2>())) return rc;
+  if ((rc = set_attr_slab<T, BN, 3>())) return rc;
+  return set_attr_slab<T, BN, 4>();
 }
 template <typename T>
 static int set_attrs() {
@@ -336,14 +477,15 @@ static void pick_patch_tile(int oh, int ow, int* tw, int* th) {
 static int plan_slab(const buctd_tapgemm_args& a, int bn, int n_tiles, int num_kc, int sm_count, SlabParams* sp) {
   const int halo = a.ntaps == 9 ? a.out_w + 2 : 0;        // (W+1) + 1 rows on each side
   const int wtile = bn * 128;
-  const int fixed = 1024 + 128 * (bn * 2 + 16) + 512;     // alignment slack + epilogue stage + barriers
+  const int stage = stage_bytes(bn);
+  const int fixed = 1024 + bn * 4 + 512;                  // alignment slack + bias tile + barriers
   const long long total_w = (long long)a.ntaps * num_kc * wtile;
   const bool resident = n_tiles == 1 && total_w <= 80 * 1024;
+  const char* force = getenv("BUCTD_FORCE_MSUB");         // test knob: pin the super-tile size
+  const int forced = force ? atoi(force) : 0;
   bool have = false;
   SlabParams best;
   memset(&best, 0, sizeof(best));
-  const char* force = getenv("BUCTD_FORCE_MSUB");         // test knob: pin the super-tile size
-  const int forced = force ? atoi(force) : 0;
   for (int msub = 4; msub >= 1; --msub) {
     if (2 * msub * bn > 512) continue;                    // two accumulator sets in TMEM
     if (forced > 0 && msub > forced) continue;
@@ -351,23 +493,22 @@ static int plan_slab(const buctd_tapgemm_args& a, int bn, int n_tiles, int num_k
     const int nboxes = ceil_div(rows, 256);
     const int box_rows = (ceil_div(rows, nboxes) + 7) / 8 * 8;   // every box starts on a 1024-byte swizzle atom
     const long long slab = (long long)nboxes * box_rows * 128;
-    int sw = resident ? 0 : 4;
-    int sa = 0;
+    // preference order: two stage buffers, deep rings; then thinner weight ring; then one stage buffer
+    int sa = 0, sw = 0, se = 0;
     long long need = 0;
-    for (; sa == 0 && (resident || sw >= 2); --sw) {
-      for (int c = (num_kc > 1 ? 3 : 2); c >= 2; --c) {
-        need = fixed + c * slab + (resident ? total_w : (long long)sw * wtile);
-        if (need <= kSmemBudget) { sa = c; break; }
-      }
-      if (resident) break;
-    }
+    const int sa_max = num_kc > 1 ? 3 : 2;
+    for (int cse = 2; cse >= 1 && sa == 0; --cse)
+      for (int csw = resident ? 0 : 4; (resident ? csw == 0 : csw >= 2) && sa == 0; --csw)
+        for (int csa = sa_max; csa >= 2; --csa) {
+          need = fixed + (long long)cse * stage + csa * slab + (resident ? total_w : (long long)csw * wtile);
+          if (need <= kSmemBudget) { sa = csa; sw = csw; se = cse; break; }
+        }
     if (sa == 0) continue;
-    if (!resident) ++sw;                                  // undo the loop's last decrement
     SlabParams c;
     memset(&c, 0, sizeof(c));
     const long long supers = (a.m_rows + (long long)msub * 128 - 1) / ((long long)msub * 128);
     c.msub = msub; c.halo = halo; c.nboxes = nboxes; c.box_rows = box_rows; c.slab_bytes = (int)slab;
-    c.sa = sa; c.sw = sw; c.w_resident = resident; c.w_tiles = resident ? a.ntaps * num_kc : sw;
+    c.sa = sa; c.sw = sw; c.stage_bufs = se; c.w_resident = resident; c.w_tiles = resident ? a.ntaps * num_kc : sw;
     c.num_super = (int)supers; c.num_items = (int)supers * n_tiles; c.smem_bytes = (int)need;
     const int cols = 2 * msub * bn;
     c.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
@@ -383,12 +524,24 @@ static int plan_slab(const buctd_tapgemm_args& a, int bn, int n_tiles, int num_k
   return BUCTD_OK;
 }
 
+template <typename T, int BN, int MSUB>
+static void launch_slab(const TapGemmLaunch& L, cudaStream_t st) {
+  if constexpr (2 * MSUB * BN <= 512) {
+    tapgemm_slab_kernel<T, BN, MSUB><<<L.grid, kSlabThreads, L.sp.smem_bytes, st>>>(L.map_a, L.map_b, L.map_out, L.map_res, L.kp, L.sp);
+  }
+}
+
 template <typename T, int BN>
 static int launch_one(const TapGemmLaunch& L, cudaStream_t st) {
   if (L.kp.mode == BUCTD_TG_PATCH) {
-    tapgemm_patch_kernel<T, BN><<<L.grid, kThreads, patch_smem_bytes(BN), st>>>(L.map_a, L.map_b, L.kp);
+    tapgemm_patch_kernel<T, BN><<<L.grid, kThreads, patch_smem_bytes(BN), st>>>(L.map_a, L.map_b, L.map_out, L.map_res, L.kp);
   } else {
-    tapgemm_slab_kernel<T, BN><<<L.grid, kThreads, L.sp.smem_bytes, st>>>(L.map_a, L.map_b, L.kp, L.sp);
+    switch (L.sp.msub) {
+      case 1: launch_slab<T, BN, 1>(L, st); break;
+      case 2: launch_slab<T, BN, 2>(L, st); break;
+      case 3: launch_slab<T, BN, 3>(L, st); break;
+      default: launch_slab<T, BN, 4>(L, st); break;
+    }
   }
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;
@@ -489,9 +642,43 @@ int tapgemm_prepare(const buctd_tapgemm_args& a, TapGemmLaunch* L, int sm_count)
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     BUCTD_CHECK(cr == CUDA_SUCCESS, BUCTD_ERR_CUDA, "cuTensorMapEncodeTiled(W) failed: %d", (int)cr);
   }
+  // output / residual tile maps: [64 channels x 128 rows] SWIZZLE_128B boxes of the same row geometry as the tile
+  L->map_out = L->map_a;
+  L->map_res = L->map_a;
+  if (a.out_mode != BUCTD_OUT_NCHW32) {
+    for (int which = 0; which < 2; ++which) {
+      void* base = which == 0 ? a.out : const_cast<void*>(a.residual);
+      const int cs = which == 0 ? a.out_cs : a.res_cs;
+      CUtensorMap* m = which == 0 ? &L->map_out : &L->map_res;
+      if (base == nullptr) { *m = L->map_out; continue; }
+      if (a.mode == BUCTD_TG_FLAT) {
+        cuuint64_t dims[2] = {(cuuint64_t)cs, (cuuint64_t)a.m_rows};
+        cuuint64_t strides[1] = {(cuuint64_t)cs * 2};
+        cuuint32_t box[2] = {64, kBlockM};
+        cuuint32_t es[2] = {1, 1};
+        cr = enc(m, dt, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      } else {
+        const cuuint64_t wp = a.out_w + 1, hp = a.out_h + 1;
+        cuuint64_t dims[4] = {(cuuint64_t)cs, wp, hp, (cuuint64_t)a.batch};
+        cuuint64_t strides[3] = {(cuuint64_t)cs * 2, wp * cs * 2, hp * wp * cs * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)kp.tw, (cuuint32_t)kp.th, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        cr = enc(m, dt, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      }
+      BUCTD_CHECK(cr == CUDA_SUCCESS, BUCTD_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed: %d", which ? "residual" : "out", (int)cr);
+    }
+  }
   L->kp = kp; L->grid = grid; L->bn = bn; L->dtype = a.dtype;
   return BUCTD_OK;
 }
+
+#ifdef BUCTD_ROLE_TIMERS
+extern "C" __attribute__((visibility("default"))) int buctd_debug_role_cycles(unsigned long long* out, int n) {
+  return (int)cudaMemcpyFromSymbol(out, g_role_cycles, sizeof(unsigned long long) * n);
+}
+#endif
 
 int tapgemm_launch(const TapGemmLaunch& L, cudaStream_t st) {
   if (L.dtype == BUCTD_F16) return dispatch_bn<__half>(L, st);
