@@ -60,23 +60,38 @@ class ClockSampler:
         self.gpu = gpu_index
 
     def start(self):
+        """started before the warm-up (nvidia-smi needs ~0.5 s to produce its first sample); only samples whose
+        arrival time falls inside [mark_begin, mark_end] are reported"""
+        self.t0 = self.t1 = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.gpu), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
         self.proc.terminate()
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t) + 0.06]
+        window = "timed region"
+        if len(inside) < 2:                      # very short run: fall back to every sample taken under load
+            inside = [r for t, r in self.rows if self.t0 is None or t >= self.t0 - 1.0]
+            window = "warm-up + timed region"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except (ValueError, IndexError):
@@ -85,7 +100,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def make_inputs(torch, cfg, batch, device, seed):
@@ -127,14 +142,14 @@ def run_native(args):
     net = net.cuda().eval()
     x, center, scale = make_inputs(torch, cfg, B, device, 1234 + rank)
     K = cfg.MODEL.NUM_JOINTS
-    gathered = [torch.empty(B, K, 3, device=device) for _ in range(world)] if world > 1 else None
+    from buctd_b200.distributed import gather_keypoints
 
     def step(xin):
         hm = net(xin)
         preds, maxvals = inference.decode_device(hm, center, scale, post_process=True)
         res = torch.cat([preds, maxvals], -1)                 # [B,K,3] = 204 B per crop
         if world > 1:                                          # the ONE collective: decoded keypoints only
-            dist.all_gather(gathered, res)
+            return gather_keypoints(res, B * world)
         return res
 
     def barrier():
@@ -142,22 +157,24 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     with torch.no_grad():
         for _ in range(max(args.warmup, 3)):
             step(x)
         barrier()
         ctx = net._plans[(B, local)]["ctx"]
-        sampler = ClockSampler(local)
-        if rank == 0:
-            sampler.start()
         l0 = ctx.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        sampler.mark_begin()
         e0.record()
         for _ in range(args.steps):
             step(x)
         e1.record()
         barrier()
+        sampler.mark_end()
         ms = e0.elapsed_time(e1)
         launches = ctx.launch_count() - l0
         clocks = sampler.stop() if rank == 0 else None
@@ -181,7 +198,7 @@ def run_native(args):
                 main.wait_event(ready[b])
                 res = step(xd[b])
                 freed[b].record(main)
-                out_h.copy_(res, non_blocking=True)             # 13 KB device -> host
+                out_h.copy_(res[:B] if world == 1 else res[rank * B:(rank + 1) * B], non_blocking=True)   # 13 KB device -> host
             main.synchronize()
 
         e2e_loop(2)
@@ -343,7 +360,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--dtype", default=os.environ.get("BUCTD_DTYPE", "fp16"), choices=["fp16", "bf16"])
