@@ -76,6 +76,26 @@ struct Geo {
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 #ifdef __CUDACC__
+// ---- programmatic dependent launch ------------------------------------------------------------
+// Every kernel of the plan is launched with cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs
+// may be scheduled (and run their prologue: barrier init, TMEM alloc, descriptor prefetch) while the
+// previous kernel drains.  pdl_wait() blocks until the previous grid has completed and its writes are
+// visible; nothing that depends on earlier kernels may be read before it.  pdl_launch_dependents()
+// allows the NEXT kernel to start scheduling.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -60,10 +60,12 @@ __device__ __forceinline__ EpiRow epi_row(const TapGemmKParams& p, const EpiTile
     const long long r = t.m0 + row;
     o.valid = r < p.m_rows;
     if (o.valid && p.out_mode != BUCTD_OUT_ROWS16) {
-      o.x = (int)(r % Wp);
-      const long long ry = r / Wp;
-      o.y = (int)(ry % Hp);
-      o.b = (int)(ry / Hp);
+      // 32-bit arithmetic on purpose (m_rows < 2^31 is checked on the host): 64-bit div/mod costs hundreds of cycles
+      const unsigned ru = (unsigned)r;
+      const unsigned ry = ru / (unsigned)Wp;
+      o.x = (int)(ru - ry * (unsigned)Wp);
+      o.b = (int)(ry / (unsigned)Hp);
+      o.y = (int)(ry - (unsigned)o.b * (unsigned)Hp);
       o.pad = (o.x == p.W) || (o.y == p.H);
     }
   } else {
@@ -153,20 +155,17 @@ __device__ __forceinline__ void epi_compute(const TapGemmKParams& p, const EpiTi
     if (zero) o = make_uint4(0, 0, 0, 0);
     *a = o;
   };
-  uint32_t acc_a[8], acc_b[8];
-  int u = grp;
-  tmem_ld8(taddr + u * 8, acc_a);
-  while (true) {
+  // up to 4 units in flight per tcgen05.wait::ld (the TMEM read latency, not its bandwidth, is what costs)
+  uint32_t acc[4][8];
+#pragma unroll 1
+  for (int u0 = grp; u0 < units; u0 += 4 * ngrp) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (u0 + i * ngrp < units) tmem_ld8(taddr + (u0 + i * ngrp) * 8, acc[i]);
     tmem_ld_wait();
-    if (u + ngrp < units) tmem_ld8(taddr + (u + ngrp) * 8, acc_b);
-    process(u, acc_a);
-    u += ngrp;
-    if (u >= units) break;
-    tmem_ld_wait();
-    if (u + ngrp < units) tmem_ld8(taddr + (u + ngrp) * 8, acc_a);
-    process(u, acc_b);
-    u += ngrp;
-    if (u >= units) break;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (u0 + i * ngrp < units) process(u0 + i * ngrp, acc[i]);
   }
 }
 

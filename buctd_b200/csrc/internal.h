@@ -34,7 +34,8 @@ struct SlabParams {
   int msub;          // 128-row sub-tiles per super-tile
   int halo;          // slab rows loaded before/after the super-tile (W+2 for 3x3, 0 for 1x1)
   int nboxes, box_rows, slab_bytes;
-  int sa, sw;        // slab ring / weight ring depth
+  int sa, sw;        // slab ring / weight ring depth (stages)
+  int tg;            // taps per weight-ring stage
   int stage_bufs;    // epilogue stage buffers (2: residual prefetch + store overlap)
   int w_resident, w_tiles;
   int num_super, num_items;
@@ -73,5 +74,8 @@ int launch_act16_to_nchw32(int dtype, const void* act, int B, int H, int W, int 
 int launch_nchw32_to_act16(int dtype, const float* x, int B, int xc, int c_off, int C, int H, int W, int cs, void* out,
                            cudaStream_t st);
 int pos_att_init_device();
+int pos_att_tc_init_device();
+bool pos_att_tc_supported(const buctd_pos_att_args& a);
+int launch_pos_att_tc(const buctd_pos_att_args& a, cudaStream_t st);
 
 }  // namespace buctd

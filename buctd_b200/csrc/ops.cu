@@ -89,6 +89,8 @@ int launch_stem(const buctd_stem_args& a, cudaStream_t st) {
 // =================================================================================================
 template <typename T>
 __global__ void __launch_bounds__(256) fuse_kernel(buctd_fuse_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cv = a.c / 8;
   const int Hp = a.h + 1, Wp = a.w + 1;
   const long long total = (long long)a.batch * Hp * Wp * cv;
@@ -139,8 +141,8 @@ int launch_fuse(const buctd_fuse_args& a, cudaStream_t st) {
   }
   const long long total = (long long)a.batch * (a.h + 1) * (a.w + 1) * (a.c / 8);
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  if (a.dtype == BUCTD_F16) fuse_kernel<__half><<<blocks, 256, 0, st>>>(a);
-  else fuse_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(a);
+  if (a.dtype == BUCTD_F16) launch_pdl(fuse_kernel<__half>, dim3(blocks), dim3(256), 0, st, a);
+  else launch_pdl(fuse_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, a);
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;
 }
@@ -154,6 +156,7 @@ int launch_fuse(const buctd_fuse_args& a, cudaStream_t st) {
 // =================================================================================================
 constexpr int kRzRows = 4;      // output rows per block
 constexpr int kRzMaxW = 512;
+constexpr int kRzMaxOw = 128;
 
 __device__ __forceinline__ void aa_span(float scale, float support, int o, int n_in, int* lo, int* hi, float* center) {
   *center = scale * (o + 0.5f);
@@ -163,57 +166,190 @@ __device__ __forceinline__ void aa_span(float scale, float support, int o, int n
 
 template <typename T>
 __global__ void __launch_bounds__(256) resize_kernel(buctd_resize_args a) {
-  // block = kRzRows output rows of one (b, c) plane.  Pass 1 (threads over input columns, coalesced):
-  // vertical triangle filter into shared memory; pass 2: horizontal filter + 16-bit store.
+  // block = kRzRows output rows of one crop, ALL channels: per channel, pass 1 (threads over input columns,
+  // coalesced) = vertical triangle filter into shared memory, pass 2 = horizontal filter into a channel-last
+  // shared tile; the tile leaves with coalesced 16-byte stores (act16 rows are out_cs*2 bytes of contiguous channels).
   __shared__ float s_v[kRzRows][kRzMaxW];
-  const int c = blockIdx.y, b = blockIdx.z;
+  extern __shared__ __align__(16) uint8_t s_out[];            // [kRzRows][ow][out_cs] 16-bit
+  const int b = blockIdx.y;
   const int oy0 = blockIdx.x * kRzRows;
+  const int nrows = min(kRzRows, a.oh - oy0);
   const float sy = (float)a.h / a.oh, sx = (float)a.w / a.ow;
   const bool aay = a.antialias && sy > 1.f, aax = a.antialias && sx > 1.f;
   const float supy = aay ? sy : 1.f, supx = aax ? sx : 1.f;
   const float invy = aay ? 1.f / sy : 1.f, invx = aax ? 1.f / sx : 1.f;
-  const float* src = a.x + (((long long)b * a.x_channels + a.c_off + c) * a.h) * a.w;
-  for (int g = 0; g < kRzRows; ++g) {
-    const int oy = oy0 + g;
-    if (oy >= a.oh) break;
-    int lo, hi; float center;
-    aa_span(sy, supy, oy, a.h, &lo, &hi, &center);
-    float tot = 0.f;
-    for (int j = lo; j < hi; ++j) tot += fmaxf(0.f, 1.f - fabsf((j - center + 0.5f) * invy));
-    const float rt = 1.f / tot;
-    for (int x = threadIdx.x; x < a.w; x += blockDim.x) {
-      float acc = 0.f;
-      for (int j = lo; j < hi; ++j)
-        acc = fmaf(fmaxf(0.f, 1.f - fabsf((j - center + 0.5f) * invy)) * rt, __ldg(src + (long long)j * a.w + x), acc);
-      s_v[g][x] = acc;
+  T* so = reinterpret_cast<T*>(s_out);
+  for (int i = threadIdx.x; i < nrows * a.ow * a.out_cs; i += blockDim.x) so[i] = T16<T>::from_f(0.f);
+  for (int c = 0; c < a.cc; ++c) {
+    const float* src = a.x + (((long long)b * a.x_channels + a.c_off + c) * a.h) * a.w;
+    for (int g = 0; g < nrows; ++g) {
+      int lo, hi; float center;
+      aa_span(sy, supy, oy0 + g, a.h, &lo, &hi, &center);
+      float tot = 0.f;
+      for (int j = lo; j < hi; ++j) tot += fmaxf(0.f, 1.f - fabsf((j - center + 0.5f) * invy));
+      const float rt = 1.f / tot;
+      for (int x = threadIdx.x; x < a.w; x += blockDim.x) {
+        float acc = 0.f;
+        for (int j = lo; j < hi; ++j)
+          acc = fmaf(fmaxf(0.f, 1.f - fabsf((j - center + 0.5f) * invy)) * rt, __ldg(src + (long long)j * a.w + x), acc);
+        s_v[g][x] = acc;
+      }
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nrows * a.ow; i += blockDim.x) {
+      const int g = i / a.ow, ox = i - g * a.ow;
+      int lo, hi; float center;
+      aa_span(sx, supx, ox, a.w, &lo, &hi, &center);
+      float tot = 0.f, acc = 0.f;
+      for (int j = lo; j < hi; ++j) {
+        const float w = fmaxf(0.f, 1.f - fabsf((j - center + 0.5f) * invx));
+        tot += w;
+        acc = fmaf(w, s_v[g][j], acc);
+      }
+      so[(g * a.ow + ox) * a.out_cs + c] = T16<T>::from_f(acc / tot);
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < kRzRows * a.ow; i += blockDim.x) {
-    const int g = i / a.ow, ox = i - g * a.ow;
-    const int oy = oy0 + g;
-    if (oy >= a.oh) break;
-    int lo, hi; float center;
-    aa_span(sx, supx, ox, a.w, &lo, &hi, &center);
-    float tot = 0.f, acc = 0.f;
-    for (int j = lo; j < hi; ++j) {
-      const float w = fmaxf(0.f, 1.f - fabsf((j - center + 0.5f) * invx));
-      tot += w;
-      acc = fmaf(w, s_v[g][j], acc);
-    }
-    T* o = reinterpret_cast<T*>(a.out) + (((long long)b * (a.oh + 1) + oy) * (a.ow + 1) + ox) * a.out_cs + c;
-    *o = T16<T>::from_f(acc / tot);
+  // rows of the tile are contiguous in the act16 tensor: (ow * out_cs * 2) bytes per output row
+  const int chunks_per_row = a.ow * a.out_cs / 8;
+  for (int i = threadIdx.x; i < nrows * chunks_per_row; i += blockDim.x) {
+    const int g = i / chunks_per_row, ch = i - g * chunks_per_row;
+    T* o = reinterpret_cast<T*>(a.out) + (((long long)b * (a.oh + 1) + oy0 + g) * (a.ow + 1)) * a.out_cs;
+    reinterpret_cast<uint4*>(o)[ch] = reinterpret_cast<const uint4*>(so + (size_t)g * a.ow * a.out_cs)[ch];
   }
 }
 
+// Fast path: antialiased, integer scale S (4 / 8 / 16 for the W48 and W32 families), W % 4 == 0.
+// Block = kRzRows output rows x 8 channels x the full width; thread = (channel, 4 consecutive input columns).
+// Vertical pass: every thread streams the (kRzRows+1)*S input rows of its band with 128-bit loads (all
+// independent, compile-time trip count, running pointer) into 4x4 accumulators -- input row i feeds output row
+// i/S with tap i%S and output row i/S-1 with tap i%S+S.  Horizontal pass from shared memory, then one
+// 16-byte (8-channel) store per output pixel.
+template <int S> __device__ __forceinline__ float aa_w(int t) { return 1.f - fabsf(t - S + 0.5f) * (1.f / S); }
+
+template <typename T, int S>
+__global__ void __launch_bounds__(576) resize_int_kernel(buctd_resize_args a) {
+  extern __shared__ __align__(16) float s_rz[];            // [8 ch][kRzRows][w] fp32, then [rows][ow][8] 16-bit
+  const int b = blockIdx.z, c0 = blockIdx.y * 8;
+  const int oy0 = blockIdx.x * kRzRows;
+  const int nrows = min(kRzRows, a.oh - oy0);
+  const int w4 = a.w >> 2;
+  float* s_v = s_rz;
+  T* so = reinterpret_cast<T*>(s_rz + 8 * kRzRows * a.w);
+  const int base = S * oy0 - S / 2;
+  // normalisation of the vertical taps (same for every column): sum of the weights of the rows that exist
+  float rtot[kRzRows];
+#pragma unroll
+  for (int g = 0; g < kRzRows; ++g) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2 * S; ++k) {
+      const int jrow = base + g * S + k;
+      t += (jrow >= 0 && jrow < a.h) ? aa_w<S>(k) : 0.f;
+    }
+    rtot[g] = t > 0.f ? 1.f / t : 0.f;
+  }
+  for (int i = threadIdx.x; i < 8 * w4; i += blockDim.x) {
+    const int cc = i / w4, x4 = i - cc * w4;
+    float4 acc[kRzRows];
+#pragma unroll
+    for (int g = 0; g < kRzRows; ++g) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c0 + cc < a.cc) {
+      const float4* ptr = reinterpret_cast<const float4*>(a.x + (((long long)b * a.x_channels + a.c_off + c0 + cc) * a.h) * a.w) +
+                          (long long)base * w4 + x4;
+#pragma unroll
+      for (int r = 0; r < (kRzRows + 1) * S; ++r) {
+        const bool ok = (unsigned)(base + r) < (unsigned)a.h;
+        const float4 v = ok ? __ldg(ptr) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ptr += w4;
+        const int g = r / S, t = r % S;                   // compile-time after unrolling
+        if (g < kRzRows) {
+          const float wt = aa_w<S>(t);
+          acc[g].x = fmaf(wt, v.x, acc[g].x); acc[g].y = fmaf(wt, v.y, acc[g].y);
+          acc[g].z = fmaf(wt, v.z, acc[g].z); acc[g].w = fmaf(wt, v.w, acc[g].w);
+        }
+        if (g >= 1) {
+          const float wt = aa_w<S>(t + S);
+          acc[g - 1].x = fmaf(wt, v.x, acc[g - 1].x); acc[g - 1].y = fmaf(wt, v.y, acc[g - 1].y);
+          acc[g - 1].z = fmaf(wt, v.z, acc[g - 1].z); acc[g - 1].w = fmaf(wt, v.w, acc[g - 1].w);
+        }
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < kRzRows; ++g) {
+      float4 o = acc[g];
+      o.x *= rtot[g]; o.y *= rtot[g]; o.z *= rtot[g]; o.w *= rtot[g];
+      reinterpret_cast<float4*>(s_v + (cc * kRzRows + g) * a.w)[x4] = o;
+    }
+  }
+  __syncthreads();
+  // horizontal pass: one thread per (row, output pixel), all 8 channels -> one 16-byte chunk
+  for (int i = threadIdx.x; i < nrows * a.ow; i += blockDim.x) {
+    const int g = i / a.ow, ox = i - g * a.ow;
+    const int lo = S * ox - S / 2;
+    float tot = 0.f;
+#pragma unroll
+    for (int t = 0; t < 2 * S; ++t) tot += ((unsigned)(lo + t) < (unsigned)a.w) ? aa_w<S>(t) : 0.f;
+    const float rt = 1.f / tot;
+    float o[8];
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+      const float* row = s_v + (cc * kRzRows + g) * a.w;
+      float acc = 0.f;
+#pragma unroll
+      for (int t = 0; t < 2 * S; ++t) {
+        const int jx = lo + t;
+        acc = fmaf(aa_w<S>(t), ((unsigned)jx < (unsigned)a.w) ? row[jx] : 0.f, acc);
+      }
+      o[cc] = (c0 + cc < a.cc) ? acc * rt : 0.f;
+    }
+    uint4 u;
+    u.x = T16<T>::pack2(o[0], o[1]); u.y = T16<T>::pack2(o[2], o[3]);
+    u.z = T16<T>::pack2(o[4], o[5]); u.w = T16<T>::pack2(o[6], o[7]);
+    reinterpret_cast<uint4*>(so)[i] = u;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nrows * a.ow; i += blockDim.x) {
+    const int g = i / a.ow, ox = i - g * a.ow;
+    T* o = reinterpret_cast<T*>(a.out) + (((long long)b * (a.oh + 1) + oy0 + g) * (a.ow + 1) + ox) * a.out_cs + c0;
+    *reinterpret_cast<uint4*>(o) = reinterpret_cast<const uint4*>(so)[i];
+  }
+}
+
+template <typename T>
+static int resize_dispatch(const buctd_resize_args& a, cudaStream_t st) {
+  const bool int_scale = a.antialias && a.h % a.oh == 0 && a.w % a.ow == 0 && a.h / a.oh == a.w / a.ow && a.w <= kRzMaxW &&
+                         a.ow <= kRzMaxOw && a.out_cs % 8 == 0 && a.w % 4 == 0 && ((uintptr_t)a.x & 15) == 0;
+  const int sc = int_scale ? a.h / a.oh : 0;
+  dim3 gi(ceil_div(a.oh, kRzRows), ceil_div(a.cc, 8), a.batch);     // channel groups beyond cc stay zero (workspace is zero-filled)
+  const size_t smi = (size_t)8 * kRzRows * a.w * 4 + (size_t)kRzRows * a.ow * 16;
+  if (sc == 4 || sc == 8 || sc == 16) {
+    if (sc == 4) {
+      BUCTD_CUDA(cudaFuncSetAttribute(resize_int_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smi));
+      resize_int_kernel<T, 4><<<gi, 576, smi, st>>>(a);
+    } else if (sc == 8) {
+      BUCTD_CUDA(cudaFuncSetAttribute(resize_int_kernel<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smi));
+      resize_int_kernel<T, 8><<<gi, 576, smi, st>>>(a);
+    } else {
+      BUCTD_CUDA(cudaFuncSetAttribute(resize_int_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smi));
+      resize_int_kernel<T, 16><<<gi, 576, smi, st>>>(a);
+    }
+    return BUCTD_OK;
+  }
+  dim3 grid(ceil_div(a.oh, kRzRows), a.batch);
+  const size_t smem = (size_t)kRzRows * a.ow * a.out_cs * 2;
+  BUCTD_CHECK(smem <= 40 * 1024, BUCTD_ERR_INVALID, "resize: output tile too large (%zu B)", smem);
+  resize_kernel<T><<<grid, 256, smem, st>>>(a);
+  return BUCTD_OK;
+}
+
 int launch_resize(const buctd_resize_args& a, cudaStream_t st) {
-  BUCTD_CHECK(a.cc > 0 && a.cc <= a.out_cs, BUCTD_ERR_INVALID, "resize: cc %d vs out_cs %d", a.cc, a.out_cs);
-  BUCTD_CHECK(a.w <= kRzMaxW, BUCTD_ERR_INVALID, "resize: input width %d > %d", a.w, kRzMaxW);
+  BUCTD_CHECK(a.cc > 0 && a.cc <= a.out_cs && a.out_cs % 8 == 0, BUCTD_ERR_INVALID, "resize: cc %d vs out_cs %d", a.cc, a.out_cs);
+  BUCTD_CHECK(a.w <= kRzMaxW && a.ow <= kRzMaxOw, BUCTD_ERR_INVALID, "resize: width %d -> %d out of range", a.w, a.ow);
   BUCTD_CHECK(a.x && a.out, BUCTD_ERR_INVALID, "resize: null pointer");
   if (a.batch == 0) return BUCTD_OK;
-  dim3 grid(ceil_div(a.oh, kRzRows), a.cc, a.batch);
-  if (a.dtype == BUCTD_F16) resize_kernel<__half><<<grid, 256, 0, st>>>(a);
-  else resize_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a);
+  int rc = a.dtype == BUCTD_F16 ? resize_dispatch<__half>(a, st) : resize_dispatch<__nv_bfloat16>(a, st);
+  if (rc) return rc;
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;
 }
@@ -230,6 +366,8 @@ constexpr int kCaRows = 32;      // rows staged per step
 
 template <typename T, int kCaTile>
 __global__ void __launch_bounds__(256) chan_scores_kernel(buctd_chan_att_args a, int rows_per_chunk) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int PER = kCaTile / 16;
   __shared__ float s_q[kCaRows][kCaTile + 1];
   __shared__ float s_k[kCaRows][kCaTile + 1];
@@ -272,6 +410,8 @@ __global__ void __launch_bounds__(256) chan_scores_kernel(buctd_chan_att_args a,
 }
 
 __global__ void chan_softmax_kernel(float* S, int c, float scale, int nrows) {
+  pdl_launch_dependents();
+  pdl_wait();
   // one warp per row of S
   const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   const int lane = threadIdx.x & 31;
@@ -290,6 +430,8 @@ __global__ void chan_softmax_kernel(float* S, int c, float scale, int nrows) {
 constexpr int kCaPix = 64;
 template <typename T, int kCaTile>
 __global__ void __launch_bounds__(256) chan_apply_kernel(buctd_chan_att_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
   // block: 64 valid pixels x kCaTile output channels (c1 tile); dynamic smem: att[tile][C] f32, y[64][C+1] f32
   constexpr int G = kCaTile / 4;   // channels per thread group
   extern __shared__ float s_dyn[];
@@ -337,10 +479,10 @@ static int chan_att_run(const buctd_chan_att_args& a, cudaStream_t st) {
   const size_t smem = sizeof(float) * ((size_t)TILE * a.c + (size_t)kCaPix * (a.c + 1));
   dim3 g3(ceil_div(a.h * a.w, kCaPix), tiles, a.batch);
   const float scale = 1.f / sqrtf((float)(a.h * a.w));
-  chan_scores_kernel<T, TILE><<<g1, 256, 0, st>>>(a, chunk);
-  chan_softmax_kernel<<<ceil_div(a.batch * a.c, 8), 256, 0, st>>>(a.scratch, a.c, scale, a.batch * a.c);
+  launch_pdl(chan_scores_kernel<T, TILE>, g1, dim3(256), 0, st, a, chunk);
+  launch_pdl(chan_softmax_kernel, dim3(ceil_div(a.batch * a.c, 8)), dim3(256), 0, st, a.scratch, a.c, scale, a.batch * a.c);
   BUCTD_CUDA(cudaFuncSetAttribute(chan_apply_kernel<T, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  chan_apply_kernel<T, TILE><<<g3, 256, smem, st>>>(a);
+  launch_pdl(chan_apply_kernel<T, TILE>, g3, dim3(256), smem, st, a);
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;
 }
@@ -362,6 +504,8 @@ int launch_chan_att(const buctd_chan_att_args& a, cudaStream_t st, int* nlaunch)
 // =================================================================================================
 template <typename T>
 __global__ void __launch_bounds__(256) da_combine_kernel(buctd_da_combine_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_c[32][33];
   const int b = blockIdx.z;
   const int hw = a.h * a.w;
@@ -389,8 +533,8 @@ __global__ void __launch_bounds__(256) da_combine_kernel(buctd_da_combine_args a
 int launch_da_combine(const buctd_da_combine_args& a, cudaStream_t st) {
   BUCTD_CHECK(a.x && a.c_out && a.out && (a.channel_only || a.p_out), BUCTD_ERR_INVALID, "da_combine: null pointer");
   dim3 grid(ceil_div(a.h * a.w, 32), ceil_div(a.c, 32), a.batch);
-  if (a.dtype == BUCTD_F16) da_combine_kernel<__half><<<grid, 256, 0, st>>>(a);
-  else da_combine_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a);
+  if (a.dtype == BUCTD_F16) launch_pdl(da_combine_kernel<__half>, grid, dim3(256), 0, st, a);
+  else launch_pdl(da_combine_kernel<__nv_bfloat16>, grid, dim3(256), 0, st, a);
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;
 }

@@ -30,6 +30,19 @@ template <> struct MmaOp<__nv_bfloat16> {
   }
 };
 
+// 2 exponentials per MUFU op, result already in the 16-bit type the P.V MMA consumes
+template <typename T> __device__ __forceinline__ uint32_t ex2_pair(float a, float b);
+template <> __device__ __forceinline__ uint32_t ex2_pair<__half>(float a, float b) {
+  uint32_t h = T16<__half>::pack2(a, b), r;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(h));
+  return r;
+}
+template <> __device__ __forceinline__ uint32_t ex2_pair<__nv_bfloat16>(float a, float b) {
+  uint32_t h = T16<__nv_bfloat16>::pack2(a, b), r;
+  asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(r) : "r"(h));
+  return r;
+}
+
 __device__ __forceinline__ void ldsm_x4(uint32_t* r, uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
@@ -56,6 +69,8 @@ __global__ void __launch_bounds__(128) pos_att_kernel(buctd_pos_att_args a) {
   uint8_t* s_v = s_k + 2 * TILE;               // [2][64][PITCH]
   float* s_bias = reinterpret_cast<float*>(s_v + 2 * TILE);   // [2][64] additive key mask
 
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y;
   const int Wp = a.w + 1, Hp = a.h + 1;
   const int nrows = Hp * Wp;
@@ -98,7 +113,12 @@ __global__ void __launch_bounds__(128) pos_att_kernel(buctd_pos_att_args a) {
   float o[NT_O][4];
 #pragma unroll
   for (int i = 0; i < NT_O; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
-  float row_m[2] = {-INFINITY, -INFINITY}, row_l[2] = {0.f, 0.f};
+  float row_m[2] = {-INFINITY, -INFINITY};
+  // Row sums come out of the tensor cores: a constant extra B fragment ("ones column" appended to V) makes
+  // o_l[0] / o_l[2] (lanes with lane%4 == 0) accumulate sum_k P[row][k] with exactly the rounded P that P.V uses.
+  float o_l[4] = {0.f, 0.f, 0.f, 0.f};
+  uint32_t ones_frag[2];
+  ones_frag[0] = ones_frag[1] = (lane >> 2) == 0 ? T16<T>::pack2(1.f, 1.f) : 0u;
   const float sc = rsqrtf((float)a.c) * 1.4426950408889634f;   // 1/sqrt(C) * log2(e)
 
   cp_async_wait<0>();
@@ -156,30 +176,24 @@ __global__ void __launch_bounds__(128) pos_att_kernel(buctd_pos_att_args a) {
       msafe[h] = (mx[h] == -INFINITY) ? 0.f : mx[h];          // a tile of pads only
       corr[h] = exp2f(row_m[h] - msafe[h]);                   // row_m = -inf on the first tile -> 0
       row_m[h] = mx[h];
-      row_l[h] *= corr[h];
     }
     uint32_t pf[kBN / 16][4];
-    float ls[2] = {0.f, 0.f};
 #pragma unroll
     for (int nt = 0; nt < kBN / 8; ++nt) {
-      const float p0 = exp2f(s[nt][0] - msafe[0]), p1 = exp2f(s[nt][1] - msafe[0]);
-      const float p2 = exp2f(s[nt][2] - msafe[1]), p3 = exp2f(s[nt][3] - msafe[1]);
-      ls[0] += p0 + p1;
-      ls[1] += p2 + p3;
       // C fragment of n-tiles (2k, 2k+1) -> A fragment of k-step k
-      pf[nt >> 1][(nt & 1) * 2 + 0] = T16<T>::pack2(p0, p1);
-      pf[nt >> 1][(nt & 1) * 2 + 1] = T16<T>::pack2(p2, p3);
+      pf[nt >> 1][(nt & 1) * 2 + 0] = ex2_pair<T>(s[nt][0] - msafe[0], s[nt][1] - msafe[0]);
+      pf[nt >> 1][(nt & 1) * 2 + 1] = ex2_pair<T>(s[nt][2] - msafe[1], s[nt][3] - msafe[1]);
     }
-    row_l[0] += ls[0];
-    row_l[1] += ls[1];
 #pragma unroll
     for (int nt = 0; nt < NT_O; ++nt) {
       o[nt][0] *= corr[0]; o[nt][1] *= corr[0];
       o[nt][2] *= corr[1]; o[nt][3] *= corr[1];
     }
+    o_l[0] *= corr[0]; o_l[1] *= corr[0]; o_l[2] *= corr[1]; o_l[3] *= corr[1];
     // ---- O += P V -------------------------------------------------------------------------------
 #pragma unroll
     for (int ks = 0; ks < kBN / 16; ++ks) {
+      MmaOp<T>::mma(o_l, pf[ks], ones_frag);
 #pragma unroll
       for (int np = 0; np < NT_O / 2; ++np) {
         uint32_t vf[4];
@@ -193,11 +207,9 @@ __global__ void __launch_bounds__(128) pos_att_kernel(buctd_pos_att_args a) {
   }
 
   // ---- finalise: divide by the row sum (reduced over the 4 lanes of a row) and store ----------
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    row_l[h] += __shfl_xor_sync(0xffffffff, row_l[h], 1);
-    row_l[h] += __shfl_xor_sync(0xffffffff, row_l[h], 2);
-  }
+  float row_l[2];
+  row_l[0] = __shfl_sync(0xffffffff, o_l[0], lane & ~3);      // column 0 of the ones tile lives in lane%4 == 0
+  row_l[1] = __shfl_sync(0xffffffff, o_l[2], lane & ~3);
   T* go = reinterpret_cast<T*>(a.o) + base * a.o_cs;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -219,7 +231,7 @@ template <typename T, int D>
 static int pa_launch(const buctd_pos_att_args& a, cudaStream_t st) {
   const int nrows = (a.h + 1) * (a.w + 1);
   dim3 grid((nrows + kBM - 1) / kBM, a.batch);
-  pos_att_kernel<T, D><<<grid, 128, pa_smem<D>(), st>>>(a);
+  launch_pdl(pos_att_kernel<T, D>, grid, dim3(128), pa_smem<D>(), st, a);
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;
 }
@@ -263,6 +275,7 @@ int launch_pos_att(const buctd_pos_att_args& a, cudaStream_t st) {
   BUCTD_CHECK((((uintptr_t)a.q | (uintptr_t)a.k | (uintptr_t)a.v) & 15) == 0, BUCTD_ERR_INVALID,
               "pos_att: q/k/v must be 16-byte aligned");
   if (a.batch == 0) return BUCTD_OK;
+  if (pos_att_tc_supported(a)) return launch_pos_att_tc(a, st);       // tcgen05 path (C <= 64)
   return a.dtype == BUCTD_F16 ? pa_dispatch<__half>(a, st) : pa_dispatch<__nv_bfloat16>(a, st);
 }
 

@@ -1,0 +1,459 @@
+// CoAM position attention on the sm_100a tensor cores (head dim C <= 64: the 96x72 branch of W48, and
+// every branch of W32 up to C = 64).  Same contract as pos_att_kernel (posatt.cu); this version keeps S = QK^T
+// and O in TMEM and issues both GEMMs with tcgen05.mma:
+//
+//   per CTA: 128 queries (one thread of the 4 soft-max warps per query row = TMEM lane), loop over 128-key tiles:
+//     warp 0  TMA: Q once, K/V tiles through a 2-stage ring (SWIZZLE_128B, 64-channel boxes, zero fill above C)
+//     warp 1  MMA: S[128x128] = Q K^T (K-major A and B), then O[128xC] += P V  (P from shared memory, V as an
+//             MN-major B operand: the tile is [keys][channels], exactly as it lies in the act16 tensor)
+//     warps 2..5  soft-max: two passes over the S row in TMEM (max, then exp2 -> 16-bit P into shared memory),
+//             running max / sum in registers, O rescaled in TMEM only when a row maximum grows
+//   Two CTAs per SM interleave, so one CTA's soft-max overlaps the other's MMAs.
+#include "common.cuh"
+#include "internal.h"
+
+namespace buctd {
+
+#ifdef BUCTD_ROLE_TIMERS
+__device__ unsigned long long g_pa_cycles[16];
+#define PT_DECL(n) long long n = 0
+#define PT_BEGIN(t) const long long t = clock64()
+#define PT_ADD(a, t) a += clock64() - t
+#else
+#define PT_DECL(n)
+#define PT_BEGIN(t)
+#define PT_ADD(a, t)
+#endif
+
+constexpr int kTcThreads = 192;
+constexpr int kTcTile = 128;
+constexpr int kTcBlk = 128 * 128;      // one [128 rows][128 B] SWIZZLE_128B block
+
+struct PosAttTcParams {
+  int nrows, W, H, c, n2;              // rows per crop (padded), geometry, channels, channels rounded up to 16
+  int o_cs;
+  float sc;                            // 1/sqrt(C) * log2(e)
+  void* o;
+};
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+      "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
+          taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// MN-major, SWIZZLE_128B descriptor: the tile is [K rows][64 MN elements = 128 B]; 8-row groups are 1024 B apart
+// (SBO); LBO would be the distance between 64-element column blocks (not used for N <= 64)
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(kTcBlk >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+__device__ __forceinline__ float ex2f(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// non-saturating pack (the values are probabilities scaled by at most 2^8)
+template <typename T> __device__ __forceinline__ uint32_t pack_ns(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack_ns<__half>(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack_ns<__nv_bfloat16>(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <typename T> __device__ __forceinline__ uint32_t ex2_pack(float a, float b);
+template <> __device__ __forceinline__ uint32_t ex2_pack<__half>(float a, float b) {
+  uint32_t h = T16<__half>::pack2(a, b), r;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(h));
+  return r;
+}
+template <> __device__ __forceinline__ uint32_t ex2_pack<__nv_bfloat16>(float a, float b) {
+  uint32_t h = T16<__nv_bfloat16>::pack2(a, b), r;
+  asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(r) : "r"(h));
+  return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kTcThreads, 2)
+pos_att_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                  const __grid_constant__ CUtensorMap map_v, const PosAttTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_q = smem;                       // [128][128 B]
+  uint8_t* s_kv = s_q + kTcBlk;              // ring of 3 tiles holding the stream K0 V0 K1 V1 ... (load n -> slot n % 3)
+  uint8_t* s_p = s_kv + 3 * kTcBlk;          // [2 blocks: keys 0..63 | 64..127][128 queries][128 B]
+  float* s_bias = reinterpret_cast<float*>(s_p + 2 * kTcBlk);   // [2][128] additive key mask (double buffered)
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_bias + 2 * kTcTile);   // [2][4] bit c%32 of word c/32: key c of the tile is masked
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(s_mask + 8);
+  uint64_t* kv_full = q_full + 1;            // [3]
+  uint64_t* kv_empty = kv_full + 3;          // [3]
+  uint64_t* s_full = kv_empty + 3;
+  uint64_t* p_full = s_full + 1;
+  uint64_t* o_done = p_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int m0 = blockIdx.x * kTcTile;
+  const int ntiles = (p.nrows + kTcTile - 1) / kTcTile;
+  const int row_base = b * p.nrows;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 3; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_s = tmem_base, tm_o = tmem_base + kTcTile;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(q_full, kTcBlk);
+      tma_load_2d(s_q, &map_q, q_full, 0, row_base + m0);
+      for (int n = 0; n < 2 * ntiles; ++n) {                  // n even: K(n/2), n odd: V(n/2)
+        const int slot = n % 3;
+        mbar_wait(&kv_empty[slot], ((n / 3) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[slot], kTcBlk);
+        tma_load_2d(s_kv + slot * kTcBlk, (n & 1) ? &map_v : &map_k, &kv_full[slot], 0, row_base + (n >> 1) * kTcTile);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc_s = umma_idesc_f16(T16<T>::kFmt, 128, kTcTile);                 // S = Q K^T, both K-major
+      const uint32_t idesc_o = umma_idesc_f16(T16<T>::kFmt, 128, p.n2) | (1u << 16);       // O += P V, B (=V) MN-major
+      const uint64_t qd = umma_desc_sw128(smem_u32(s_q));
+      const uint64_t pd = umma_desc_sw128(smem_u32(s_p));
+      const int ks_qk = (p.c + 15) >> 4;
+      mbar_wait(q_full, 0);
+      const uint32_t kv_addr = smem_u32(s_kv);
+      PT_DECL(m_k); PT_DECL(m_p); PT_DECL(m_v); PT_DECL(m_tot);
+      PT_BEGIN(m_start);
+      for (int j = 0; j < ntiles; ++j) {
+        const int nk = 2 * j, nv = 2 * j + 1;
+        const int sk = nk % 3, sv = nv % 3;
+        { PT_BEGIN(t0); mbar_wait(&kv_full[sk], (nk / 3) & 1); PT_ADD(m_k, t0); }
+        tc_fence_after();
+        const uint64_t kd = umma_desc_sw128(kv_addr + sk * kTcBlk);
+        for (int k = 0; k < ks_qk; ++k) tc_mma_f16(tm_s, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_s, k != 0);
+        tc_commit(&kv_empty[sk]);
+        tc_commit(s_full);
+        { PT_BEGIN(t0); mbar_wait(p_full, j & 1); PT_ADD(m_p, t0); }
+        { PT_BEGIN(t0); mbar_wait(&kv_full[sv], (nv / 3) & 1); PT_ADD(m_v, t0); }
+        tc_fence_after();
+        const uint64_t vd = umma_desc_sw128_mn(kv_addr + sv * kTcBlk);
+#pragma unroll
+        for (int k = 0; k < kTcTile / 16; ++k) {
+          // A: P block k/4 (64 keys each), 32 B per k-step inside the 128-byte row; B: 16 key rows = 2048 B further
+          const uint64_t pa = pd + (uint64_t)((k >> 2) * (kTcBlk >> 4) + (k & 3) * 2);
+          tc_mma_f16(tm_o, pa, vd + (uint64_t)(k * (2048 >> 4)), idesc_o, (j | k) != 0);
+        }
+        tc_commit(&kv_empty[sv]);
+        tc_commit(o_done);
+      }
+#ifdef BUCTD_ROLE_TIMERS
+      PT_ADD(m_tot, m_start);
+      if (blockIdx.x == 3 && blockIdx.y == 1) { g_pa_cycles[0] = m_tot; g_pa_cycles[1] = m_k; g_pa_cycles[2] = m_p; g_pa_cycles[3] = m_v; }
+#endif
+    }
+    __syncwarp();
+  } else {
+    // ---- soft-max warps: thread = query row --------------------------------------------------------------
+    // Single pass per tile in the common case: P = exp2(s*sc + bias - m_run) with the running maximum of EARLIER
+    // tiles; the tile's own maximum is tracked on the side and only when it exceeds m_run by more than 8 (P would
+    // leave the safe range of the 16-bit type) is the row state updated (O rescaled in TMEM) and the tile redone.
+    // The result is independent of the reference maximum, so this is exact.  Row sums: when a channel slot is free
+    // (C < 64) a column of ones is planted in the V tile, so O[:, C] accumulates sum_k P with the tensor cores.
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int etid = threadIdx.x - 64;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const int Wp = p.W + 1;
+    const bool ones = p.n2 > p.c;                // a free channel slot exists for the ones column
+    float m_run = -INFINITY, l_run = 0.f;
+    uint8_t* prow = s_p + row * 128;
+    const int sw = row & 7;
+    PT_DECL(x_bar); PT_DECL(x_s); PT_DECL(x_o); PT_DECL(x_main); PT_DECL(x_v); PT_DECL(x_tot); PT_DECL(x_redo);
+    PT_BEGIN(x_start);
+    for (int j = 0; j < ntiles; ++j) {
+      float* bias = s_bias + (j & 1) * kTcTile;
+      {
+        const int r = j * kTcTile + etid;
+        const bool valid = r < p.nrows && (r % Wp) != p.W && (r / Wp) != p.H;
+        bias[etid] = valid ? 0.f : -INFINITY;
+        const uint32_t bal = __ballot_sync(0xffffffff, !valid);
+        if (lane == 0) s_mask[(j & 1) * 4 + (etid >> 5)] = bal;
+      }
+      { PT_BEGIN(t0); asm volatile("bar.sync 1, 128;" ::: "memory"); PT_ADD(x_bar, t0); }
+      { PT_BEGIN(t0); mbar_wait(s_full, j & 1); PT_ADD(x_s, t0); }
+      tc_fence_after();
+      bool first = true;
+      float ls = 0.f;
+      for (;;) {
+        // on the very first tile (or on a redo) the row maximum must be known before P can be formed
+        if (m_run == -INFINITY || !first) {
+          float mx = -INFINITY;
+#pragma unroll 1
+          for (int c0 = 0; c0 < kTcTile; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tm_s + lane_off + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 bq = *reinterpret_cast<const float4*>(bias + c0 + i);
+              mx = fmaxf(mx, fmaf(__uint_as_float(v[i]), p.sc, bq.x));
+              mx = fmaxf(mx, fmaf(__uint_as_float(v[i + 1]), p.sc, bq.y));
+              mx = fmaxf(mx, fmaf(__uint_as_float(v[i + 2]), p.sc, bq.z));
+              mx = fmaxf(mx, fmaf(__uint_as_float(v[i + 3]), p.sc, bq.w));
+            }
+          }
+          if (mx == -INFINITY && j + 1 < ntiles) mx = -1e30f;      // a tile of masked keys only: keep the state finite
+          const float m_new = fmaxf(m_run, mx);
+          const float m_use = m_new == -INFINITY ? 0.f : m_new;
+          const float corr = exp2f(m_run - m_use);            // 0 when m_run = -inf
+          if (j > 0) {                                        // rescale O (and l, which may live in O[:, C])
+            mbar_wait(o_done, (j - 1) & 1);
+            tc_fence_after();
+            if (__any_sync(0xffffffff, corr != 1.f)) {
+#pragma unroll 1
+              for (int c0 = 0; c0 < p.n2; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(tm_o + lane_off + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * corr);
+                tmem_st16(tm_o + lane_off + c0, v);
+              }
+              tmem_st_wait();
+            }
+          }
+          l_run *= corr;
+          m_run = m_new;
+        } else if (j > 0) {
+          PT_BEGIN(t0);
+          mbar_wait(o_done, (j - 1) & 1);                     // the P buffer is free once the previous PV has been issued+done
+          PT_ADD(x_o, t0);
+          tc_fence_after();
+        }
+        PT_BEGIN(t_main);
+        const float m_use = m_run == -INFINITY ? 0.f : m_run;
+        float mx2 = -INFINITY;
+        ls = 0.f;
+        // one 32-column chunk: scores -> P (16 bit) -> this row of the P tile
+        auto chunk = [&](int c0, const uint32_t (&v)[32]) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const float4 bq = *reinterpret_cast<const float4*>(bias + c0 + 2 * i);
+            const float t0 = fmaf(__uint_as_float(v[2 * i]), p.sc, bq.x), t1 = fmaf(__uint_as_float(v[2 * i + 1]), p.sc, bq.y);
+            const float t2 = fmaf(__uint_as_float(v[2 * i + 2]), p.sc, bq.z), t3 = fmaf(__uint_as_float(v[2 * i + 3]), p.sc, bq.w);
+            mx2 = fmaxf(fmaxf(mx2, fmaxf(t0, t1)), fmaxf(t2, t3));
+            pk[i] = ex2_pack<T>(t0 - m_use, t1 - m_use);
+            pk[i + 1] = ex2_pack<T>(t2 - m_use, t3 - m_use);
+            if (!ones) {
+              const float2 f0 = T16<T>::unpack2(pk[i]), f1 = T16<T>::unpack2(pk[i + 1]);
+              ls += (f0.x + f0.y) + (f1.x + f1.y);
+            }
+          }
+          uint8_t* blk = prow + (c0 >> 6) * kTcBlk;
+          const int ci = (c0 & 63) >> 3;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch)
+            *reinterpret_cast<uint4*>(blk + (((ci + ch) ^ sw) << 4)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+        };
+        // fast variant (row sums come from the ones column): no per-element mask, 3.5 instructions per score --
+        // raw max, one FFMA, one ex2, half a pack; masked keys are zeroed afterwards in the P tile
+        float rawmax = -INFINITY;
+        const float neg_m = -m_use;
+        auto chunk_fast = [&](int c0, const uint32_t (&v)[32]) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float s0 = __uint_as_float(v[2 * i]), s1 = __uint_as_float(v[2 * i + 1]);
+            rawmax = fmaxf(rawmax, fmaxf(s0, s1));
+            pk[i] = pack_ns<T>(ex2f(fmaf(s0, p.sc, neg_m)), ex2f(fmaf(s1, p.sc, neg_m)));
+          }
+          uint8_t* blk = prow + (c0 >> 6) * kTcBlk;
+          const int ci = (c0 & 63) >> 3;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch)
+            *reinterpret_cast<uint4*>(blk + (((ci + ch) ^ sw) << 4)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+        };
+        // TMEM reads are software pipelined: the load of chunk c+1 is in flight while chunk c is processed
+        {
+          uint32_t va[32], vb[32];
+          tmem_ld32(tm_s + lane_off + 0, va);
+          tmem_ld_wait();
+          tmem_ld32(tm_s + lane_off + 32, vb);
+          if (ones) chunk_fast(0, va); else chunk(0, va);
+          tmem_ld_wait();
+          tmem_ld32(tm_s + lane_off + 64, va);
+          if (ones) chunk_fast(32, vb); else chunk(32, vb);
+          tmem_ld_wait();
+          tmem_ld32(tm_s + lane_off + 96, vb);
+          if (ones) chunk_fast(64, va); else chunk(64, va);
+          tmem_ld_wait();
+          if (ones) chunk_fast(96, vb); else chunk(96, vb);
+        }
+        if (ones) {
+          mx2 = rawmax * p.sc;
+          // zero the masked keys of this row's P (1-2 pad columns per interior tile; the tail tiles have more)
+          const uint32_t* mw = s_mask + (j & 1) * 4;
+#pragma unroll 1
+          for (int wd = 0; wd < 4; ++wd) {
+            uint32_t bits = mw[wd];
+            while (bits) {
+              const int c = wd * 32 + __ffs(bits) - 1;
+              bits &= bits - 1;
+              *reinterpret_cast<T*>(prow + (c >> 6) * kTcBlk + ((((c & 63) >> 3) ^ sw) << 4) + (c & 7) * 2) = T16<T>::from_f(0.f);
+            }
+          }
+        }
+        // redo (warp-uniform decision) if some row of this warp saw a score more than 8 above its reference maximum
+        PT_ADD(x_main, t_main);
+        if (first && __any_sync(0xffffffff, mx2 > m_use + 8.f)) {
+          first = false;
+#ifdef BUCTD_ROLE_TIMERS
+          x_redo += 1;
+#endif
+          continue;
+        }
+        break;
+      }
+      l_run += ls;
+      if (ones) {                                             // plant the ones column in this tile's V (one key row per thread)
+        const int nv = 2 * j + 1, sv = nv % 3;
+        { PT_BEGIN(t0); mbar_wait(&kv_full[sv], (nv / 3) & 1); PT_ADD(x_v, t0); }
+        *reinterpret_cast<T*>(s_kv + sv * kTcBlk + etid * 128 + ((((p.c >> 3)) ^ (etid & 7)) << 4) + (p.c & 7) * 2) = T16<T>::from_f(1.f);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+#ifdef BUCTD_ROLE_TIMERS
+    PT_ADD(x_tot, x_start);
+    if (blockIdx.x == 3 && blockIdx.y == 1 && threadIdx.x == 64 + 5) {
+      g_pa_cycles[4] = x_tot; g_pa_cycles[5] = x_bar; g_pa_cycles[6] = x_s; g_pa_cycles[7] = x_o; g_pa_cycles[8] = x_main;
+      g_pa_cycles[9] = x_v; g_pa_cycles[10] = x_redo; g_pa_cycles[11] = ntiles;
+    }
+#endif
+    // ---- finalise ---------------------------------------------------------------------------------------------
+    mbar_wait(o_done, (ntiles - 1) & 1);
+    tc_fence_after();
+    const int r = m0 + row;
+    const bool ok = r < p.nrows;
+    const bool pad = ok && ((r % Wp) == p.W || (r / Wp) == p.H);
+    if (ones) {                                               // l = O[row][C]
+      uint32_t lv;
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(lv) : "r"(tm_o + lane_off + p.c));
+      tmem_ld_wait();
+      l_run = __uint_as_float(lv);
+    }
+    const float inv = (ok && !pad) ? 1.f / l_run : 0.f;
+    T* go = reinterpret_cast<T*>(p.o) + ((long long)row_base + r) * p.o_cs;
+#pragma unroll 1
+    for (int c0 = 0; c0 < p.c; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(tm_o + lane_off + c0, v);
+      tmem_ld_wait();
+      if (ok) {
+        uint4 u0, u1;
+        u0.x = T16<T>::pack2(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
+        u0.y = T16<T>::pack2(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
+        u0.z = T16<T>::pack2(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
+        u0.w = T16<T>::pack2(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
+        u1.x = T16<T>::pack2(__uint_as_float(v[8]) * inv, __uint_as_float(v[9]) * inv);
+        u1.y = T16<T>::pack2(__uint_as_float(v[10]) * inv, __uint_as_float(v[11]) * inv);
+        u1.z = T16<T>::pack2(__uint_as_float(v[12]) * inv, __uint_as_float(v[13]) * inv);
+        u1.w = T16<T>::pack2(__uint_as_float(v[14]) * inv, __uint_as_float(v[15]) * inv);
+        if (c0 + 8 <= p.c) *reinterpret_cast<uint4*>(go + c0) = u0;
+        if (c0 + 16 <= p.c) *reinterpret_cast<uint4*>(go + c0 + 8) = u1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+#ifdef BUCTD_ROLE_TIMERS
+extern "C" __attribute__((visibility("default"))) int buctd_debug_pa_cycles(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_pa_cycles, sizeof(unsigned long long) * 16);
+}
+#endif
+
+static size_t tc_smem_bytes() { return 1024 + 6 * (size_t)kTcBlk + 2 * kTcTile * 4 + 256; }
+
+int pos_att_tc_init_device() {
+  BUCTD_CUDA(cudaFuncSetAttribute(pos_att_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes()));
+  BUCTD_CUDA(cudaFuncSetAttribute(pos_att_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes()));
+  return BUCTD_OK;
+}
+
+bool pos_att_tc_supported(const buctd_pos_att_args& a) {
+  const char* off = getenv("BUCTD_POSATT_LEGACY");
+  if (off && atoi(off)) return false;
+  return a.c % 8 == 0 && a.c >= 16 && a.c <= 64;
+}
+
+int launch_pos_att_tc(const buctd_pos_att_args& a, cudaStream_t st) {
+  EncodeTiledFn enc = get_encode_tiled();
+  BUCTD_CHECK(enc != nullptr, BUCTD_ERR_NO_DEVICE, "cuTensorMapEncodeTiled entry point not available");
+  const int nrows = (a.h + 1) * (a.w + 1);
+  const long long total = (long long)a.batch * nrows;
+  const CUtensorMapDataType dt = a.dtype == BUCTD_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUtensorMap mq, mk, mv;
+  const void* ptrs[3] = {a.q, a.k, a.v};
+  const int cs[3] = {a.q_cs, a.k_cs, a.v_cs};
+  CUtensorMap* maps[3] = {&mq, &mk, &mv};
+  for (int i = 0; i < 3; ++i) {
+    cuuint64_t dims[2] = {(cuuint64_t)a.c, (cuuint64_t)total};
+    cuuint64_t strides[1] = {(cuuint64_t)cs[i] * 2};
+    cuuint32_t box[2] = {64, kTcTile};
+    cuuint32_t es[2] = {1, 1};
+    CUresult cr = enc(maps[i], dt, 2, const_cast<void*>(ptrs[i]), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    BUCTD_CHECK(cr == CUDA_SUCCESS, BUCTD_ERR_CUDA, "cuTensorMapEncodeTiled(pos_att %d) failed: %d", i, (int)cr);
+  }
+  PosAttTcParams p;
+  p.nrows = nrows; p.W = a.w; p.H = a.h; p.c = a.c; p.o_cs = a.o_cs;
+  p.n2 = a.c < 64 ? (a.c + 1 + 15) / 16 * 16 : 64;      // PV output columns: C (+ the ones column when a slot is free)
+  p.sc = 1.4426950408889634f / sqrtf((float)a.c);
+  p.o = a.o;
+  dim3 grid((nrows + kTcTile - 1) / kTcTile, a.batch);
+  cudaError_t e;
+  if (a.dtype == BUCTD_F16) e = launch_pdl(pos_att_tc_kernel<__half>, grid, dim3(kTcThreads), tc_smem_bytes(), st, mq, mk, mv, p);
+  else e = launch_pdl(pos_att_tc_kernel<__nv_bfloat16>, grid, dim3(kTcThreads), tc_smem_bytes(), st, mq, mk, mv, p);
+  BUCTD_CHECK(e == cudaSuccess, BUCTD_ERR_CUDA, "pos_att_tc launch failed: %s", cudaGetErrorString(e));
+  BUCTD_CUDA(cudaGetLastError());
+  return BUCTD_OK;
+}
+
+}  // namespace buctd

@@ -30,11 +30,11 @@ namespace buctd {
 // Optional role timers (debug builds: -DBUCTD_ROLE_TIMERS): cycles each warp role spends waiting / working,
 // written to a global buffer [grid][8] that tools/role_timers.py reads back.
 #ifdef BUCTD_ROLE_TIMERS
-__device__ unsigned long long g_role_cycles[160 * 8];
+__device__ unsigned long long g_role_cycles[160 * 16];
 #define RT_DECL(name) long long name = 0
 #define RT_BEGIN(t) const long long t = clock64()
 #define RT_ADD(acc, t) acc += clock64() - t
-#define RT_STORE(slot, v) g_role_cycles[blockIdx.x * 8 + (slot)] = (unsigned long long)(v)
+#define RT_STORE(slot, v) g_role_cycles[blockIdx.x * 16 + (slot)] = (unsigned long long)(v)
 #else
 #define RT_DECL(name)
 #define RT_BEGIN(t)
@@ -45,7 +45,7 @@ __device__ unsigned long long g_role_cycles[160 * 8];
 constexpr int kBlockM = 128;
 constexpr int kATileBytes = kBlockM * 128;
 constexpr int kThreads = 192;          // patch kernel: producer + MMA + 4 epilogue warps
-constexpr int kSlabThreads = 320;      // slab kernel: producer + MMA + 8 epilogue warps (2 per TMEM lane quarter)
+constexpr int kSlabThreads = 352;      // slab kernel: producer + MMA + 8 epilogue warps (2 per TMEM lane quarter) + DMA warp
 constexpr int kSmemBudget = 227 * 1024;
 
 template <int BN> __host__ __device__ constexpr int patch_stages() { return BN <= 128 ? 4 : 3; }
@@ -105,6 +105,8 @@ tapgemm_patch_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();                                   // inputs of this kernel are produced by the previous one
   const uint32_t tmem_base = *tmem_slot;
   const int iters = p.ntaps * p.num_kc;
 
@@ -201,8 +203,9 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint64_t* w_empty = w_full + 8;             // [sw]
   uint64_t* acc_full = w_empty + 8;           // [2]
   uint64_t* acc_empty = acc_full + 2;         // [2]
-  uint64_t* res_bar = acc_empty + 2;          // [2] residual tile landed in stage buffer e
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
+  uint64_t* st_ready = acc_empty + 2;         // [2] stage buffer e may be written (its residual tile, if any, has landed)
+  uint64_t* st_done = st_ready + 2;           // [2] stage buffer e holds a finished 16-bit tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(st_done + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -212,7 +215,10 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     tma_prefetch_desc(&map_b);
     for (int s = 0; s < 4; ++s) { mbar_init(&slab_full[s], 1); mbar_init(&slab_empty[s], 1); }
     for (int s = 0; s < 8; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); mbar_init(&res_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8);
+      mbar_init(&st_ready[s], 1); mbar_init(&st_done[s], 8);
+    }
     tma_prefetch_desc(&map_out);
     fence_mbar_init();
   }
@@ -220,6 +226,8 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();                                   // inputs of this kernel are produced by the previous one
   const uint32_t tmem_base = *tmem_slot;
   const int R = MSUB * kBlockM;
 
@@ -318,11 +326,7 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     __syncwarp();
   } else {
-    const int etid = threadIdx.x - 64;
-    RT_DECL(e_wait); RT_DECL(e_total);
-    RT_BEGIN(e_start);
-    const int q = warp & 3;
-    const int grp = (warp - 2) >> 2;          // 0: warps 2..5, 1: warps 6..9
+    // ---- epilogue: warps 2..9 compute (TMEM -> stage), warp 10 moves tiles (residual TMA loads, TMA stores) ----
     const bool has_res = p.residual != nullptr;
     const bool head = p.out_mode == BUCTD_OUT_NCHW32;
     const int SE = sp.stage_bufs;
@@ -337,65 +341,78 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       t.m0 = (long long)s * R + (long long)j * kBlockM;
       t.tb = t.ty0 = t.tx0 = 0;
     };
-    if (has_res && etid == 0 && total_u > 0) {
-      EpiTile t0; int nt0;
-      sub(0, t0, nt0);
-      epi_load_residual<BN>(p, &map_res, t0, nt0 * BN, stage, &res_bar[0]);
-    }
-    int cur_nt = -1;
-    for (int u = 0; u < total_u; ++u) {
-      const int k = u / MSUB, j = u - k * MSUB;
-      const uint32_t buf = k & 1;
-      const int e = SE == 2 ? (u & 1) : 0;
-      uint8_t* st = stage + (size_t)e * epi_stage_bytes<BN>();
-      EpiTile tile; int nt;
-      sub(u, tile, nt);
-      if (nt != cur_nt) {                      // (re)load the bias tile of this N tile
-        epi_sync<256>();
-        epi_load_bias<BN, 256>(p, nt * BN, s_bias, etid);
-        cur_nt = nt;
-        epi_sync<256>();
-      }
-      if (j == 0) {
-        RT_BEGIN(t0); mbar_wait(&acc_full[buf], (k >> 1) & 1); RT_ADD(e_wait, t0);
-        tc_fence_after();
-      }
-      const uint32_t acc = tmem_base + (buf * MSUB + j) * BN;
-      if (head) {
-        if (grp == 0) epi_head_nchw32<BN>(p, tile, nt * BN, acc, q, lane);
-      } else {
-        if (etid == 0) {
-          // stores are committed one group per sub-tile, in order.  SE == 2: store(u-1) (other buffer) must have
-          // been read before the residual of u+1 lands there; SE == 1: store(u-1) used this very buffer.
-          tma_store_wait_read<0>();
+    if (warp == 10) {
+      if (!head && elect_one()) {
+        // prepare(u): the store that last used buffer u%SE has been read -> (re)fill it with the residual tile
+        auto prepare = [&](int u) {
+          const int e = SE == 2 ? (u & 1) : 0;
           if (has_res) {
-            if (SE == 2) {
-              if (u + 1 < total_u) {
-                EpiTile tn; int ntn;
-                sub(u + 1, tn, ntn);
-                epi_load_residual<BN>(p, &map_res, tn, ntn * BN, stage + (size_t)(e ^ 1) * epi_stage_bytes<BN>(), &res_bar[e ^ 1]);
-              }
-            } else if (u > 0) {
-              epi_load_residual<BN>(p, &map_res, tile, nt * BN, st, &res_bar[0]);
-            }
+            EpiTile t; int nt;
+            sub(u, t, nt);
+            epi_load_residual<BN>(p, &map_res, t, nt * BN, stage + (size_t)e * epi_stage_bytes<BN>(), &st_ready[e]);
+          } else {
+            mbar_arrive(&st_ready[e]);
+          }
+        };
+        for (int u = 0; u < SE && u < total_u; ++u) prepare(u);
+        for (int u = 0; u < total_u; ++u) {
+          const int e = SE == 2 ? (u & 1) : 0;
+          mbar_wait(&st_done[e], (SE == 2 ? (u >> 1) : u) & 1);
+          EpiTile t; int nt;
+          sub(u, t, nt);
+          epi_store<BN>(p, &map_out, t, nt * BN, stage + (size_t)e * epi_stage_bytes<BN>());
+          if (u + SE < total_u) {
+            tma_store_wait_read<0>();          // buffer e is free again once its store has read it
+            prepare(u + SE);
           }
         }
-        if (SE == 1 && !has_res) epi_sync<256>();   // nobody may overwrite the stage before store(u-1) has been read
-        if (has_res) mbar_wait(&res_bar[e], (SE == 2 ? (u >> 1) : u) & 1);
-        epi_compute<T, BN>(p, tile, nt * BN, acc, st, s_bias, has_res, q, lane, grp, 2);
-        fence_proxy_async_smem();
-        epi_sync<256>();
-        if (etid == 0) epi_store<BN>(p, &map_out, tile, nt * BN, st);
+        tma_store_wait_all();
       }
-      if (j == MSUB - 1) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      __syncwarp();
+    } else {
+      const int etid = threadIdx.x - 64;
+      RT_DECL(e_wait); RT_DECL(e_total); RT_DECL(e_res); RT_DECL(e_comp);
+      RT_BEGIN(e_start);
+      const int q = warp & 3;
+      const int grp = (warp - 2) >> 2;          // 0: warps 2..5, 1: warps 6..9
+      int cur_nt = -1;
+      for (int u = 0; u < total_u; ++u) {
+        const int k = u / MSUB, j = u - k * MSUB;
+        const uint32_t buf = k & 1;
+        const int e = SE == 2 ? (u & 1) : 0;
+        uint8_t* st = stage + (size_t)e * epi_stage_bytes<BN>();
+        EpiTile tile; int nt;
+        sub(u, tile, nt);
+        if (nt != cur_nt) {                      // (re)load the bias tile of this N tile
+          epi_sync<256>();
+          epi_load_bias<BN, 256>(p, nt * BN, s_bias, etid);
+          cur_nt = nt;
+          epi_sync<256>();
+        }
+        if (j == 0) {
+          RT_BEGIN(t0); mbar_wait(&acc_full[buf], (k >> 1) & 1); RT_ADD(e_wait, t0);
+          tc_fence_after();
+        }
+        const uint32_t acc = tmem_base + (buf * MSUB + j) * BN;
+        if (head) {
+          if (grp == 0) epi_head_nchw32<BN>(p, tile, nt * BN, acc, q, lane);
+        } else {
+          { RT_BEGIN(t0); mbar_wait(&st_ready[e], (SE == 2 ? (u >> 1) : u) & 1); RT_ADD(e_res, t0); }
+          { RT_BEGIN(t0); epi_compute<T, BN>(p, tile, nt * BN, acc, st, s_bias, has_res, q, lane, grp, 2); RT_ADD(e_comp, t0); }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&st_done[e]);
+        }
+        if (j == MSUB - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
       }
+      RT_ADD(e_total, e_start);
+      if (threadIdx.x == 64) { RT_STORE(4, e_total); RT_STORE(5, e_wait); RT_STORE(9, e_res); RT_STORE(10, e_comp); }
+      if (threadIdx.x == 64 + 37) { RT_STORE(13, e_comp); }
     }
-    if (etid == 0) tma_store_wait_all();
-    RT_ADD(e_total, e_start);
-    if (threadIdx.x == 64) { RT_STORE(4, e_total); RT_STORE(5, e_wait); }
   }
   tc_fence_before();
   __syncthreads();
@@ -527,14 +544,16 @@ static int plan_slab(const buctd_tapgemm_args& a, int bn, int n_tiles, int num_k
 template <typename T, int BN, int MSUB>
 static void launch_slab(const TapGemmLaunch& L, cudaStream_t st) {
   if constexpr (2 * MSUB * BN <= 512) {
-    tapgemm_slab_kernel<T, BN, MSUB><<<L.grid, kSlabThreads, L.sp.smem_bytes, st>>>(L.map_a, L.map_b, L.map_out, L.map_res, L.kp, L.sp);
+    launch_pdl(tapgemm_slab_kernel<T, BN, MSUB>, L.grid, dim3(kSlabThreads), L.sp.smem_bytes, st, L.map_a, L.map_b, L.map_out,
+               L.map_res, L.kp, L.sp);
   }
 }
 
 template <typename T, int BN>
 static int launch_one(const TapGemmLaunch& L, cudaStream_t st) {
   if (L.kp.mode == BUCTD_TG_PATCH) {
-    tapgemm_patch_kernel<T, BN><<<L.grid, kThreads, patch_smem_bytes(BN), st>>>(L.map_a, L.map_b, L.map_out, L.map_res, L.kp);
+    launch_pdl(tapgemm_patch_kernel<T, BN>, L.grid, dim3(kThreads), patch_smem_bytes(BN), st, L.map_a, L.map_b, L.map_out, L.map_res,
+               L.kp);
   } else {
     switch (L.sp.msub) {
       case 1: launch_slab<T, BN, 1>(L, st); break;
