@@ -16,6 +16,13 @@ ABI_VERSION = 1
 F16, BF16 = 0, 1
 TG_FLAT, TG_PATCH = 0, 1
 OUT_ACT16, OUT_ROWS16, OUT_NCHW32 = 0, 1, 2
+CHAN_ATT_ROWS_PER_CHUNK = 256
+
+
+def chan_att_scratch_floats(batch: int, h: int, w: int, c: int) -> int:
+    """float32 elements of scratch buctd_coam_channel_att needs (per-chunk partial [C][C] score matrices)"""
+    nchunks = ((h + 1) * (w + 1) + CHAN_ATT_ROWS_PER_CHUNK - 1) // CHAN_ATT_ROWS_PER_CHUNK
+    return batch * nchunks * c * c
 (OP_TAPGEMM, OP_STEM, OP_FUSE, OP_RESIZE, OP_CHAN_ATT, OP_POS_ATT, OP_DA_COMBINE, OP_PRENET, OP_DECODE,
  OP_RASTER) = range(1, 11)
 

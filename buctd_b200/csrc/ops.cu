@@ -360,17 +360,17 @@ int launch_resize(const buctd_resize_args& a, cudaStream_t st) {
 //   over all (H+1)(W+1) rows), att = softmax_c2(S), out[c1][p] = sum_c2 att[c1][c2] * y[p][c2].
 // lib/models/self_attention.py:146-158; lib/models/pose_hrnet_coam.py:673-689.
 // =================================================================================================
-// S is computed in kCaTile x kCaTile output tiles per block (16x16 threads x PER x PER); kCaTile is 48
-// for the W48 family (C = 48/96/192) and 32 for W32 (C = 32/64/128).
+// S is computed in kCaTile x kCaTile output tiles per block by 8x8 threads, each holding a PER x PER register tile
+// (6x6 for the W48 family: 36 FMAs per 12 shared-memory words); kCaTile is 48 for C = 48/96/192 and 32 for C = 32/64/128.
 constexpr int kCaRows = 32;      // rows staged per step
 
 template <typename T, int kCaTile>
-__global__ void __launch_bounds__(256) chan_scores_kernel(buctd_chan_att_args a, int rows_per_chunk) {
+__global__ void __launch_bounds__(64) chan_scores_kernel(buctd_chan_att_args a, int rows_per_chunk) {
   pdl_launch_dependents();
   pdl_wait();
-  constexpr int PER = kCaTile / 16;
-  __shared__ float s_q[kCaRows][kCaTile + 1];
-  __shared__ float s_k[kCaRows][kCaTile + 1];
+  constexpr int PER = kCaTile / 8;
+  __shared__ __align__(8) float s_q[kCaRows][kCaTile + 2];
+  __shared__ __align__(8) float s_k[kCaRows][kCaTile + 2];
   const int b = blockIdx.z;
   const int tiles = a.c / kCaTile;
   const int t1 = blockIdx.y / tiles, t2 = blockIdx.y % tiles;
@@ -379,21 +379,35 @@ __global__ void __launch_bounds__(256) chan_scores_kernel(buctd_chan_att_args a,
   const long long r1 = min(rows, r0 + rows_per_chunk);
   const T* yc = reinterpret_cast<const T*>(a.yc) + (long long)b * rows * a.yc_cs + t1 * kCaTile;
   const T* y = reinterpret_cast<const T*>(a.y) + (long long)b * rows * a.y_cs + t2 * kCaTile;
-  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const int tx = threadIdx.x % 8, ty = threadIdx.x / 8;
   float acc[PER][PER] = {};
   for (long long r = r0; r < r1; r += kCaRows) {
-    for (int i = threadIdx.x; i < kCaRows * kCaTile; i += 256) {
-      int rr = i / kCaTile, cc = i % kCaTile;
-      bool ok = r + rr < r1;
-      s_q[rr][cc] = ok ? T16<T>::to_f(yc[(r + rr) * a.yc_cs + cc]) : 0.f;
-      s_k[rr][cc] = ok ? T16<T>::to_f(y[(r + rr) * a.y_cs + cc]) : 0.f;
+    // 8 channels (16 bytes) per load
+    for (int i = threadIdx.x; i < kCaRows * (kCaTile / 8); i += 64) {
+      const int rr = i / (kCaTile / 8), c8 = (i % (kCaTile / 8)) * 8;
+      uint4 uq = make_uint4(0, 0, 0, 0), uk = make_uint4(0, 0, 0, 0);
+      if (r + rr < r1) {
+        uq = *reinterpret_cast<const uint4*>(yc + (r + rr) * a.yc_cs + c8);
+        uk = *reinterpret_cast<const uint4*>(y + (r + rr) * a.y_cs + c8);
+      }
+      const uint32_t wq[4] = {uq.x, uq.y, uq.z, uq.w}, wk[4] = {uk.x, uk.y, uk.z, uk.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 fq = T16<T>::unpack2(wq[k]), fk = T16<T>::unpack2(wk[k]);
+        *reinterpret_cast<float2*>(&s_q[rr][c8 + 2 * k]) = fq;
+        *reinterpret_cast<float2*>(&s_k[rr][c8 + 2 * k]) = fk;
+      }
     }
     __syncthreads();
 #pragma unroll 4
     for (int rr = 0; rr < kCaRows; ++rr) {
       float q[PER], k[PER];
 #pragma unroll
-      for (int i = 0; i < PER; ++i) { q[i] = s_q[rr][ty * PER + i]; k[i] = s_k[rr][tx * PER + i]; }
+      for (int i = 0; i < PER; i += 2) {
+        const float2 fq = *reinterpret_cast<const float2*>(&s_q[rr][ty * PER + i]);
+        const float2 fk = *reinterpret_cast<const float2*>(&s_k[rr][tx * PER + i]);
+        q[i] = fq.x; q[i + 1] = fq.y; k[i] = fk.x; k[i + 1] = fk.y;
+      }
 #pragma unroll
       for (int i = 0; i < PER; ++i)
 #pragma unroll
@@ -401,22 +415,30 @@ __global__ void __launch_bounds__(256) chan_scores_kernel(buctd_chan_att_args a,
     }
     __syncthreads();
   }
-  float* S = a.scratch + (long long)b * a.c * a.c;
+  // deterministic: every row chunk owns its own partial [C][C] (summed in fixed order by the soft-max kernel)
+  float* S = a.scratch + ((long long)b * gridDim.x + blockIdx.x) * a.c * a.c;
 #pragma unroll
   for (int i = 0; i < PER; ++i)
 #pragma unroll
     for (int j = 0; j < PER; ++j)
-      atomicAdd(&S[(long long)(t1 * kCaTile + ty * PER + i) * a.c + t2 * kCaTile + tx * PER + j], acc[i][j]);
+      S[(long long)(t1 * kCaTile + ty * PER + i) * a.c + t2 * kCaTile + tx * PER + j] = acc[i][j];
 }
 
-__global__ void chan_softmax_kernel(float* S, int c, float scale, int nrows) {
+__global__ void chan_softmax_kernel(float* S, int c, float scale, int nrows, int nchunks) {
   pdl_launch_dependents();
   pdl_wait();
-  // one warp per row of S
+  // one warp per row (b, c1) of S; first reduce the row-chunk partials [b][chunk][c1][:] into chunk 0, in order
   const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   const int lane = threadIdx.x & 31;
   if (row >= nrows) return;
-  float* p = S + (long long)row * c;
+  const int b = row / c, c1 = row - b * c;
+  float* p = S + ((long long)b * nchunks * c + c1) * c;
+  for (int i = lane; i < c; i += 32) {
+    float t = p[i];
+    for (int k = 1; k < nchunks; ++k) t += p[(long long)k * c * c + i];
+    p[i] = t;
+  }
+  __syncwarp();
   float m = -INFINITY;
   for (int i = lane; i < c; i += 32) m = fmaxf(m, p[i] * scale);
   for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffff, m, o));
@@ -429,44 +451,68 @@ __global__ void chan_softmax_kernel(float* S, int c, float scale, int nrows) {
 
 constexpr int kCaPix = 64;
 template <typename T, int kCaTile>
-__global__ void __launch_bounds__(256) chan_apply_kernel(buctd_chan_att_args a) {
+__global__ void __launch_bounds__(128) chan_apply_kernel(buctd_chan_att_args a) {
   pdl_launch_dependents();
   pdl_wait();
-  // block: 64 valid pixels x kCaTile output channels (c1 tile); dynamic smem: att[tile][C] f32, y[64][C+1] f32
-  constexpr int G = kCaTile / 4;   // channels per thread group
+  // block: 64 valid pixels x kCaTile output channels (c1 tile); thread = 4 pixels x G channels.
+  // dynamic smem: att[tile][C] f32, y[64][C+1] f32, out[tile][64] 16-bit
+  constexpr int G = kCaTile / 8;
   extern __shared__ float s_dyn[];
-  float* s_att = s_dyn;                         // [48][C]
+  float* s_att = s_dyn;                         // [tile][C]
   float* s_y = s_dyn + kCaTile * a.c;           // [64][C+1]
   const int b = blockIdx.z, t1 = blockIdx.y;
   const int hw = a.h * a.w;
   const int p0 = blockIdx.x * kCaPix;
   const int cs1 = a.c + 1;
-  const float* att = a.scratch + ((long long)b * a.c + t1 * kCaTile) * a.c;
-  for (int i = threadIdx.x; i < kCaTile * a.c; i += 256) s_att[i] = att[i];
+  const int nchunks = (int)(((long long)(a.h + 1) * (a.w + 1) + BUCTD_CHAN_ATT_ROWS_PER_CHUNK - 1) / BUCTD_CHAN_ATT_ROWS_PER_CHUNK);
+  const float* att = a.scratch + ((long long)b * nchunks * a.c + t1 * kCaTile) * a.c;     // probabilities live in chunk 0
+  for (int i = threadIdx.x; i < kCaTile * a.c; i += 128) s_att[i] = att[i];
   const T* y = reinterpret_cast<const T*>(a.y) + (long long)b * (a.h + 1) * (a.w + 1) * a.y_cs;
-  for (int i = threadIdx.x; i < kCaPix * a.c; i += 256) {
-    int pp = i / a.c, cc = i % a.c;
-    int p = p0 + pp;
-    float v = 0.f;
+  for (int i = threadIdx.x; i < kCaPix * (a.c / 8); i += 128) {
+    const int pp = i / (a.c / 8), c8 = (i % (a.c / 8)) * 8;
+    const int p = p0 + pp;
+    uint4 u = make_uint4(0, 0, 0, 0);
     if (p < hw) {
-      int py = p / a.w, px = p % a.w;
-      v = T16<T>::to_f(y[((long long)py * (a.w + 1) + px) * a.y_cs + cc]);
+      const int py = p / a.w, px = p % a.w;
+      u = *reinterpret_cast<const uint4*>(y + ((long long)py * (a.w + 1) + px) * a.y_cs + c8);
     }
-    s_y[pp * cs1 + cc] = v;
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = T16<T>::unpack2(w[k]);
+      s_y[pp * cs1 + c8 + 2 * k] = f.x;
+      s_y[pp * cs1 + c8 + 2 * k + 1] = f.y;
+    }
   }
   __syncthreads();
-  const int pp = threadIdx.x % kCaPix, g = threadIdx.x / kCaPix;   // 4 groups x G channels
-  float acc[G] = {};
+  const int pg = threadIdx.x % 16, cg = threadIdx.x / 16;      // 16 pixel groups x 8 channel groups
+  float acc[4][G] = {};
   for (int c2 = 0; c2 < a.c; ++c2) {
-    const float yv = s_y[pp * cs1 + c2];
+    float yv[4], av[G];
 #pragma unroll
-    for (int i = 0; i < G; ++i) acc[i] = fmaf(s_att[(g * G + i) * a.c + c2], yv, acc[i]);
+    for (int i = 0; i < 4; ++i) yv[i] = s_y[(pg * 4 + i) * cs1 + c2];
+#pragma unroll
+    for (int j = 0; j < G; ++j) av[j] = s_att[(cg * G + j) * a.c + c2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < G; ++j) acc[i][j] = fmaf(av[j], yv[i], acc[i][j]);
   }
-  const int p = p0 + pp;
-  if (p < hw) {
-    T* o = reinterpret_cast<T*>(a.out) + ((long long)b * a.c + t1 * kCaTile + g * G) * hw + p;
+  // 4 consecutive pixels of one channel = 8 bytes
 #pragma unroll
-    for (int i = 0; i < G; ++i) o[(long long)i * hw] = T16<T>::from_f(acc[i]);
+  for (int j = 0; j < G; ++j) {
+    const int p = p0 + pg * 4;
+    T* o = reinterpret_cast<T*>(a.out) + ((long long)b * a.c + t1 * kCaTile + cg * G + j) * hw + p;
+    if (p + 4 <= hw && ((hw & 3) == 0)) {
+      uint2 u;
+      u.x = T16<T>::pack2(acc[0][j], acc[1][j]);
+      u.y = T16<T>::pack2(acc[2][j], acc[3][j]);
+      *reinterpret_cast<uint2*>(o) = u;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (p + i < hw) o[i] = T16<T>::from_f(acc[i][j]);
+    }
   }
 }
 
@@ -474,15 +520,15 @@ template <typename T, int TILE>
 static int chan_att_run(const buctd_chan_att_args& a, cudaStream_t st) {
   const long long rows = (long long)(a.h + 1) * (a.w + 1);
   const int tiles = a.c / TILE;
-  const int chunk = 512;
+  const int chunk = BUCTD_CHAN_ATT_ROWS_PER_CHUNK;
   dim3 g1((unsigned)((rows + chunk - 1) / chunk), tiles * tiles, a.batch);
   const size_t smem = sizeof(float) * ((size_t)TILE * a.c + (size_t)kCaPix * (a.c + 1));
   dim3 g3(ceil_div(a.h * a.w, kCaPix), tiles, a.batch);
   const float scale = 1.f / sqrtf((float)(a.h * a.w));
-  launch_pdl(chan_scores_kernel<T, TILE>, g1, dim3(256), 0, st, a, chunk);
-  launch_pdl(chan_softmax_kernel, dim3(ceil_div(a.batch * a.c, 8)), dim3(256), 0, st, a.scratch, a.c, scale, a.batch * a.c);
+  launch_pdl(chan_scores_kernel<T, TILE>, g1, dim3(64), 0, st, a, chunk);
+  launch_pdl(chan_softmax_kernel, dim3(ceil_div(a.batch * a.c, 8)), dim3(256), 0, st, a.scratch, a.c, scale, a.batch * a.c, (int)g1.x);
   BUCTD_CUDA(cudaFuncSetAttribute(chan_apply_kernel<T, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  launch_pdl(chan_apply_kernel<T, TILE>, g3, dim3(256), smem, st, a);
+  launch_pdl(chan_apply_kernel<T, TILE>, g3, dim3(128), smem, st, a);
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;
 }
@@ -491,7 +537,6 @@ int launch_chan_att(const buctd_chan_att_args& a, cudaStream_t st, int* nlaunch)
   BUCTD_CHECK(a.c % 48 == 0 || a.c % 32 == 0, BUCTD_ERR_INVALID, "chan_att: C=%d must be a multiple of 48 or 32", a.c);
   BUCTD_CHECK(a.y && a.yc && a.scratch && a.out, BUCTD_ERR_INVALID, "chan_att: null pointer");
   BUCTD_CHECK(a.c <= 256, BUCTD_ERR_INVALID, "chan_att: C=%d too large for the shared-memory tile", a.c);
-  BUCTD_CUDA(cudaMemsetAsync(a.scratch, 0, sizeof(float) * (size_t)a.batch * a.c * a.c, st));
   if (nlaunch) *nlaunch = 3;
   const bool t48 = a.c % 48 == 0;
   if (a.dtype == BUCTD_F16) return t48 ? chan_att_run<__half, 48>(a, st) : chan_att_run<__half, 32>(a, st);

@@ -240,28 +240,30 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           for (int t = 0; t < p.ntaps; ++t)
             tma_load_2d(wbuf + (size_t)(kc * p.ntaps + t) * kWTileBytes, &map_b, &w_full[0], kc * 64, t * p.n_alloc);
       }
-      uint32_t sa_it = 0, sw_it = 0;
+      uint32_t slot = 0, slot_ph = 1, ws = 0, ws_ph = 1;     // producer waits on the "empty" phase (starts free)
+      int s = blockIdx.x % sp.num_super, nt = blockIdx.x / sp.num_super;
+      const int ds = gridDim.x % sp.num_super, dn = gridDim.x / sp.num_super;
       for (int item = blockIdx.x; item < sp.num_items; item += gridDim.x) {
-        const int s = item % sp.num_super, nt = item / sp.num_super;
         const long long r0 = (long long)s * R - sp.halo;
         for (int kc = 0; kc < p.num_kc; ++kc) {
-          const uint32_t slot = sa_it % sp.sa;
-          mbar_wait(&slab_empty[slot], ((sa_it / sp.sa) & 1) ^ 1);
+          mbar_wait(&slab_empty[slot], slot_ph);
           mbar_expect_tx(&slab_full[slot], (uint32_t)sp.slab_bytes);
           for (int i = 0; i < sp.nboxes; ++i)
             tma_load_2d(slabs + (size_t)slot * sp.slab_bytes + (size_t)i * sp.box_rows * 128, &map_a, &slab_full[slot],
                         kc * 64, (int)(r0 + (long long)i * sp.box_rows));
-          ++sa_it;
+          if (++slot == (uint32_t)sp.sa) { slot = 0; slot_ph ^= 1; }
           if (!sp.w_resident) {
             for (int t = 0; t < p.ntaps; ++t) {
-              const uint32_t ws = sw_it % sp.sw;
-              mbar_wait(&w_empty[ws], ((sw_it / sp.sw) & 1) ^ 1);
+              mbar_wait(&w_empty[ws], ws_ph);
               mbar_expect_tx(&w_full[ws], kWTileBytes);
               tma_load_2d(wbuf + (size_t)ws * kWTileBytes, &map_b, &w_full[ws], kc * 64, t * p.n_alloc + nt * BN);
-              ++sw_it;
+              if (++ws == (uint32_t)sp.sw) { ws = 0; ws_ph ^= 1; }
             }
           }
         }
+        // next item of this CTA: (s, nt) += gridDim.x in mixed radix, without a division
+        s += ds; nt += dn;
+        if (s >= sp.num_super) { s -= sp.num_super; ++nt; }
       }
     }
   } else if (warp == 1) {
@@ -269,7 +271,9 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // uniform registers: ~2 SASS instructions per tcgen05.mma).
     if (elect_one()) {
       const uint32_t idesc = umma_idesc_f16(T16<T>::kFmt, kBlockM, BN);
-      uint32_t sa_it = 0, sw_it = 0, it_local = 0;
+      uint32_t it_local = 0;
+      uint32_t slot = 0, slot_ph = 0;          // slab ring position / phase (wrap counters: no runtime div/mod in this thread)
+      uint32_t ws = 0, ws_ph = 0;              // weight ring position / phase
       RT_DECL(t_acc); RT_DECL(t_slab); RT_DECL(t_w); RT_DECL(t_total); RT_DECL(t_issue); RT_DECL(t_commit);
       RT_BEGIN(t_start);
       const uint32_t slab0_addr = smem_u32(slabs);
@@ -283,9 +287,9 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         { RT_BEGIN(t0); mbar_wait(&acc_empty[buf], ((it_local >> 1) & 1) ^ 1); RT_ADD(t_acc, t0); }
         tc_fence_after();
         const uint32_t d0 = tmem_base + buf * MSUB * BN;
+        uint32_t w_res_addr = wbuf_addr;         // resident weights: tile (kc, t) lives at (kc*ntaps + t) * kWTileBytes
         for (int kc = 0; kc < p.num_kc; ++kc) {
-          const uint32_t slot = sa_it % sp.sa;
-          { RT_BEGIN(t0); mbar_wait(&slab_full[slot], (sa_it / sp.sa) & 1); RT_ADD(t_slab, t0); }
+          { RT_BEGIN(t0); mbar_wait(&slab_full[slot], slot_ph); RT_ADD(t_slab, t0); }
           tc_fence_after();
           const uint32_t slab_addr = slab0_addr + slot * (uint32_t)sp.slab_bytes;
           const int ksteps = min(64, p.k16 - kc * 64) >> 4;
@@ -294,12 +298,11 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           for (int t = 0; t < 9; ++t) {
             if (t < p.ntaps) {
               uint32_t w_addr;
-              uint32_t ws = 0;
               if (sp.w_resident) {
-                w_addr = wbuf_addr + (uint32_t)(kc * p.ntaps + t) * kWTileBytes;
+                w_addr = w_res_addr;
+                w_res_addr += kWTileBytes;
               } else {
-                ws = sw_it % sp.sw;
-                { RT_BEGIN(t0); mbar_wait(&w_full[ws], (sw_it / sp.sw) & 1); RT_ADD(t_w, t0); }
+                { RT_BEGIN(t0); mbar_wait(&w_full[ws], ws_ph); RT_ADD(t_w, t0); }
                 tc_fence_after();
                 w_addr = wbuf_addr + ws * kWTileBytes;
               }
@@ -312,12 +315,15 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 case 3: mma_batch<BN, MSUB, 3>(d0, adesc0, bdesc, idesc, first); break;
                 default: mma_batch<BN, MSUB, 4>(d0, adesc0, bdesc, idesc, first); break;
               }
-              if (!sp.w_resident) { tc_commit(&w_empty[ws]); ++sw_it; }
+              if (!sp.w_resident) {
+                tc_commit(&w_empty[ws]);
+                if (++ws == (uint32_t)sp.sw) { ws = 0; ws_ph ^= 1; }
+              }
             }
           }
           RT_ADD(t_issue, t_i0);
           tc_commit(&slab_empty[slot]);
-          ++sa_it;
+          if (++slot == (uint32_t)sp.sa) { slot = 0; slot_ph ^= 1; }
         }
         tc_commit(&acc_full[buf]);
       }

@@ -423,7 +423,7 @@ class PoseHighResolutionNet(nn.Module):
             specs.append((L.OP_TAPGEMM, ("tg", da.chan_cnn_cond.w, cond, yc, dict(stride=1, relu=False, residual=None, k=cc)),
                           da.chan_cnn_cond.w))
             planar = raw(batch * C_ * h * w * 2)
-            scratch = raw(batch * C_ * C_ * 4)
+            scratch = raw(L.chan_att_scratch_floats(batch, h, w, C_) * 4)
             c_out = raw(batch * C_ * h * w * 2)
             specs.append((L.OP_CHAN_ATT, ("chan", y, yc, scratch, planar), p + ":chan_att"))
             specs.append((L.OP_TAPGEMM, ("lin_planar", da.chan_fc_o.w, planar, c_out, batch * C_, h * w), da.chan_fc_o.w))

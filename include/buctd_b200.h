@@ -130,10 +130,13 @@ int buctd_cond_resize(buctd_ctx* ctx, const buctd_resize_args* args, buctd_strea
 
 /* CoAM channel attention core: att = softmax_c2( yc^T y / sqrt(HW) ) [C x C] per crop, then
  * out[c1][p] = sum_c2 att[c1][c2] y[p][c2], written planar [B][C][HW] (the A operand of the
- * HW x HW fc_o tap-GEMM).  y, yc: act16 [B][H+1][W+1][cs].  scratch: float32 [B][C][C].
+ * HW x HW fc_o tap-GEMM).  y, yc: act16 [B][H+1][W+1][cs].  scratch: float32 [B][nchunks][C][C] with
+ * nchunks = ceil((H+1)(W+1) / BUCTD_CHAN_ATT_ROWS_PER_CHUNK) (per-chunk partial sums, reduced in a fixed order:
+ * the result is bit-reproducible); after the call [b][0][:][:] holds the soft-max probabilities.
  * Replaces SimplifiedScaledDotProductAttention.forward up to fc_o,
  * lib/models/self_attention.py:146-158 as called from ChannelAttentionModule.forward,
  * lib/models/pose_hrnet_coam.py:673-689. */
+#define BUCTD_CHAN_ATT_ROWS_PER_CHUNK 256
 typedef struct {
   int32_t dtype, batch, h, w, c, y_cs, yc_cs, reserved;
   const void* y; const void* yc; float* scratch; void* out;
