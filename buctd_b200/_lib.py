@@ -10,13 +10,14 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbuctd_b200.so")
+LIB_PATH = os.environ.get("BUCTD_LIB") or os.path.join(_HERE, "libbuctd_b200.so")   # BUCTD_LIB: debug builds (role timers)
 
 ABI_VERSION = 1
 F16, BF16 = 0, 1
 TG_FLAT, TG_PATCH = 0, 1
 OUT_ACT16, OUT_ROWS16, OUT_NCHW32 = 0, 1, 2
 CHAN_ATT_ROWS_PER_CHUNK = 256
+MAX_LANES = 8
 
 
 def chan_att_scratch_floats(batch: int, h: int, w: int, c: int) -> int:
@@ -95,7 +96,8 @@ EXPORTS = ["buctd_abi_version", "buctd_last_error", "buctd_create", "buctd_destr
            "buctd_tapgemm", "buctd_stem_conv", "buctd_hr_fuse", "buctd_cond_resize", "buctd_coam_channel_att",
            "buctd_coam_position_att", "buctd_da_combine", "buctd_prenet", "buctd_decode_heatmaps",
            "buctd_rasterize_condition", "buctd_act16_to_nchw32", "buctd_nchw32_to_act16", "buctd_plan_create",
-           "buctd_plan_destroy", "buctd_plan_add", "buctd_plan_size", "buctd_plan_run", "buctd_plan_run_range"]
+           "buctd_plan_destroy", "buctd_plan_add", "buctd_plan_add_lane", "buctd_plan_num_lanes", "buctd_plan_instantiate",
+           "buctd_plan_size", "buctd_plan_run", "buctd_plan_run_range"]
 
 _IMMEDIATE = {OP_TAPGEMM: "buctd_tapgemm", OP_STEM: "buctd_stem_conv", OP_FUSE: "buctd_hr_fuse",
               OP_RESIZE: "buctd_cond_resize", OP_CHAN_ATT: "buctd_coam_channel_att",
@@ -134,6 +136,9 @@ def load():
         lib.buctd_plan_create.argtypes = [vp, C.POINTER(vp)]
         lib.buctd_plan_destroy.argtypes = [vp]
         lib.buctd_plan_add.argtypes = [vp, C.c_int, vp, C.c_size_t]
+        lib.buctd_plan_add_lane.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_int, C.c_int]
+        lib.buctd_plan_instantiate.argtypes = [vp]
+        lib.buctd_plan_num_lanes.argtypes = [vp]
         lib.buctd_plan_size.argtypes = [vp]
         lib.buctd_plan_run.argtypes = [vp, vp]
         lib.buctd_plan_run_range.argtypes = [vp, C.c_int, C.c_int, vp]
@@ -195,18 +200,33 @@ class Plan:
         check(ctx.lib.buctd_plan_create(ctx.handle, C.byref(h)), "buctd_plan_create")
         self.handle = h
         self.labels = []
+        self.lanes = []
 
-    def add(self, kind: int, args: C.Structure, label: str = ""):
-        check(self.ctx.lib.buctd_plan_add(self.handle, kind, C.byref(args), C.sizeof(args)),
-              "buctd_plan_add(%s)" % (label or kind))
+    def add(self, kind: int, args: C.Structure, label: str = "", lane: int = 0, max_ctas: int = 0):
+        """lane: concurrent lane of the op (cross-lane dependencies are derived by the library from the buffers
+        the ops touch); max_ctas: SM share of a persistent tap-GEMM while other lanes run beside it (0 = all)."""
+        check(self.ctx.lib.buctd_plan_add_lane(self.handle, kind, C.byref(args), C.sizeof(args), int(lane), int(max_ctas)),
+              "buctd_plan_add_lane(%s)" % (label or kind))
         self.labels.append(label)
+        self.lanes.append(int(lane))
+
+    def instantiate(self):
+        """capture the plan into a CUDA graph; run() then costs one graph launch"""
+        check(self.ctx.lib.buctd_plan_instantiate(self.handle), "buctd_plan_instantiate")
+
+    @property
+    def num_lanes(self) -> int:
+        return int(self.ctx.lib.buctd_plan_num_lanes(self.handle))
 
     def __len__(self):
         return int(self.ctx.lib.buctd_plan_size(self.handle))
 
     def run(self, stream: int, first: int = 0, last: int | None = None):
+        if first == 0 and last is None:
+            check(self.ctx.lib.buctd_plan_run(self.handle, vp(stream)), "buctd_plan_run")
+            return
         last = len(self) if last is None else last
-        check(self.ctx.lib.buctd_plan_run_range(self.handle, first, last, vp(stream)), "buctd_plan_run")
+        check(self.ctx.lib.buctd_plan_run_range(self.handle, first, last, vp(stream)), "buctd_plan_run_range")
 
     def __del__(self):
         try:

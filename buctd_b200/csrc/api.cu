@@ -30,10 +30,21 @@ EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
+thread_local bool tl_use_pdl = true;
+
+struct Span {
+  uintptr_t lo, hi;     // [lo, hi) device bytes
+};
+
 struct PlanOp {
   int kind = 0;
   int nlaunch = 1;
+  int lane = 0;                 // concurrent lane (internal stream / parallel graph branch)
+  int ndeps = 0;                // cross-lane dependencies: the last conflicting op of every other lane
+  int deps[BUCTD_MAX_LANES];
+  bool record = false;          // some op on another lane waits for this one
   TapGemmLaunch tg;     // kind == TAPGEMM
+  buctd_tapgemm_args tga;
   union {
     buctd_stem_args stem;
     buctd_fuse_args fuse;
@@ -77,9 +88,8 @@ static int make_op(int kind, const void* args, size_t size, PlanOp* op, int sm_c
   op->kind = kind;
   switch (kind) {
     case BUCTD_OP_TAPGEMM: {
-      buctd_tapgemm_args a;
-      int rc = copy_args(&a, args, size, "tapgemm");
-      return rc ? rc : tapgemm_prepare(a, &op->tg, sm_count);
+      int rc = copy_args(&op->tga, args, size, "tapgemm");
+      return rc ? rc : tapgemm_prepare(op->tga, &op->tg, sm_count);
     }
     case BUCTD_OP_STEM: return copy_args(&op->u.stem, args, size, "stem");
     case BUCTD_OP_FUSE: return copy_args(&op->u.fuse, args, size, "fuse");
@@ -95,11 +105,128 @@ static int make_op(int kind, const void* args, size_t size, PlanOp* op, int sm_c
   return BUCTD_ERR_INVALID;
 }
 
+// ---- what an op reads and writes (byte ranges; over-approximation is safe) ---------------------
+static Span span(const void* p, long long bytes) {
+  Span s;
+  s.lo = reinterpret_cast<uintptr_t>(p);
+  s.hi = s.lo + (uintptr_t)(bytes > 0 ? bytes : 0);
+  return s;
+}
+static long long act_bytes(int b, int h, int w, int cs) { return 2ll * b * (h + 1) * (w + 1) * cs; }
+
+static void op_spans(const PlanOp& op, std::vector<Span>* rd, std::vector<Span>* wr) {
+  rd->clear();
+  wr->clear();
+  switch (op.kind) {
+    case BUCTD_OP_TAPGEMM: {
+      const buctd_tapgemm_args& a = op.tga;
+      const bool flat = a.mode == BUCTD_TG_FLAT;
+      rd->push_back(span(a.a, flat ? 2ll * a.m_rows * a.a_cs : act_bytes(a.batch, a.in_h, a.in_w, a.a_cs)));
+      const long long orows = flat ? a.m_rows : (long long)a.batch * (a.out_h + 1) * (a.out_w + 1);
+      if (a.residual) rd->push_back(span(a.residual, 2ll * orows * a.res_cs));
+      if (a.out_mode == BUCTD_OUT_NCHW32) wr->push_back(span(a.out, 4ll * a.batch * a.n * a.out_h * a.out_w));
+      else wr->push_back(span(a.out, 2ll * orows * a.out_cs));
+      break;
+    }
+    case BUCTD_OP_FUSE: {
+      const buctd_fuse_args& a = op.u.fuse;
+      for (int j = 0; j < a.nterms; ++j)
+        rd->push_back(span(a.term[j], act_bytes(a.batch, a.h >> a.term_shift[j], a.w >> a.term_shift[j], a.term_cs[j])));
+      wr->push_back(span(a.out, act_bytes(a.batch, a.h, a.w, a.out_cs)));
+      break;
+    }
+    case BUCTD_OP_CHAN_ATT: {
+      const buctd_chan_att_args& a = op.u.chan;
+      rd->push_back(span(a.y, act_bytes(a.batch, a.h, a.w, a.y_cs)));
+      rd->push_back(span(a.yc, act_bytes(a.batch, a.h, a.w, a.yc_cs)));
+      const long long nchunks = ((long long)(a.h + 1) * (a.w + 1) + BUCTD_CHAN_ATT_ROWS_PER_CHUNK - 1) / BUCTD_CHAN_ATT_ROWS_PER_CHUNK;
+      wr->push_back(span(a.scratch, 4ll * a.batch * nchunks * a.c * a.c));
+      wr->push_back(span(a.out, 2ll * a.batch * a.c * a.h * a.w));
+      break;
+    }
+    case BUCTD_OP_POS_ATT: {
+      const buctd_pos_att_args& a = op.u.pos;
+      rd->push_back(span(a.q, act_bytes(a.batch, a.h, a.w, a.q_cs)));
+      rd->push_back(span(a.k, act_bytes(a.batch, a.h, a.w, a.k_cs)));
+      rd->push_back(span(a.v, act_bytes(a.batch, a.h, a.w, a.v_cs)));
+      wr->push_back(span(a.o, act_bytes(a.batch, a.h, a.w, a.o_cs)));
+      break;
+    }
+    case BUCTD_OP_DA_COMBINE: {
+      const buctd_da_combine_args& a = op.u.da;
+      rd->push_back(span(a.x, act_bytes(a.batch, a.h, a.w, a.x_cs)));
+      if (a.p_out) rd->push_back(span(a.p_out, act_bytes(a.batch, a.h, a.w, a.p_cs)));
+      rd->push_back(span(a.c_out, 2ll * a.batch * a.c * a.h * a.w));
+      wr->push_back(span(a.out, act_bytes(a.batch, a.h, a.w, a.out_cs)));
+      break;
+    }
+    default:
+      // ops that touch caller tensors of unknown extent (stem, resize, prenet, decode, raster) order against
+      // everything: the whole address space is both read and written
+      rd->push_back(Span{0, ~(uintptr_t)0});
+      wr->push_back(Span{0, ~(uintptr_t)0});
+  }
+}
+
+static bool overlap(const std::vector<Span>& a, const std::vector<Span>& b) {
+  for (const Span& x : a)
+    for (const Span& y : b)
+      if (x.lo < y.hi && y.lo < x.hi) return true;
+  return false;
+}
+
+// For every op: the LAST conflicting (RAW / WAW / WAR) earlier op of every other lane.  Ops of one lane run in
+// program order on one stream, so earlier conflicts of that lane are implied.
+static void analyse_deps(std::vector<PlanOp>& ops) {
+  const int n = (int)ops.size();
+  std::vector<std::vector<Span>> rd(n), wr(n);
+  for (int i = 0; i < n; ++i) {
+    op_spans(ops[i], &rd[i], &wr[i]);
+    ops[i].ndeps = 0;
+    ops[i].record = false;
+  }
+  for (int i = 0; i < n; ++i) {
+    bool have[BUCTD_MAX_LANES] = {false};
+    have[ops[i].lane] = true;
+    int found = 1;
+    for (int j = i - 1; j >= 0 && found < BUCTD_MAX_LANES; --j) {
+      const int lj = ops[j].lane;
+      if (have[lj]) continue;
+      if (overlap(wr[j], rd[i]) || overlap(wr[j], wr[i]) || overlap(rd[j], wr[i])) {
+        have[lj] = true;
+        ++found;
+        ops[i].deps[ops[i].ndeps++] = j;
+        ops[j].record = true;
+      }
+    }
+  }
+}
+
 }  // namespace buctd
 
 struct buctd_plan {
   buctd_ctx* ctx = nullptr;
   std::vector<buctd::PlanOp> ops;
+  int nlanes = 1;
+  bool analysed = false;
+  std::vector<cudaEvent_t> events;                 // one per op that another lane waits for, + fork/join
+  cudaStream_t lane_stream[BUCTD_MAX_LANES] = {};
+  cudaEvent_t fork_ev = nullptr, join_ev[BUCTD_MAX_LANES] = {};
+  cudaStream_t capture_stream = nullptr;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  long long graph_launches = 0;
+  ~buctd_plan() {
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    for (cudaEvent_t e : events) if (e) cudaEventDestroy(e);
+    if (fork_ev) cudaEventDestroy(fork_ev);
+    for (int l = 0; l < BUCTD_MAX_LANES; ++l) {
+      if (join_ev[l]) cudaEventDestroy(join_ev[l]);
+      if (lane_stream[l]) cudaStreamDestroy(lane_stream[l]);
+    }
+    if (capture_stream) cudaStreamDestroy(capture_stream);
+  }
 };
 
 using namespace buctd;
@@ -215,14 +342,101 @@ BUCTD_API int buctd_plan_destroy(buctd_plan* plan) {
   delete plan;
   return BUCTD_OK;
 }
-BUCTD_API int buctd_plan_add(buctd_plan* plan, int kind, const void* args, size_t size) {
+BUCTD_API int buctd_plan_add_lane(buctd_plan* plan, int kind, const void* args, size_t size, int lane, int max_ctas) {
   BUCTD_CHECK(plan != nullptr, BUCTD_ERR_INVALID, "buctd_plan_add: null plan");
+  BUCTD_CHECK(lane >= 0 && lane < BUCTD_MAX_LANES, BUCTD_ERR_INVALID, "buctd_plan_add_lane: lane %d out of range [0,%d)", lane,
+              BUCTD_MAX_LANES);
+  BUCTD_CHECK(plan->exec == nullptr, BUCTD_ERR_INVALID, "buctd_plan_add: plan already instantiated");
   PlanOp op;
-  int rc = make_op(kind, args, size, &op, plan->ctx->sm_count);
+  const int sms = plan->ctx->sm_count;
+  int rc = make_op(kind, args, size, &op, max_ctas > 0 && max_ctas < sms ? max_ctas : sms);
   if (rc) return rc;
+  op.lane = lane;
   plan->ops.push_back(op);
+  if (lane + 1 > plan->nlanes) plan->nlanes = lane + 1;
+  plan->analysed = false;
   return BUCTD_OK;
 }
+BUCTD_API int buctd_plan_add(buctd_plan* plan, int kind, const void* args, size_t size) {
+  return buctd_plan_add_lane(plan, kind, args, size, 0, 0);
+}
+
+// Enqueue every op on its lane: lane 0 = `origin`, the others are internal streams forked from / joined back
+// into `origin` with events.  Works both directly on a caller stream and under stream capture.
+static int run_lanes(buctd_plan* plan, cudaStream_t origin) {
+  std::vector<PlanOp>& ops = plan->ops;
+  if (!plan->analysed) {
+    analyse_deps(ops);
+    size_t need = 0;
+    for (const PlanOp& op : ops) need += op.record ? 1 : 0;
+    while (plan->events.size() < need) {
+      cudaEvent_t e;
+      BUCTD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      plan->events.push_back(e);
+    }
+    if (!plan->fork_ev) BUCTD_CUDA(cudaEventCreateWithFlags(&plan->fork_ev, cudaEventDisableTiming));
+    for (int l = 1; l < plan->nlanes; ++l) {
+      if (!plan->lane_stream[l]) BUCTD_CUDA(cudaStreamCreateWithFlags(&plan->lane_stream[l], cudaStreamNonBlocking));
+      if (!plan->join_ev[l]) BUCTD_CUDA(cudaEventCreateWithFlags(&plan->join_ev[l], cudaEventDisableTiming));
+    }
+    plan->analysed = true;
+  }
+  const int n = (int)ops.size();
+  std::vector<cudaEvent_t> ev_of(n, nullptr);
+  size_t next_ev = 0;
+  auto stream_of = [&](int lane) { return lane == 0 ? origin : plan->lane_stream[lane]; };
+  if (plan->nlanes > 1) {
+    BUCTD_CUDA(cudaEventRecord(plan->fork_ev, origin));
+    for (int l = 1; l < plan->nlanes; ++l) BUCTD_CUDA(cudaStreamWaitEvent(plan->lane_stream[l], plan->fork_ev, 0));
+  }
+  long long launches = 0;
+  bool after_kernel[BUCTD_MAX_LANES] = {false};   // the previous node of this lane's stream is a kernel of this run
+  for (int i = 0; i < n; ++i) {
+    PlanOp& op = ops[i];
+    cudaStream_t st = stream_of(op.lane);
+    for (int d = 0; d < op.ndeps; ++d) BUCTD_CUDA(cudaStreamWaitEvent(st, ev_of[op.deps[d]], 0));
+    // programmatic dependent launch only kernel-after-kernel on one stream; event waits are full dependencies
+    tl_use_pdl = op.ndeps == 0 && after_kernel[op.lane];
+    int rc = run_op(op, st);
+    tl_use_pdl = true;
+    if (rc) return rc;
+    launches += op.nlaunch;
+    after_kernel[op.lane] = true;
+    if (op.record) {
+      ev_of[i] = plan->events[next_ev++];
+      BUCTD_CUDA(cudaEventRecord(ev_of[i], st));
+      after_kernel[op.lane] = false;
+    }
+  }
+  for (int l = 1; l < plan->nlanes; ++l) {
+    BUCTD_CUDA(cudaEventRecord(plan->join_ev[l], plan->lane_stream[l]));
+    BUCTD_CUDA(cudaStreamWaitEvent(origin, plan->join_ev[l], 0));
+  }
+  plan->graph_launches = launches;
+  return BUCTD_OK;
+}
+
+BUCTD_API int buctd_plan_instantiate(buctd_plan* plan) {
+  BUCTD_CHECK(plan != nullptr, BUCTD_ERR_INVALID, "buctd_plan_instantiate: null plan");
+  if (plan->exec) return BUCTD_OK;
+  if (!plan->capture_stream) BUCTD_CUDA(cudaStreamCreateWithFlags(&plan->capture_stream, cudaStreamNonBlocking));
+  BUCTD_CUDA(cudaStreamBeginCapture(plan->capture_stream, cudaStreamCaptureModeThreadLocal));
+  int rc = run_lanes(plan, plan->capture_stream);
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture(plan->capture_stream, &g);
+  if (rc) {
+    if (g) cudaGraphDestroy(g);
+    return rc;
+  }
+  if (e != cudaSuccess) {
+    set_error("buctd_plan_instantiate: cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+    return BUCTD_ERR_CUDA;
+  }
+  plan->graph = g;
+  BUCTD_CUDA(cudaGraphInstantiate(&plan->exec, g, 0));
+  return BUCTD_OK;
+}
+BUCTD_API int buctd_plan_num_lanes(const buctd_plan* plan) { return plan ? plan->nlanes : 0; }
 BUCTD_API int buctd_plan_size(const buctd_plan* plan) { return plan ? (int)plan->ops.size() : 0; }
 
 BUCTD_API int buctd_plan_run_range(buctd_plan* plan, int first, int last, buctd_stream stream) {
@@ -240,5 +454,17 @@ BUCTD_API int buctd_plan_run_range(buctd_plan* plan, int first, int last, buctd_
   return BUCTD_OK;
 }
 BUCTD_API int buctd_plan_run(buctd_plan* plan, buctd_stream stream) {
-  return buctd_plan_run_range(plan, 0, plan ? (int)plan->ops.size() : 0, stream);
+  BUCTD_CHECK(plan != nullptr, BUCTD_ERR_INVALID, "buctd_plan_run: null plan");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (plan->exec) {                       // instantiated: one graph launch, lanes are parallel branches
+    BUCTD_CUDA(cudaGraphLaunch(plan->exec, st));
+    plan->ctx->launches += plan->graph_launches;
+    return BUCTD_OK;
+  }
+  if (plan->nlanes > 1) {                 // multi-lane, not instantiated: internal streams forked from the caller's
+    int rc = run_lanes(plan, st);
+    if (!rc) plan->ctx->launches += plan->graph_launches;
+    return rc;
+  }
+  return buctd_plan_run_range(plan, 0, (int)plan->ops.size(), stream);
 }

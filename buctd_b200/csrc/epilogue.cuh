@@ -22,6 +22,16 @@ template <int NT> __device__ __forceinline__ void epi_sync() {
   asm volatile("bar.sync %0, %1;" ::"n"(kEpiBarrier), "n"(NT) : "memory");
 }
 
+// group-private barrier (ids 1 and 2) of the 4 warps of one epilogue group
+__device__ __forceinline__ void epi_sync_grp(int grp) {
+  asm volatile("bar.sync %0, 128;" ::"r"(kEpiBarrier + grp) : "memory");
+}
+// n / d for n < 2^31 with a host-computed (mul, shift) pair (internal.h, fastdiv_make): no integer division on
+// the epilogue's critical path
+__device__ __forceinline__ unsigned fastdiv(unsigned n, unsigned mul, unsigned shift) {
+  return (__umulhi(n, mul) + n) >> shift;
+}
+
 template <int BN> __host__ __device__ constexpr int epi_blocks() { return (BN + 63) / 64; }
 template <int BN> __host__ __device__ constexpr int epi_stage_bytes() { return epi_blocks<BN>() * kEpiBlockBytes; }
 
@@ -60,11 +70,11 @@ __device__ __forceinline__ EpiRow epi_row(const TapGemmKParams& p, const EpiTile
     const long long r = t.m0 + row;
     o.valid = r < p.m_rows;
     if (o.valid && p.out_mode != BUCTD_OUT_ROWS16) {
-      // 32-bit arithmetic on purpose (m_rows < 2^31 is checked on the host): 64-bit div/mod costs hundreds of cycles
+      // 32-bit multiply-high division (m_rows < 2^31 is checked on the host)
       const unsigned ru = (unsigned)r;
-      const unsigned ry = ru / (unsigned)Wp;
+      const unsigned ry = fastdiv(ru, p.wp_mul, p.wp_sh);
       o.x = (int)(ru - ry * (unsigned)Wp);
-      o.b = (int)(ry / (unsigned)Hp);
+      o.b = (int)fastdiv(ry, p.hp_mul, p.hp_sh);
       o.y = (int)(ry - (unsigned)o.b * (unsigned)Hp);
       o.pad = (o.x == p.W) || (o.y == p.H);
     }
@@ -108,6 +118,86 @@ template <> __device__ __forceinline__ uint32_t relu2<__nv_bfloat16>(uint32_t u)
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// ---- fast path: a full tile (all BN columns real), one group per tile -------------------------------
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// round two fp32 values to the 16-bit type, clamp to [lo, +max finite] on the packed pair (lo = 0 for ReLU)
+template <typename T> struct Finish;
+template <> struct Finish<__half> {
+  __device__ static __forceinline__ uint32_t lo(bool relu) { return relu ? 0u : 0xFBFFFBFFu; }     // -65504 | -65504
+  __device__ static __forceinline__ uint32_t run(float a, float b, uint32_t lo2) {
+    __half2 h = __floats2half2_rn(a, b);
+    const uint32_t hi2 = 0x7BFF7BFFu;                                                               // 65504 | 65504
+    h = __hmin2(__hmax2(h, *reinterpret_cast<const __half2*>(&lo2)), *reinterpret_cast<const __half2*>(&hi2));
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+};
+template <> struct Finish<__nv_bfloat16> {
+  __device__ static __forceinline__ uint32_t lo(bool relu) { return relu ? 0u : 0xFF7FFF7Fu; }     // lowest finite bf16
+  __device__ static __forceinline__ uint32_t run(float a, float b, uint32_t lo2) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    h = __hmax2(h, *reinterpret_cast<const __nv_bfloat162*>(&lo2));
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+};
+
+// Straight-line code: 64 columns per TMEM round trip, shared-space 128-bit accesses (no generic loads), packed
+// clamps, no divergent branches.  Same arithmetic as the general path below (fp32 bias + residual add, one rounding).
+template <typename T, int BN, bool RES>
+__device__ __forceinline__ void epi_compute_fast(const TapGemmKParams& p, const EpiTile& tile, uint32_t tmem_acc, uint8_t* stage,
+                                                 const float* s_bias, int q, int lane) {
+  const int row = q * 32 + lane;
+  const EpiRow me = epi_row(p, tile, row);
+  const bool zero = me.pad || !me.valid;
+  const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
+  const uint32_t srow = smem_u32(stage) + (uint32_t)row * 128u;
+  const uint32_t sw = (uint32_t)row & 7u;
+  const uint32_t bias_addr = smem_u32(s_bias);
+  const uint32_t lo2 = Finish<T>::lo(p.relu != 0);
+#pragma unroll
+  for (int c0 = 0; c0 < BN; c0 += 64) {
+    constexpr int kMaxW = BN < 64 ? BN : 64;
+    const int cw = (BN - c0) < 64 ? (BN - c0) : 64;          // compile-time after unrolling
+    uint32_t acc[kMaxW];
+#pragma unroll
+    for (int i = 0; i < kMaxW / 16; ++i)
+      if (i * 16 < cw) tmem_ld16(taddr + c0 + i * 16, &acc[i * 16]);
+    tmem_ld_wait();
+    const uint32_t blk = srow + (uint32_t)(c0 >> 6) * kEpiBlockBytes;
+#pragma unroll
+    for (int u = 0; u < kMaxW / 8; ++u) {
+      if (u * 8 < cw) {
+        const uint32_t a = blk + ((((uint32_t)u) ^ sw) << 4);
+        const uint4 b0 = lds128(bias_addr + (uint32_t)(c0 + u * 8) * 4u), b1 = lds128(bias_addr + (uint32_t)(c0 + u * 8 + 4) * 4u);
+        float v[8];
+        v[0] = __uint_as_float(acc[u * 8 + 0]) + __uint_as_float(b0.x); v[1] = __uint_as_float(acc[u * 8 + 1]) + __uint_as_float(b0.y);
+        v[2] = __uint_as_float(acc[u * 8 + 2]) + __uint_as_float(b0.z); v[3] = __uint_as_float(acc[u * 8 + 3]) + __uint_as_float(b0.w);
+        v[4] = __uint_as_float(acc[u * 8 + 4]) + __uint_as_float(b1.x); v[5] = __uint_as_float(acc[u * 8 + 5]) + __uint_as_float(b1.y);
+        v[6] = __uint_as_float(acc[u * 8 + 6]) + __uint_as_float(b1.z); v[7] = __uint_as_float(acc[u * 8 + 7]) + __uint_as_float(b1.w);
+        if (RES) {
+          const uint4 r = lds128(a);
+          float2 f;
+          f = T16<T>::unpack2(r.x); v[0] += f.x; v[1] += f.y;
+          f = T16<T>::unpack2(r.y); v[2] += f.x; v[3] += f.y;
+          f = T16<T>::unpack2(r.z); v[4] += f.x; v[5] += f.y;
+          f = T16<T>::unpack2(r.w); v[6] += f.x; v[7] += f.y;
+        }
+        uint4 o;
+        o.x = Finish<T>::run(v[0], v[1], lo2); o.y = Finish<T>::run(v[2], v[3], lo2);
+        o.z = Finish<T>::run(v[4], v[5], lo2); o.w = Finish<T>::run(v[6], v[7], lo2);
+        if (zero) o = make_uint4(0, 0, 0, 0);
+        sts128(a, o);
+      }
+    }
+  }
+}
+
 // TMEM -> (+bias, +residual from stage, ReLU, mask) -> 16-bit -> stage (in place).  Work unit = 8
 // columns (one 16-byte chunk); warp group `grp` of `ngrp` takes every ngrp-th unit of its rows.  The
 // next unit's tcgen05.ld is issued before the current one is processed.
@@ -115,6 +205,11 @@ template <typename T, int BN>
 __device__ __forceinline__ void epi_compute(const TapGemmKParams& p, const EpiTile& tile, int n0, uint32_t tmem_acc,
                                             uint8_t* stage, const float* s_bias, bool has_res, int q, int lane, int grp,
                                             int ngrp) {
+  if (ngrp == 1 && n0 + BN <= p.n) {
+    if (has_res) epi_compute_fast<T, BN, true>(p, tile, tmem_acc, stage, s_bias, q, lane);
+    else epi_compute_fast<T, BN, false>(p, tile, tmem_acc, stage, s_bias, q, lane);
+    return;
+  }
   const int row = q * 32 + lane;
   const EpiRow me = epi_row(p, tile, row);
   const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
@@ -155,16 +250,17 @@ __device__ __forceinline__ void epi_compute(const TapGemmKParams& p, const EpiTi
     if (zero) o = make_uint4(0, 0, 0, 0);
     *a = o;
   };
-  // up to 4 units in flight per tcgen05.wait::ld (the TMEM read latency, not its bandwidth, is what costs)
-  uint32_t acc[4][8];
+  // up to 6 units in flight per tcgen05.wait::ld (the TMEM read latency, not its bandwidth, is what costs)
+  constexpr int kFly = 6;
+  uint32_t acc[kFly][8];
 #pragma unroll 1
-  for (int u0 = grp; u0 < units; u0 += 4 * ngrp) {
+  for (int u0 = grp; u0 < units; u0 += kFly * ngrp) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < kFly; ++i)
       if (u0 + i * ngrp < units) tmem_ld8(taddr + (u0 + i * ngrp) * 8, acc[i]);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < kFly; ++i)
       if (u0 + i * ngrp < units) process(u0 + i * ngrp, acc[i]);
   }
 }

@@ -24,6 +24,7 @@ struct TapGemmKParams {
   int n, n_alloc;
   int out_cs, res_cs, relu, out_mode;
   uint32_t a_tile_bytes;
+  uint32_t wp_mul, wp_sh, hp_mul, hp_sh;   // fastdiv pairs for (W+1) and (H+1)
   const float* bias;
   const void* residual;
   void* out;
@@ -41,7 +42,16 @@ struct SlabParams {
   int num_super, num_items;
   int tmem_cols, smem_bytes;
   int desc_mode;
+  int jmajor;        // resident weights + one K chunk: sub-tile-major MMA order (per-sub-tile hand-off to the epilogue)
 };
+
+// (mul, shift) with n / d == (umulhi(n, mul) + n) >> shift for every n < 2^31 (round-up method, 33-bit magic)
+inline void fastdiv_make(uint32_t d, uint32_t* mul, uint32_t* shift) {
+  uint32_t s = 0;
+  while ((1ull << s) < d) ++s;
+  *mul = (uint32_t)(((1ull << 32) * ((1ull << s) - d)) / d + 1);
+  *shift = s;
+}
 
 // everything a tap-GEMM launch needs, computed (tensor maps encoded) once
 struct TapGemmLaunch {

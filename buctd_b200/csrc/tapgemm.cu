@@ -169,18 +169,46 @@ tapgemm_patch_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 }
 
 // =================================================================================================
-// SLAB kernel (FLAT mode): persistent, A-slab + row-shifted tap views, double-buffered accumulators
+// SLAB kernel (FLAT mode): persistent, A-slab + row-shifted tap views, ring of TMEM accumulators
 // =================================================================================================
-// all MMAs of one (tap, chunk): MSUB sub-tiles x KS k-steps, fully unrolled so every descriptor is
-// adesc0/bdesc plus an immediate (no dependent address arithmetic between tcgen05.mma issues)
-template <int BN, int MSUB, int KS>
-__device__ __forceinline__ void mma_batch(uint32_t d0, uint64_t adesc0, uint64_t bdesc, uint32_t idesc, uint32_t first) {
+constexpr int kMaxAcc = 8;   // accumulator ring slots (barrier array size)
+template <int BN> __host__ __device__ constexpr int slab_nacc() { return (512 / BN) < kMaxAcc ? (512 / BN) : kMaxAcc; }
+
+// Walks the 128-row sub-tiles of one CTA in processing order: work item k = blockIdx.x + k*gridDim.x is
+// (super-tile s, N tile nt) in mixed radix; every item has MSUB sub-tiles.  No division after init().
+struct SubIter {
+  int s, nt, j, ds, dn, num_super;
+  __device__ __forceinline__ void init(int num_super_) {
+    num_super = num_super_;
+    s = (int)blockIdx.x % num_super; nt = (int)blockIdx.x / num_super;
+    ds = (int)gridDim.x % num_super; dn = (int)gridDim.x / num_super;
+    j = 0;
+  }
+  __device__ __forceinline__ void next_item() {
+    s += ds; nt += dn;
+    if (s >= num_super) { s -= num_super; ++nt; }
+  }
+  template <int MSUB> __device__ __forceinline__ void next() {
+    if (++j == MSUB) { j = 0; next_item(); }
+  }
+  template <int MSUB> __device__ __forceinline__ long long m0() const {
+    return (long long)s * (MSUB * kBlockM) + (long long)j * kBlockM;
+  }
+};
+
+// all k-steps of one (sub-tile, tap, chunk): fully unrolled, every descriptor is base + immediate
+template <int BN, int KS>
+__device__ __forceinline__ void mma_ksteps(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t first) {
 #pragma unroll
-  for (int j = 0; j < MSUB; ++j) {
-#pragma unroll
-    for (int k = 0; k < KS; ++k)
-      tc_mma_f16(d0 + j * BN, adesc0 + (uint64_t)(j * (kBlockM * 128 / 16) + 2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                 k == 0 ? first : 1u);
+  for (int k = 0; k < KS; ++k) tc_mma_f16(d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k == 0 ? first : 1u);
+}
+template <int BN>
+__device__ __forceinline__ void mma_ksteps_rt(int ksteps, uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t first) {
+  switch (ksteps) {
+    case 1: mma_ksteps<BN, 1>(d, adesc, bdesc, idesc, first); break;
+    case 2: mma_ksteps<BN, 2>(d, adesc, bdesc, idesc, first); break;
+    case 3: mma_ksteps<BN, 3>(d, adesc, bdesc, idesc, first); break;
+    default: mma_ksteps<BN, 4>(d, adesc, bdesc, idesc, first); break;
   }
 }
 
@@ -189,36 +217,41 @@ __global__ void __launch_bounds__(kSlabThreads, 1)
 tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
                     const TapGemmKParams p, const SlabParams sp) {
+  RT_BEGIN(t_cta_start);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kWTileBytes = BN * 128;
+  constexpr int NACC = slab_nacc<BN>();
+  static_assert(MSUB <= NACC, "a super-tile needs MSUB accumulators at once");
   uint8_t* slabs = smem;                                         // [sa][slab_bytes]
   uint8_t* wbuf = slabs + (size_t)sp.sa * sp.slab_bytes;         // resident: [num_kc*ntaps] tiles; ring: [sw] tiles
   uint8_t* stage = wbuf + (size_t)sp.w_tiles * kWTileBytes;       // [stage_bufs][epi_stage_bytes]
-  float* s_bias = reinterpret_cast<float*>(stage + (size_t)sp.stage_bufs * epi_stage_bytes<BN>());
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + BN);
+  float* s_bias = reinterpret_cast<float*>(stage + (size_t)sp.stage_bufs * epi_stage_bytes<BN>());   // [2][BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 2 * BN);
   uint64_t* slab_full = bars;                 // [sa]
   uint64_t* slab_empty = slab_full + 4;       // [sa]
   uint64_t* w_full = slab_empty + 4;          // [sw] (resident: [0] only)
   uint64_t* w_empty = w_full + 8;             // [sw]
-  uint64_t* acc_full = w_empty + 8;           // [2]
-  uint64_t* acc_empty = acc_full + 2;         // [2]
-  uint64_t* st_ready = acc_empty + 2;         // [2] stage buffer e may be written (its residual tile, if any, has landed)
+  uint64_t* acc_full = w_empty + 8;           // [NACC] accumulator slot holds a finished sub-tile
+  uint64_t* acc_empty = acc_full + kMaxAcc;   // [NACC] accumulator slot has been read out
+  uint64_t* st_ready = acc_empty + kMaxAcc;   // [2] stage buffer e may be written (its residual tile, if any, has landed)
   uint64_t* st_done = st_ready + 2;           // [2] stage buffer e holds a finished 16-bit tile
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(st_done + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // Epilogue organisation.  Two groups of 4 warps (one warp per TMEM lane quarter).  With two stage buffers
+  // each group owns one buffer and takes every other sub-tile (whole tiles in parallel); with one stage
+  // buffer (shared memory is tight) both groups work on the same tile and split its columns.
+  const bool split = sp.stage_bufs == 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     for (int s = 0; s < 4; ++s) { mbar_init(&slab_full[s], 1); mbar_init(&slab_empty[s], 1); }
     for (int s = 0; s < 8; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8);
-      mbar_init(&st_ready[s], 1); mbar_init(&st_done[s], 8);
-    }
+    for (int s = 0; s < kMaxAcc; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], split ? 8 : 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&st_ready[s], 1); mbar_init(&st_done[s], split ? 8 : 4); }
     tma_prefetch_desc(&map_out);
     fence_mbar_init();
   }
@@ -227,24 +260,28 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   __syncthreads();
   tc_fence_after();
   pdl_launch_dependents();
-  pdl_wait();                                   // inputs of this kernel are produced by the previous one
+  if (warp == 0 && lane == 0 && sp.w_resident) {
+    // the weights are constants: fetch them while the previous kernel of the stream drains
+    mbar_expect_tx(&w_full[0], (uint32_t)(sp.w_tiles * kWTileBytes));
+    for (int kc = 0; kc < p.num_kc; ++kc)
+      for (int t = 0; t < p.ntaps; ++t)
+        tma_load_2d(wbuf + (size_t)(kc * p.ntaps + t) * kWTileBytes, &map_b, &w_full[0], kc * 64, t * p.n_alloc);
+  }
+  RT_DECL(t_pro); RT_DECL(t_pdl);
+  RT_ADD(t_pro, t_cta_start);
+  pdl_wait();                                   // activations are produced by the previous kernel
+  RT_ADD(t_pdl, t_cta_start);
   const uint32_t tmem_base = *tmem_slot;
-  const int R = MSUB * kBlockM;
+  constexpr int R = MSUB * kBlockM;
+  const int my_items = (sp.num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 0) {
     if (lane == 0) {
-      if (sp.w_resident) {
-        // all weight tiles of this CTA's N tile... resident mode is only chosen when there is one N tile
-        mbar_expect_tx(&w_full[0], (uint32_t)(sp.w_tiles * kWTileBytes));
-        for (int kc = 0; kc < p.num_kc; ++kc)
-          for (int t = 0; t < p.ntaps; ++t)
-            tma_load_2d(wbuf + (size_t)(kc * p.ntaps + t) * kWTileBytes, &map_b, &w_full[0], kc * 64, t * p.n_alloc);
-      }
       uint32_t slot = 0, slot_ph = 1, ws = 0, ws_ph = 1;     // producer waits on the "empty" phase (starts free)
-      int s = blockIdx.x % sp.num_super, nt = blockIdx.x / sp.num_super;
-      const int ds = gridDim.x % sp.num_super, dn = gridDim.x / sp.num_super;
-      for (int item = blockIdx.x; item < sp.num_items; item += gridDim.x) {
-        const long long r0 = (long long)s * R - sp.halo;
+      SubIter it;
+      it.init(sp.num_super);
+      for (int k = 0; k < my_items; ++k, it.next_item()) {
+        const long long r0 = (long long)it.s * R - sp.halo;
         for (int kc = 0; kc < p.num_kc; ++kc) {
           mbar_wait(&slab_empty[slot], slot_ph);
           mbar_expect_tx(&slab_full[slot], (uint32_t)sp.slab_bytes);
@@ -256,14 +293,11 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             for (int t = 0; t < p.ntaps; ++t) {
               mbar_wait(&w_empty[ws], ws_ph);
               mbar_expect_tx(&w_full[ws], kWTileBytes);
-              tma_load_2d(wbuf + (size_t)ws * kWTileBytes, &map_b, &w_full[ws], kc * 64, t * p.n_alloc + nt * BN);
+              tma_load_2d(wbuf + (size_t)ws * kWTileBytes, &map_b, &w_full[ws], kc * 64, t * p.n_alloc + it.nt * BN);
               if (++ws == (uint32_t)sp.sw) { ws = 0; ws_ph ^= 1; }
             }
           }
         }
-        // next item of this CTA: (s, nt) += gridDim.x in mixed radix, without a division
-        s += ds; nt += dn;
-        if (s >= sp.num_super) { s -= sp.num_super; ++nt; }
       }
     }
   } else if (warp == 1) {
@@ -271,9 +305,9 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // uniform registers: ~2 SASS instructions per tcgen05.mma).
     if (elect_one()) {
       const uint32_t idesc = umma_idesc_f16(T16<T>::kFmt, kBlockM, BN);
-      uint32_t it_local = 0;
       uint32_t slot = 0, slot_ph = 0;          // slab ring position / phase (wrap counters: no runtime div/mod in this thread)
       uint32_t ws = 0, ws_ph = 0;              // weight ring position / phase
+      uint32_t aslot = 0, aph = 1;             // accumulator ring: wait for "empty" (starts free)
       RT_DECL(t_acc); RT_DECL(t_slab); RT_DECL(t_w); RT_DECL(t_total); RT_DECL(t_issue); RT_DECL(t_commit);
       RT_BEGIN(t_start);
       const uint32_t slab0_addr = smem_u32(slabs);
@@ -282,50 +316,86 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
       for (int t = 0; t < 9; ++t) tap_shift[t] = sp.halo + (p.ntaps == 9 ? (t / 3 - 1) * p.wp + (t % 3 - 1) : 0);
       if (sp.w_resident) { mbar_wait(&w_full[0], 0); }
-      for (int item = blockIdx.x; item < sp.num_items; item += gridDim.x, ++it_local) {
-        const uint32_t buf = it_local & 1;
-        { RT_BEGIN(t0); mbar_wait(&acc_empty[buf], ((it_local >> 1) & 1) ^ 1); RT_ADD(t_acc, t0); }
-        tc_fence_after();
-        const uint32_t d0 = tmem_base + buf * MSUB * BN;
-        uint32_t w_res_addr = wbuf_addr;         // resident weights: tile (kc, t) lives at (kc*ntaps + t) * kWTileBytes
-        for (int kc = 0; kc < p.num_kc; ++kc) {
+      tc_fence_after();
+      if (sp.jmajor) {
+        // resident weights, one K chunk: sub-tile-major order.  Sub-tile j is finished (and handed to the epilogue)
+        // after its own taps, so the epilogue lags the tensor core by ONE sub-tile, not one super-tile.
+        const int ksteps = p.k16 >> 4;
+        for (int k = 0; k < my_items; ++k) {
           { RT_BEGIN(t0); mbar_wait(&slab_full[slot], slot_ph); RT_ADD(t_slab, t0); }
           tc_fence_after();
           const uint32_t slab_addr = slab0_addr + slot * (uint32_t)sp.slab_bytes;
-          const int ksteps = min(64, p.k16 - kc * 64) >> 4;
-          RT_BEGIN(t_i0);
 #pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            if (t < p.ntaps) {
-              uint32_t w_addr;
-              if (sp.w_resident) {
-                w_addr = w_res_addr;
-                w_res_addr += kWTileBytes;
-              } else {
-                { RT_BEGIN(t0); mbar_wait(&w_full[ws], ws_ph); RT_ADD(t_w, t0); }
-                tc_fence_after();
-                w_addr = wbuf_addr + ws * kWTileBytes;
-              }
-              const uint64_t bdesc = umma_desc_sw128(w_addr);
-              const uint64_t adesc0 = umma_desc_sw128(slab_addr + (uint32_t)tap_shift[t] * 128);
-              const uint32_t first = (kc | t) == 0 ? 0u : 1u;
-              switch (ksteps) {
-                case 1: mma_batch<BN, MSUB, 1>(d0, adesc0, bdesc, idesc, first); break;
-                case 2: mma_batch<BN, MSUB, 2>(d0, adesc0, bdesc, idesc, first); break;
-                case 3: mma_batch<BN, MSUB, 3>(d0, adesc0, bdesc, idesc, first); break;
-                default: mma_batch<BN, MSUB, 4>(d0, adesc0, bdesc, idesc, first); break;
-              }
-              if (!sp.w_resident) {
-                tc_commit(&w_empty[ws]);
-                if (++ws == (uint32_t)sp.sw) { ws = 0; ws_ph ^= 1; }
+          for (int j = 0; j < MSUB; ++j) {
+            { RT_BEGIN(t0); mbar_wait(&acc_empty[aslot], aph); RT_ADD(t_acc, t0); }
+            tc_fence_after();
+            const uint32_t d = tmem_base + aslot * BN;
+            RT_BEGIN(t_i0);
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              if (t < p.ntaps) {
+                const uint64_t bdesc = umma_desc_sw128(wbuf_addr + t * kWTileBytes);
+                const uint64_t adesc = umma_desc_sw128(slab_addr + (uint32_t)(tap_shift[t] + j * kBlockM) * 128);
+                mma_ksteps_rt<BN>(ksteps, d, adesc, bdesc, idesc, t == 0 ? 0u : 1u);
               }
             }
+            RT_ADD(t_issue, t_i0);
+            tc_commit(&acc_full[aslot]);
+            if (++aslot == NACC) { aslot = 0; aph ^= 1; }
           }
-          RT_ADD(t_issue, t_i0);
           tc_commit(&slab_empty[slot]);
           if (++slot == (uint32_t)sp.sa) { slot = 0; slot_ph ^= 1; }
         }
-        tc_commit(&acc_full[buf]);
+      } else {
+        // streamed weights / several K chunks: tap-major order, every weight tile is used by all MSUB sub-tiles
+        for (int k = 0; k < my_items; ++k) {
+          uint32_t d[MSUB], dslot[MSUB];
+#pragma unroll
+          for (int j = 0; j < MSUB; ++j) {
+            { RT_BEGIN(t0); mbar_wait(&acc_empty[aslot], aph); RT_ADD(t_acc, t0); }
+            dslot[j] = aslot;
+            d[j] = tmem_base + aslot * BN;
+            if (++aslot == NACC) { aslot = 0; aph ^= 1; }
+          }
+          tc_fence_after();
+          uint32_t w_res_addr = wbuf_addr;         // resident weights: tile (kc, t) lives at (kc*ntaps + t) * kWTileBytes
+          for (int kc = 0; kc < p.num_kc; ++kc) {
+            { RT_BEGIN(t0); mbar_wait(&slab_full[slot], slot_ph); RT_ADD(t_slab, t0); }
+            tc_fence_after();
+            const uint32_t slab_addr = slab0_addr + slot * (uint32_t)sp.slab_bytes;
+            const int ksteps = min(64, p.k16 - kc * 64) >> 4;
+            RT_BEGIN(t_i0);
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              if (t < p.ntaps) {
+                uint32_t w_addr;
+                if (sp.w_resident) {
+                  w_addr = w_res_addr;
+                  w_res_addr += kWTileBytes;
+                } else {
+                  { RT_BEGIN(t0); mbar_wait(&w_full[ws], ws_ph); RT_ADD(t_w, t0); }
+                  tc_fence_after();
+                  w_addr = wbuf_addr + ws * kWTileBytes;
+                }
+                const uint64_t bdesc = umma_desc_sw128(w_addr);
+                const uint64_t adesc0 = umma_desc_sw128(slab_addr + (uint32_t)tap_shift[t] * 128);
+                const uint32_t first = (kc | t) == 0 ? 0u : 1u;
+#pragma unroll
+                for (int j = 0; j < MSUB; ++j)
+                  mma_ksteps_rt<BN>(ksteps, d[j], adesc0 + (uint64_t)(j * (kBlockM * 128 / 16)), bdesc, idesc, first);
+                if (!sp.w_resident) {
+                  tc_commit(&w_empty[ws]);
+                  if (++ws == (uint32_t)sp.sw) { ws = 0; ws_ph ^= 1; }
+                }
+              }
+            }
+            RT_ADD(t_issue, t_i0);
+            tc_commit(&slab_empty[slot]);
+            if (++slot == (uint32_t)sp.sa) { slot = 0; slot_ph ^= 1; }
+          }
+#pragma unroll
+          for (int j = 0; j < MSUB; ++j) tc_commit(&acc_full[dslot[j]]);
+        }
       }
       RT_ADD(t_total, t_start);
       RT_STORE(0, t_total); RT_STORE(1, t_acc); RT_STORE(2, t_slab); RT_STORE(3, t_w); RT_STORE(6, t_issue); RT_STORE(7, t_commit);
@@ -336,37 +406,34 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const bool has_res = p.residual != nullptr;
     const bool head = p.out_mode == BUCTD_OUT_NCHW32;
     const int SE = sp.stage_bufs;
-    const int my_items = (sp.num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int total_u = my_items * MSUB;
-    // sub-tile u of this CTA -> tile origin and N tile
-    auto sub = [&](int u, EpiTile& t, int& nt) {
-      const int k = u / MSUB, j = u - k * MSUB;
-      const int item = blockIdx.x + k * gridDim.x;
-      const int s = item % sp.num_super;
-      nt = item / sp.num_super;
-      t.m0 = (long long)s * R + (long long)j * kBlockM;
-      t.tb = t.ty0 = t.tx0 = 0;
-    };
     if (warp == 10) {
       if (!head && elect_one()) {
+        SubIter st_it, pr_it;
+        st_it.init(sp.num_super);
+        pr_it.init(sp.num_super);
         // prepare(u): the store that last used buffer u%SE has been read -> (re)fill it with the residual tile
         auto prepare = [&](int u) {
           const int e = SE == 2 ? (u & 1) : 0;
           if (has_res) {
-            EpiTile t; int nt;
-            sub(u, t, nt);
-            epi_load_residual<BN>(p, &map_res, t, nt * BN, stage + (size_t)e * epi_stage_bytes<BN>(), &st_ready[e]);
+            EpiTile t;
+            t.m0 = pr_it.template m0<MSUB>();
+            t.tb = t.ty0 = t.tx0 = 0;
+            epi_load_residual<BN>(p, &map_res, t, pr_it.nt * BN, stage + (size_t)e * epi_stage_bytes<BN>(), &st_ready[e]);
           } else {
             mbar_arrive(&st_ready[e]);
           }
+          pr_it.template next<MSUB>();
         };
         for (int u = 0; u < SE && u < total_u; ++u) prepare(u);
         for (int u = 0; u < total_u; ++u) {
           const int e = SE == 2 ? (u & 1) : 0;
           mbar_wait(&st_done[e], (SE == 2 ? (u >> 1) : u) & 1);
-          EpiTile t; int nt;
-          sub(u, t, nt);
-          epi_store<BN>(p, &map_out, t, nt * BN, stage + (size_t)e * epi_stage_bytes<BN>());
+          EpiTile t;
+          t.m0 = st_it.template m0<MSUB>();
+          t.tb = t.ty0 = t.tx0 = 0;
+          epi_store<BN>(p, &map_out, t, st_it.nt * BN, stage + (size_t)e * epi_stage_bytes<BN>());
+          st_it.template next<MSUB>();
           if (u + SE < total_u) {
             tma_store_wait_read<0>();          // buffer e is free again once its store has read it
             prepare(u + SE);
@@ -376,44 +443,50 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
       __syncwarp();
     } else {
-      const int etid = threadIdx.x - 64;
       RT_DECL(e_wait); RT_DECL(e_total); RT_DECL(e_res); RT_DECL(e_comp);
       RT_BEGIN(e_start);
       const int q = warp & 3;
       const int grp = (warp - 2) >> 2;          // 0: warps 2..5, 1: warps 6..9
+      const int step = split ? 1 : 2;
+      const int gtid = (threadIdx.x - 64) & (split ? 255 : 127);
+      float* my_bias = s_bias + (split ? 0 : grp * BN);
+      SubIter it;
+      it.init(sp.num_super);
+      int u = split ? 0 : grp;
+      if (u == 1) it.template next<MSUB>();
+      uint32_t aslot = (uint32_t)u, aph = 0;
       int cur_nt = -1;
-      for (int u = 0; u < total_u; ++u) {
-        const int k = u / MSUB, j = u - k * MSUB;
-        const uint32_t buf = k & 1;
-        const int e = SE == 2 ? (u & 1) : 0;
-        uint8_t* st = stage + (size_t)e * epi_stage_bytes<BN>();
-        EpiTile tile; int nt;
-        sub(u, tile, nt);
+      for (; u < total_u; u += step) {
+        const int nt = it.nt;
+        EpiTile tile;
+        tile.m0 = it.template m0<MSUB>();
+        tile.tb = tile.ty0 = tile.tx0 = 0;
         if (nt != cur_nt) {                      // (re)load the bias tile of this N tile
-          epi_sync<256>();
-          epi_load_bias<BN, 256>(p, nt * BN, s_bias, etid);
+          if (split) { epi_sync<256>(); epi_load_bias<BN, 256>(p, nt * BN, my_bias, gtid); epi_sync<256>(); }
+          else { epi_sync_grp(grp); epi_load_bias<BN, 128>(p, nt * BN, my_bias, gtid); epi_sync_grp(grp); }
           cur_nt = nt;
-          epi_sync<256>();
         }
-        if (j == 0) {
-          RT_BEGIN(t0); mbar_wait(&acc_full[buf], (k >> 1) & 1); RT_ADD(e_wait, t0);
-          tc_fence_after();
-        }
-        const uint32_t acc = tmem_base + (buf * MSUB + j) * BN;
+        { RT_BEGIN(t0); mbar_wait(&acc_full[aslot], aph); RT_ADD(e_wait, t0); }
+        tc_fence_after();
+        const uint32_t acc = tmem_base + aslot * BN;
         if (head) {
-          if (grp == 0) epi_head_nchw32<BN>(p, tile, nt * BN, acc, q, lane);
+          if (!split || grp == 0) epi_head_nchw32<BN>(p, tile, nt * BN, acc, q, lane);
         } else {
-          { RT_BEGIN(t0); mbar_wait(&st_ready[e], (SE == 2 ? (u >> 1) : u) & 1); RT_ADD(e_res, t0); }
-          { RT_BEGIN(t0); epi_compute<T, BN>(p, tile, nt * BN, acc, st, s_bias, has_res, q, lane, grp, 2); RT_ADD(e_comp, t0); }
+          const int e = split ? 0 : grp;
+          uint8_t* st = stage + (size_t)e * epi_stage_bytes<BN>();
+          { RT_BEGIN(t0); mbar_wait(&st_ready[e], (split ? u : (u >> 1)) & 1); RT_ADD(e_res, t0); }
+          { RT_BEGIN(t0); epi_compute<T, BN>(p, tile, nt * BN, acc, st, my_bias, has_res, q, lane, split ? grp : 0, split ? 2 : 1); RT_ADD(e_comp, t0); }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&st_done[e]);
         }
-        if (j == MSUB - 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[buf]);
-        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[aslot]);
+        it.template next<MSUB>();
+        if (step == 2) it.template next<MSUB>();
+        aslot += step;
+        if (aslot >= NACC) { aslot -= NACC; aph ^= 1; }
       }
       RT_ADD(e_total, e_start);
       if (threadIdx.x == 64) { RT_STORE(4, e_total); RT_STORE(5, e_wait); RT_STORE(9, e_res); RT_STORE(10, e_comp); }
@@ -423,6 +496,9 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, sp.tmem_cols);
+#ifdef BUCTD_ROLE_TIMERS
+  if (threadIdx.x == 0) { RT_DECL(t_all); RT_ADD(t_all, t_cta_start); RT_STORE(11, t_pro); RT_STORE(12, t_pdl); RT_STORE(14, t_all); }
+#endif
 }
 
 // ---- host side --------------------------------------------------------------------------------
@@ -434,7 +510,7 @@ static size_t patch_smem_bytes(int bn) {
 
 template <typename T, int BN, int MSUB>
 static int set_attr_slab() {
-  if constexpr (2 * MSUB * BN <= 512) {
+  if constexpr (MSUB <= slab_nacc<BN>()) {
     BUCTD_CUDA(cudaFuncSetAttribute(tapgemm_slab_kernel<T, BN, MSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
   }
   return BUCTD_OK;
@@ -496,60 +572,105 @@ static void pick_patch_tile(int oh, int ow, int* tw, int* th) {
   }
 }
 
-// choose super-tile size, ring depths and the shared-memory carve-up of the slab kernel
-static int plan_slab(const buctd_tapgemm_args& a, int bn, int n_tiles, int num_kc, int sm_count, SlabParams* sp) {
+// ---- slab planning ----------------------------------------------------------------------------
+// One candidate (bn, msub): shared-memory carve-up + an estimate of the kernel time from the three rates that
+// bound the kernel (measured with tools/conv_sweep.py on B200):
+//   ingest  : TMA fill of one SM's shared memory, ~36 B/clk (A slab incl. halo + streamed weight tiles),
+//   tensor  : one 128 x bn x 16 SS-mode tcgen05.mma every ~max(60, 50 + 0.35 bn) clk (measured; the math alone is bn/2),
+//   epilogue: ~700 + 9 bn clk per 128-row tile and group of 4 warps, two groups in parallel.
+static bool plan_slab_one(const buctd_tapgemm_args& a, int bn, int num_kc, int k16, int msub, int ctas, SlabParams* out,
+                          double* t_est) {
+  const int nacc = (512 / bn) < kMaxAcc ? (512 / bn) : kMaxAcc;
+  if (msub > nacc) return false;
+  const int n_tiles = ceil_div(a.n_alloc, bn);
   const int halo = a.ntaps == 9 ? a.out_w + 2 : 0;        // (W+1) + 1 rows on each side
   const int wtile = bn * 128;
   const int stage = stage_bytes(bn);
-  const int fixed = 1024 + bn * 4 + 512;                  // alignment slack + bias tile + barriers
+  const int fixed = 1024 + 2 * bn * 4 + 512;              // alignment slack + two bias tiles + barriers
   const long long total_w = (long long)a.ntaps * num_kc * wtile;
   const bool resident = n_tiles == 1 && total_w <= 80 * 1024;
-  const char* force = getenv("BUCTD_FORCE_MSUB");         // test knob: pin the super-tile size
+  const int rows = msub * 128 + 2 * halo;
+  const int nboxes = ceil_div(rows, 256);
+  const int box_rows = (ceil_div(rows, nboxes) + 7) / 8 * 8;   // every box starts on a 1024-byte swizzle atom
+  const long long slab = (long long)nboxes * box_rows * 128;
+  // preference order: two stage buffers, deep rings; then thinner weight ring; then one stage buffer
+  int sa = 0, sw = 0, se = 0;
+  long long need = 0;
+  const int sa_max = num_kc > 1 ? 3 : 2;
+  for (int cse = 2; cse >= 1 && sa == 0; --cse)
+    for (int csw = resident ? 0 : 4; (resident ? csw == 0 : csw >= 2) && sa == 0; --csw)
+      for (int csa = sa_max; csa >= 2; --csa) {
+        need = fixed + (long long)cse * stage + csa * slab + (resident ? total_w : (long long)csw * wtile);
+        if (need <= kSmemBudget) { sa = csa; sw = csw; se = cse; break; }
+      }
+  if (sa == 0) return false;
+  SlabParams c;
+  memset(&c, 0, sizeof(c));
+  const long long supers = (a.m_rows + (long long)msub * 128 - 1) / ((long long)msub * 128);
+  c.msub = msub; c.halo = halo; c.nboxes = nboxes; c.box_rows = box_rows; c.slab_bytes = (int)slab;
+  c.sa = sa; c.sw = sw; c.stage_bufs = se; c.w_resident = resident; c.w_tiles = resident ? a.ntaps * num_kc : sw;
+  c.num_super = (int)supers; c.num_items = (int)supers * n_tiles; c.smem_bytes = (int)need;
+  // sub-tile-major order serialises 9*ksteps MMAs on ONE accumulator (measured 71 instead of 47 clk per MMA at bn=48):
+  // kept behind a knob, off by default
+  static const bool want_jmajor = getenv("BUCTD_JMAJOR") != nullptr && atoi(getenv("BUCTD_JMAJOR")) != 0;
+  c.jmajor = want_jmajor && resident && num_kc == 1;
+  const int cols = nacc * bn;
+  c.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+  *out = c;
+  // ---- time estimate (microseconds at 1.965 GHz) ----
+  const double clk = 1965.0, fill_rate = 36.0 * clk;       // bytes per microsecond into one SM
+  const int used = c.num_items < ctas ? c.num_items : ctas;
+  const double rounds = (double)((c.num_items + used - 1) / used);
+  const double ingest_item = ((double)nboxes * box_rows * k16 * 2 + (resident ? 0.0 : (double)a.ntaps * bn * k16 * 2)) / fill_rate;
+  const double cyc_mma = fmax(60.0, 50.0 + 0.35 * bn);      // measured issue interval (tools/conv_sweep.py, role timers)
+  const double mma_tile = a.ntaps * (k16 / 16) * cyc_mma / clk;
+  const double epi_tile = (700.0 + 9.0 * bn) * (a.residual ? 1.2 : 1.0) / clk;
+  const double mma_item = msub * mma_tile, epi_item = msub * epi_tile / 2.0;
+  const bool overlapped = c.jmajor ? nacc >= 2 : nacc >= 2 * msub;
+  const double steady = rounds * (overlapped ? fmax(fmax(ingest_item, mma_item), epi_item) : fmax(ingest_item, mma_item + epi_item));
+  const double fill = ingest_item + (resident ? (double)total_w / fill_rate : 0.0) + (c.jmajor ? mma_tile : mma_item);
+  const double drain = c.jmajor ? epi_tile : fmax(epi_tile, epi_item);
+  *t_est = 3.0 + fill + steady + drain;
+  return true;
+}
+
+// choose (bn, msub) for a FLAT tap-GEMM.  Measured on B200 over the whole (bn, msub) space for the W48 shapes
+// (tools/slab_tune.py, profiles/r01_slab_tune.txt): one N tile whenever n_alloc <= 256 and, for wider layers, the
+// widest exact tiling win everywhere (a 128 x bn x 16 tcgen05.mma costs ~50 + 0.35 bn clk, so wide tiles are the
+// efficient ones); the best super-tile is the largest one that still leaves every CTA two work items, with double
+// buffered accumulators (2 msub bn <= 512).  The time estimate of plan_slab_one only breaks ties / feeds the debug print.
+static int plan_slab(const buctd_tapgemm_args& a, int num_kc, int k16, int ctas, int* bn_out, SlabParams* sp) {
+  const char* force = getenv("BUCTD_FORCE_MSUB");         // test knobs: pin the super-tile size / the N tile
   const int forced = force ? atoi(force) : 0;
+  const char* fbn = getenv("BUCTD_FORCE_BN");
+  int bn = fbn ? atoi(fbn) : pick_bn(a.n_alloc);
+  if (ceil_div(a.n_alloc, bn) > 1 && bn % 64 != 0) bn = pick_bn(a.n_alloc);   // store boxes of neighbouring N tiles must not overlap
   bool have = false;
-  SlabParams best;
-  memset(&best, 0, sizeof(best));
+  double t = 0.0;
   for (int msub = 4; msub >= 1; --msub) {
-    if (2 * msub * bn > 512) continue;                    // two accumulator sets in TMEM
-    if (forced > 0 && msub > forced) continue;
-    const int rows = msub * 128 + 2 * halo;
-    const int nboxes = ceil_div(rows, 256);
-    const int box_rows = (ceil_div(rows, nboxes) + 7) / 8 * 8;   // every box starts on a 1024-byte swizzle atom
-    const long long slab = (long long)nboxes * box_rows * 128;
-    // preference order: two stage buffers, deep rings; then thinner weight ring; then one stage buffer
-    int sa = 0, sw = 0, se = 0;
-    long long need = 0;
-    const int sa_max = num_kc > 1 ? 3 : 2;
-    for (int cse = 2; cse >= 1 && sa == 0; --cse)
-      for (int csw = resident ? 0 : 4; (resident ? csw == 0 : csw >= 2) && sa == 0; --csw)
-        for (int csa = sa_max; csa >= 2; --csa) {
-          need = fixed + (long long)cse * stage + csa * slab + (resident ? total_w : (long long)csw * wtile);
-          if (need <= kSmemBudget) { sa = csa; sw = csw; se = cse; break; }
-        }
-    if (sa == 0) continue;
+    if (forced > 0 ? msub > forced : 2 * msub * bn > 512) continue;
     SlabParams c;
-    memset(&c, 0, sizeof(c));
-    const long long supers = (a.m_rows + (long long)msub * 128 - 1) / ((long long)msub * 128);
-    c.msub = msub; c.halo = halo; c.nboxes = nboxes; c.box_rows = box_rows; c.slab_bytes = (int)slab;
-    c.sa = sa; c.sw = sw; c.stage_bufs = se; c.w_resident = resident; c.w_tiles = resident ? a.ntaps * num_kc : sw;
-    c.num_super = (int)supers; c.num_items = (int)supers * n_tiles; c.smem_bytes = (int)need;
-    const int cols = 2 * msub * bn;
-    c.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
-    best = c;
+    if (!plan_slab_one(a, bn, num_kc, k16, msub, ctas, &c, &t)) continue;
+    *sp = c;
     have = true;
-    if (forced > 0 || c.num_items >= 2 * sm_count) break; // largest super-tile that still gives every SM >= 2 items
+    if (forced > 0 || c.num_items >= 2 * ctas) break;     // largest super-tile that still gives every CTA >= 2 items
   }
   if (!have) {
-    set_error("tapgemm: no shared-memory plan for bn=%d kc=%d halo=%d", bn, num_kc, halo);
+    set_error("tapgemm: no shared-memory plan for n_alloc=%d kc=%d w=%d", a.n_alloc, num_kc, a.out_w);
     return BUCTD_ERR_INVALID;
   }
-  *sp = best;
+  *bn_out = bn;
+  static const bool debug = getenv("BUCTD_PLAN_DEBUG") != nullptr;
+  if (debug)
+    fprintf(stderr, "[buctd] slab plan: rows %lld k %d n %d taps %d ctas %d -> bn %d msub %d sa %d sw %d stage_bufs %d resident %d items %d est %.1f us\n",
+            (long long)a.m_rows, a.k, a.n, a.ntaps, ctas, bn, sp->msub, sp->sa, sp->sw, sp->stage_bufs, sp->w_resident,
+            sp->num_items, t);
   return BUCTD_OK;
 }
 
 template <typename T, int BN, int MSUB>
 static void launch_slab(const TapGemmLaunch& L, cudaStream_t st) {
-  if constexpr (2 * MSUB * BN <= 512) {
+  if constexpr (MSUB <= slab_nacc<BN>()) {
     launch_pdl(tapgemm_slab_kernel<T, BN, MSUB>, L.grid, dim3(kSlabThreads), L.sp.smem_bytes, st, L.map_a, L.map_b, L.map_out,
                L.map_res, L.kp, L.sp);
   }
@@ -616,8 +737,9 @@ int tapgemm_prepare(const buctd_tapgemm_args& a, TapGemmLaunch* L, int sm_count)
   kp.bias = a.bias; kp.residual = a.residual; kp.out = a.out;
 
   const CUtensorMapDataType dt = a.dtype == BUCTD_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  const int bn = pick_bn(a.n_alloc);
-  const int ntiles = ceil_div(a.n_alloc, bn);
+  int bn = pick_bn(a.n_alloc);
+  fastdiv_make((uint32_t)(a.out_w + 1), &kp.wp_mul, &kp.wp_sh);
+  fastdiv_make((uint32_t)(a.out_h + 1), &kp.hp_mul, &kp.hp_sh);
   const cuuint64_t a_inner = (cuuint64_t)(a.a_cs < k16 ? a.a_cs : k16);
   CUresult cr;
   dim3 grid;
@@ -627,7 +749,7 @@ int tapgemm_prepare(const buctd_tapgemm_args& a, TapGemmLaunch* L, int sm_count)
     if (a.out_mode != BUCTD_OUT_ROWS16 || a.ntaps == 9)
       BUCTD_CHECK((long long)a.batch * (a.out_h + 1) * (a.out_w + 1) == a.m_rows, BUCTD_ERR_INVALID,
                   "tapgemm: m_rows %lld does not match act16 geometry %dx%dx%d", (long long)a.m_rows, a.batch, a.out_h, a.out_w);
-    int rc = plan_slab(a, bn, ntiles, kp.num_kc, sm_count, &L->sp);
+    int rc = plan_slab(a, kp.num_kc, k16, sm_count, &bn, &L->sp);
     if (rc) return rc;
     const char* dm = getenv("BUCTD_DESC_MODE");        // debug knob for the row-shifted descriptor experiment
     L->sp.desc_mode = dm ? atoi(dm) : 0;
@@ -656,7 +778,7 @@ int tapgemm_prepare(const buctd_tapgemm_args& a, TapGemmLaunch* L, int sm_count)
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     BUCTD_CHECK(cr == CUDA_SUCCESS, BUCTD_ERR_CUDA, "cuTensorMapEncodeTiled(A patch) failed: %d", (int)cr);
     kp.a_tile_bytes = (uint32_t)(tw * th * 128);
-    grid = dim3((unsigned)(a.batch * kp.tiles_x * kp.tiles_y), ntiles);
+    grid = dim3((unsigned)(a.batch * kp.tiles_x * kp.tiles_y), ceil_div(a.n_alloc, bn));
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)a.w_cs, (cuuint64_t)a.ntaps * a.n_alloc};

@@ -265,8 +265,19 @@ class PoseHighResolutionNet(nn.Module):
         a.out = dst_ptr
         return a
 
+    @staticmethod
+    def _lane_shares(nb: int, sm_count: int):
+        """SM share of each branch's persistent tap-GEMMs while the branches of a stage run side by side:
+        proportional to the measured marginal cost of one BasicBlock conv of that branch (tools/conv_sweep.py)."""
+        w = [float(v) for v in os.environ.get("BUCTD_LANE_WEIGHTS", "40,20,10,10").split(",")][:nb]
+        tot = sum(w)
+        sh = [max(8, int(round(sm_count * v / tot))) for v in w]
+        sh[0] += sm_count - sum(sh)
+        return sh
+
     def _build(self, batch: int, device) -> dict:
         arch, dt = self.arch, self._dt
+        sm_count = torch.cuda.get_device_properties(device).multi_processor_count if torch.cuda.is_available() else 148
         bump = _Bump()
         H4, W4 = arch.img_h // 4, arch.img_w // 4
         specs: List[tuple] = []      # (kind, args, label) with workspace-relative pointers resolved later
@@ -290,11 +301,31 @@ class PoseHighResolutionNet(nn.Module):
         def mark(name, a):
             marks[name] = (len(specs), a)
 
+        # Lanes (include/buctd_b200.h, "Lanes"): branch i of a stage is lane i; the term chains of an exchange/fuse
+        # step are spread over all lanes.  `sched` = [lane, max_ctas] of the ops appended next.
+        lane_mode = os.environ.get("BUCTD_LANES", "2")          # 0: one lane; 1: all phases; 2: CoAM + fuse steps only (default:
+        # BasicBlock convs of different branches slow each other down when run side by side, tools/lane_bench.py)
+        use_lanes = lane_mode != "0"
+        block_lanes = lane_mode == "1"
+        nl_max = L.MAX_LANES if use_lanes else 1
+        sched = [0, 0]
+
+        def at(lane, share=0):
+            sched[0], sched[1] = (lane % nl_max, share) if use_lanes else (0, 0)
+
+        def emit(kind, spec, label):
+            specs.append((kind, spec, label, sched[0], sched[1]))
+
+        class _Emit:                      # list-like view for _build_coam
+            @staticmethod
+            def append(t):
+                emit(*t)
+
         def conv(cv: Conv, src: Act, dst: Act, residual=None, relu=None, key=None):
             oh, ow = (src.h, src.w) if cv.stride == 1 else (src.h // 2, src.w // 2)
             assert (dst.h, dst.w) == (oh, ow), (cv.w, dst, oh, ow)
-            specs.append((L.OP_TAPGEMM, ("tg", key or cv.w, src, dst, dict(stride=cv.stride, relu=cv.relu if relu is None else relu,
-                                                                         residual=residual)), cv.w))
+            emit(L.OP_TAPGEMM, ("tg", key or cv.w, src, dst, dict(stride=cv.stride, relu=cv.relu if relu is None else relu,
+                                                                   residual=residual)), cv.w)
 
         # ---- stem ---------------------------------------------------------------------------
         s1 = act("stem1", arch.img_h // 2, arch.img_w // 2, 64)
@@ -334,9 +365,11 @@ class PoseHighResolutionNet(nn.Module):
                 rot[i] = (rot[i] + 1) % 3
                 return bufs[i][rot[i]]
 
+            shares = self._lane_shares(nb, sm_count) if use_lanes else [0] * nb
             xs = []
             for i in range(nb):
                 t = trans[i]
+                at(i, shares[i])
                 if t is None:
                     xs.append(ys[i])
                 elif i < len(ys):
@@ -354,10 +387,12 @@ class PoseHighResolutionNet(nn.Module):
             mark("transition%d" % (si + 1), list(xs))
             # make sure every branch tensor lives in this stage's rotation (needed for in-place rotation logic)
             if si in arch.coam and arch.use_attention:
-                xs = self._build_coam(arch.coam[si], xs, batch, act, raw, specs, head_ops, nxt, cond_acts)
+                xs = self._build_coam(arch.coam[si], xs, batch, act, raw, _Emit, head_ops, nxt, cond_acts,
+                                      lambda i: at(i, shares[i]))
                 mark("stage%d_att" % (si + 1), list(xs))
             for mi, m in enumerate(mods):
                 for i in range(nb):
+                    at(i, shares[i]) if block_lanes else at(0)
                     for blk in m.branches[i]:
                         tmp = nxt(i)
                         conv(blk.convs[0], xs[i], tmp)
@@ -371,9 +406,11 @@ class PoseHighResolutionNet(nn.Module):
                 outs = []
                 scratch_id = 0
                 pending = []
+                fuse_share = max(sm_count // 4, 1) if use_lanes else 0
                 for i, terms in enumerate(m.fuse):
                     fa_terms = []
                     for t in terms:
+                        at(i * nb + t.src, fuse_share)
                         if t.kind == "id":
                             fa_terms.append((xs[t.src], 0))
                         elif t.kind == "up":
@@ -395,7 +432,8 @@ class PoseHighResolutionNet(nn.Module):
                     out = nxt(i)
                     if out.ptr == xs[i].ptr:
                         out = nxt(i)
-                    specs.append((L.OP_FUSE, ("fuse", fa_terms, out), "%s.fuse%d" % (m.prefix, i)))
+                    at(i) if block_lanes else at(0)
+                    emit(L.OP_FUSE, ("fuse", fa_terms, out), "%s.fuse%d" % (m.prefix, i))
                     new_xs.append(out)
                 xs = new_xs
             mark("stage%d" % (si + 2), list(xs))
@@ -405,10 +443,11 @@ class PoseHighResolutionNet(nn.Module):
         return {"specs": specs, "acts": acts, "marks": marks, "bytes": nbytes, "final_src": final_src, "s1": s1,
                 "head_ops": head_ops, "cond_acts": cond_acts}
 
-    def _build_coam(self, das: List[DAModule], xs, batch, act, raw, specs, head_ops, nxt, cond_acts):
+    def _build_coam(self, das: List[DAModule], xs, batch, act, raw, specs, head_ops, nxt, cond_acts, at):
         arch = self.arch
         outs = []
         for i, (da, x) in enumerate(zip(das, xs)):
+            at(i)
             C_, cc, h, w = da.c, da.cc, da.h, da.w
             assert (x.h, x.w, x.c) == (h, w, C_)
             ccs = _rup(cc, 16)
@@ -461,7 +500,7 @@ class PoseHighResolutionNet(nn.Module):
         def fix(a: Act) -> Act:
             return Act(base + a.ptr, a.b, a.h, a.w, a.c, a.cs)
 
-        for kind, spec, label in bld["specs"]:
+        for kind, spec, label, lane, share in bld["specs"]:
             tag = spec[0]
             if tag == "tg":
                 _, key, src, dst, kw = spec
@@ -507,7 +546,9 @@ class PoseHighResolutionNet(nn.Module):
                 args.p_out = base + p_out.ptr if p_out is not None else None
             else:
                 raise AssertionError(tag)
-            plan.add(kind, args, label)
+            plan.add(kind, args, label, lane=lane, max_ctas=share)
+        if os.environ.get("BUCTD_GRAPH", "1") != "0":
+            plan.instantiate()
         marks = {}
         for name, (idx, a) in bld["marks"].items():
             marks[name] = (idx, [fix(t) for t in a] if isinstance(a, list) else fix(a))

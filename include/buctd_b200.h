@@ -223,12 +223,26 @@ int buctd_nchw32_to_act16(buctd_ctx* ctx, int dtype, const float* x, int batch, 
 enum { BUCTD_OP_TAPGEMM = 1, BUCTD_OP_STEM = 2, BUCTD_OP_FUSE = 3, BUCTD_OP_RESIZE = 4, BUCTD_OP_CHAN_ATT = 5,
        BUCTD_OP_POS_ATT = 6, BUCTD_OP_DA_COMBINE = 7, BUCTD_OP_PRENET = 8, BUCTD_OP_DECODE = 9,
        BUCTD_OP_RASTER = 10 };
+#define BUCTD_MAX_LANES 8
 int buctd_plan_create(buctd_ctx* ctx, buctd_plan** out);
 int buctd_plan_destroy(buctd_plan* plan);
 int buctd_plan_add(buctd_plan* plan, int kind, const void* args, size_t args_size);
+/* Lanes: HRNet's branches (and the terms of an exchange/fuse step) are independent chains.  An op added
+ * with lane L runs in program order with the other ops of lane L and concurrently with other lanes;
+ * dependencies BETWEEN lanes are derived by the library from the device byte ranges every op reads and
+ * writes (RAW, WAW and WAR against the last conflicting op of each other lane), so the result is the
+ * one the serial program order gives.  max_ctas (> 0) caps the CTAs of a persistent tap-GEMM: its share
+ * of the SMs while other lanes run beside it.  buctd_plan_add == lane 0, all SMs. */
+int buctd_plan_add_lane(buctd_plan* plan, int kind, const void* args, size_t args_size, int lane, int max_ctas);
+int buctd_plan_num_lanes(const buctd_plan* plan);
+/* Capture the whole plan once into a CUDA graph (lanes become parallel branches); buctd_plan_run then
+ * costs one cudaGraphLaunch on the caller's stream.  The plan is frozen afterwards. */
+int buctd_plan_instantiate(buctd_plan* plan);
 int buctd_plan_size(const buctd_plan* plan);
+/* all ops: the instantiated graph if there is one, else the lanes on internal streams forked from and
+ * joined back into `stream` */
 int buctd_plan_run(buctd_plan* plan, buctd_stream stream);
-/* run ops [first, last) only (stage-boundary parity tests) */
+/* run ops [first, last) only, serially in program order on `stream` (stage-boundary parity tests) */
 int buctd_plan_run_range(buctd_plan* plan, int first, int last, buctd_stream stream);
 
 #ifdef __cplusplus

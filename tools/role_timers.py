@@ -16,7 +16,9 @@ from gpu_utils import TDT, tapgemm, to_act16  # noqa: E402
 
 lib = L.load()
 CASES = [(48, 48, 3, 64, 96, 72, False), (48, 48, 3, 64, 96, 72, True), (96, 96, 3, 64, 48, 36, True),
-         (192, 192, 3, 64, 24, 18, True), (64, 256, 1, 64, 96, 72, True)]
+         (192, 192, 3, 64, 24, 18, True), (384, 384, 3, 64, 12, 9, True), (64, 256, 1, 64, 96, 72, True),
+         (48, 48, 3, 8, 96, 72, False), (48, 48, 3, 16, 96, 72, False), (48, 48, 3, 32, 96, 72, False), (48, 48, 3, 128, 96, 72, False),
+         (96, 96, 3, 16, 48, 36, False), (96, 96, 3, 128, 48, 36, False)]
 for (cin, cout, k, B, h, w, res) in CASES:
     dt = L.F16
     x = torch.randn(B, cin, h, w, device="cuda")
@@ -32,6 +34,7 @@ for (cin, cout, k, B, h, w, res) in CASES:
     tapgemm(dt, a16, wt, bias, out, H=h, W=w, relu=True, residual=r16)
     e1.record()
     torch.cuda.synchronize()
+    print("%d->%d k%d B%d %dx%d res=%d: %.1f us (one launch incl. host prepare)" % (cin, cout, k, B, h, w, res, e0.elapsed_time(e1) * 1e3))
     buf = (ctypes.c_ulonglong * (148 * 16))()
     if hasattr(lib, "buctd_debug_role_cycles"):
         lib.buctd_debug_role_cycles(buf, 148 * 16)
