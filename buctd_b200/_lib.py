@@ -87,6 +87,29 @@ class RasterArgs(C.Structure):
                 ("out_channels", i32), ("c_off", i32), ("kpts", fp), ("colors", fp), ("out", fp), ("scratch", vp)]
 
 
+MAX_FLIP_CHANNELS = 64
+
+
+class FlipArgs(C.Structure):
+    _fields_ = [("batch", i32), ("channels", i32), ("h", i32), ("w", i32), ("perm", i32 * MAX_FLIP_CHANNELS),
+                ("x", fp), ("out", fp)]
+
+
+class FlipMergeArgs(C.Structure):
+    _fields_ = [("batch", i32), ("k", i32), ("h", i32), ("w", i32), ("shift", i32), ("reserved", i32),
+                ("perm", i32 * MAX_FLIP_CHANNELS), ("hm", fp), ("hm_flipped", fp), ("out", fp)]
+
+
+class JointsMseArgs(C.Structure):
+    _fields_ = [("batch", i32), ("k", i32), ("hw", i32), ("use_target_weight", i32),
+                ("output", fp), ("target", fp), ("target_weight", fp), ("loss", fp), ("grad", fp), ("scratch", vp)]
+
+
+class AdamArgs(C.Structure):
+    _fields_ = [("n", i64), ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+                ("step", i32), ("reserved", i32), ("param", fp), ("grad", fp), ("exp_avg", fp), ("exp_avg_sq", fp)]
+
+
 OP_STRUCT = {OP_TAPGEMM: TapGemmArgs, OP_STEM: StemArgs, OP_FUSE: FuseArgs, OP_RESIZE: ResizeArgs,
              OP_CHAN_ATT: ChanAttArgs, OP_POS_ATT: PosAttArgs, OP_DA_COMBINE: DaCombineArgs, OP_PRENET: PrenetArgs,
              OP_DECODE: DecodeArgs, OP_RASTER: RasterArgs}
@@ -95,7 +118,8 @@ OP_STRUCT = {OP_TAPGEMM: TapGemmArgs, OP_STEM: StemArgs, OP_FUSE: FuseArgs, OP_R
 EXPORTS = ["buctd_abi_version", "buctd_last_error", "buctd_create", "buctd_destroy", "buctd_launch_count",
            "buctd_tapgemm", "buctd_stem_conv", "buctd_hr_fuse", "buctd_cond_resize", "buctd_coam_channel_att",
            "buctd_coam_position_att", "buctd_da_combine", "buctd_prenet", "buctd_decode_heatmaps",
-           "buctd_rasterize_condition", "buctd_act16_to_nchw32", "buctd_nchw32_to_act16", "buctd_plan_create",
+           "buctd_rasterize_condition", "buctd_flip_channels", "buctd_flip_merge", "buctd_joints_mse", "buctd_adam_step",
+           "buctd_act16_to_nchw32", "buctd_nchw32_to_act16", "buctd_plan_create",
            "buctd_plan_destroy", "buctd_plan_add", "buctd_plan_add_lane", "buctd_plan_num_lanes", "buctd_plan_instantiate",
            "buctd_plan_size", "buctd_plan_run", "buctd_plan_run_range"]
 
@@ -128,7 +152,7 @@ def load():
         lib.buctd_launch_count.argtypes = [vp]
         lib.buctd_create.argtypes = [C.c_int, C.POINTER(vp)]
         lib.buctd_destroy.argtypes = [vp]
-        for name in _IMMEDIATE.values():
+        for name in list(_IMMEDIATE.values()) + ["buctd_flip_channels", "buctd_flip_merge", "buctd_joints_mse", "buctd_adam_step"]:
             getattr(lib, name).argtypes = [vp, vp, vp]
         lib.buctd_act16_to_nchw32.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
         lib.buctd_nchw32_to_act16.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -181,6 +205,10 @@ class Context:
     def run(self, kind: int, args: C.Structure, stream: int):
         fn = getattr(self.lib, _IMMEDIATE[kind])
         check(fn(self.handle, C.byref(args), vp(stream)), _IMMEDIATE[kind])
+
+    def call(self, name: str, args: C.Structure, stream: int):
+        """immediate entry points outside the plan op table (flip / loss / Adam)"""
+        check(getattr(self.lib, name)(self.handle, C.byref(args), vp(stream)), name)
 
     def act16_to_nchw32(self, dtype, act_ptr, b, h, w, c, cs, out_ptr, stream):
         check(self.lib.buctd_act16_to_nchw32(self.handle, dtype, vp(act_ptr), b, h, w, c, cs, vp(out_ptr), vp(stream)),

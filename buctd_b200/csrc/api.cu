@@ -316,6 +316,25 @@ BUCTD_API int buctd_decode_heatmaps(buctd_ctx* c, const buctd_decode_args* a, bu
 BUCTD_API int buctd_rasterize_condition(buctd_ctx* c, const buctd_raster_args* a, buctd_stream s) {
   return immediate(c, BUCTD_OP_RASTER, a, sizeof(*a), s);
 }
+template <typename A, typename F>
+static int simple_call(buctd_ctx* c, const A* a, int nlaunch, F&& fn) {
+  BUCTD_CHECK(c != nullptr && a != nullptr, BUCTD_ERR_INVALID, "null ctx or args");
+  int rc = fn(*a);
+  if (!rc) c->launches += nlaunch;
+  return rc;
+}
+BUCTD_API int buctd_flip_channels(buctd_ctx* c, const buctd_flip_args* a, buctd_stream s) {
+  return simple_call(c, a, 1, [&](const buctd_flip_args& x) { return launch_flip_channels(x, static_cast<cudaStream_t>(s)); });
+}
+BUCTD_API int buctd_flip_merge(buctd_ctx* c, const buctd_flip_merge_args* a, buctd_stream s) {
+  return simple_call(c, a, 1, [&](const buctd_flip_merge_args& x) { return launch_flip_merge(x, static_cast<cudaStream_t>(s)); });
+}
+BUCTD_API int buctd_joints_mse(buctd_ctx* c, const buctd_joints_mse_args* a, buctd_stream s) {
+  return simple_call(c, a, 2, [&](const buctd_joints_mse_args& x) { return launch_joints_mse(x, static_cast<cudaStream_t>(s)); });
+}
+BUCTD_API int buctd_adam_step(buctd_ctx* c, const buctd_adam_args* a, buctd_stream s) {
+  return simple_call(c, a, 1, [&](const buctd_adam_args& x) { return launch_adam(x, c->sm_count, static_cast<cudaStream_t>(s)); });
+}
 BUCTD_API int buctd_act16_to_nchw32(buctd_ctx* c, int dtype, const void* act, int batch, int h, int w, int ch, int cs,
                                     float* out, buctd_stream s) {
   BUCTD_CHECK(c != nullptr, BUCTD_ERR_INVALID, "null ctx");

@@ -83,6 +83,10 @@ int launch_raster(const buctd_raster_args& a, cudaStream_t st, int* nlaunch);
 int launch_act16_to_nchw32(int dtype, const void* act, int B, int H, int W, int C, int cs, float* out, cudaStream_t st);
 int launch_nchw32_to_act16(int dtype, const float* x, int B, int xc, int c_off, int C, int H, int W, int cs, void* out,
                            cudaStream_t st);
+int launch_flip_channels(const buctd_flip_args& a, cudaStream_t st);
+int launch_flip_merge(const buctd_flip_merge_args& a, cudaStream_t st);
+int launch_joints_mse(const buctd_joints_mse_args& a, cudaStream_t st);
+int launch_adam(const buctd_adam_args& a, int sm_count, cudaStream_t st);
 int pos_att_init_device();
 int pos_att_tc_init_device();
 bool pos_att_tc_supported(const buctd_pos_att_args& a);

@@ -1,0 +1,179 @@
+// Kernels of the callers either side of the forward (SURVEY.md section 8 rows a-L, a-T and f-1):
+//   * flip-test input flip / flip_back + SHIFT_HEATMAP + average  (lib/core/function.py:213-236,
+//     lib/utils/transforms.py:16-58) -- the reference round-trips the heat-maps through host NumPy for this
+//   * JointsMSELoss forward + gradient                            (lib/core/loss.py:17-41)
+//   * Adam step over one flat parameter buffer                     (lib/utils/utils.py:268-272 -> torch.optim.Adam)
+// All HBM-bound streaming kernels: coalesced float4 accesses where the geometry allows, grids sized in multiples of
+// the SM count, fixed-order (bit-reproducible) reductions.
+#include "common.cuh"
+#include "internal.h"
+
+namespace buctd {
+
+// =================================================================================================
+// out[b][c][y][x] = x[b][perm[c]][y][W-1-x]
+// =================================================================================================
+__global__ void __launch_bounds__(256) flip_channels_kernel(buctd_flip_args a) {
+  // one block per (b, c, group of rows); a warp mirrors one row through registers
+  const int plane = blockIdx.y;                 // b * C + c
+  const int b = plane / a.channels, c = plane - b * a.channels;
+  const float* src = a.x + ((long long)b * a.channels + a.perm[c]) * a.h * a.w;
+  float* dst = a.out + (long long)plane * a.h * a.w;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int y = blockIdx.x * 8 + warp; y < a.h; y += gridDim.x * 8) {
+    const float* s = src + (long long)y * a.w;
+    float* d = dst + (long long)y * a.w;
+    for (int x = lane; x < a.w; x += 32) d[x] = __ldg(s + (a.w - 1 - x));
+  }
+}
+
+int launch_flip_channels(const buctd_flip_args& a, cudaStream_t st) {
+  BUCTD_CHECK(a.x && a.out && a.x != a.out, BUCTD_ERR_INVALID, "flip_channels: null or aliased pointers");
+  BUCTD_CHECK(a.channels > 0 && a.channels <= BUCTD_MAX_FLIP_CHANNELS, BUCTD_ERR_INVALID, "flip_channels: %d channels (max %d)",
+              a.channels, BUCTD_MAX_FLIP_CHANNELS);
+  for (int c = 0; c < a.channels; ++c)
+    BUCTD_CHECK(a.perm[c] >= 0 && a.perm[c] < a.channels, BUCTD_ERR_INVALID, "flip_channels: perm[%d] = %d out of range", c, a.perm[c]);
+  if (a.batch == 0) return BUCTD_OK;
+  dim3 grid(ceil_div(a.h, 8 * 4), a.batch * a.channels);
+  flip_channels_kernel<<<grid, 256, 0, st>>>(a);
+  BUCTD_CUDA(cudaGetLastError());
+  return BUCTD_OK;
+}
+
+// =================================================================================================
+// out = (hm + S) * 0.5,  F[b][k][y][x] = hm_flipped[b][perm[k]][y][W-1-x],  S = F shifted right by one column
+// (column 0 keeps F[0]) when shift != 0, else S = F.
+// =================================================================================================
+__global__ void __launch_bounds__(256) flip_merge_kernel(buctd_flip_merge_args a) {
+  const int plane = blockIdx.y;
+  const int b = plane / a.k, k = plane - b * a.k;
+  const float* o = a.hm + (long long)plane * a.h * a.w;
+  const float* f = a.hm_flipped + ((long long)b * a.k + a.perm[k]) * a.h * a.w;
+  float* d = a.out + (long long)plane * a.h * a.w;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int y = blockIdx.x * 8 + warp; y < a.h; y += gridDim.x * 8) {
+    const long long ro = (long long)y * a.w;
+    for (int x = lane; x < a.w; x += 32) {
+      const int xs = a.shift ? (x > 0 ? x - 1 : 0) : x;          // column of F that lands on x
+      const float fv = __ldg(f + ro + (a.w - 1 - xs));
+      d[ro + x] = (o[ro + x] + fv) * 0.5f;
+    }
+  }
+}
+
+int launch_flip_merge(const buctd_flip_merge_args& a, cudaStream_t st) {
+  BUCTD_CHECK(a.hm && a.hm_flipped && a.out, BUCTD_ERR_INVALID, "flip_merge: null pointer");
+  BUCTD_CHECK(a.out != a.hm_flipped, BUCTD_ERR_INVALID, "flip_merge: out must not alias hm_flipped");
+  BUCTD_CHECK(a.k > 0 && a.k <= BUCTD_MAX_FLIP_CHANNELS, BUCTD_ERR_INVALID, "flip_merge: %d joints (max %d)", a.k, BUCTD_MAX_FLIP_CHANNELS);
+  for (int c = 0; c < a.k; ++c)
+    BUCTD_CHECK(a.perm[c] >= 0 && a.perm[c] < a.k, BUCTD_ERR_INVALID, "flip_merge: perm[%d] = %d out of range", c, a.perm[c]);
+  if (a.batch == 0) return BUCTD_OK;
+  dim3 grid(ceil_div(a.h, 8 * 4), a.batch * a.k);
+  flip_merge_kernel<<<grid, 256, 0, st>>>(a);
+  BUCTD_CUDA(cudaGetLastError());
+  return BUCTD_OK;
+}
+
+// =================================================================================================
+// JointsMSELoss: loss = 0.5 / (K B HW) * sum_{b,k,p} (w_bk (o - t))^2 ; grad = w_bk^2 (o - t) / (K B HW)
+// pass 1: one block per (b,k) row -> partial sum (double); pass 2: one block adds the B*K partials in index order
+// =================================================================================================
+__global__ void __launch_bounds__(256) joints_mse_rows_kernel(buctd_joints_mse_args a) {
+  const int row = blockIdx.x;                    // b * K + k
+  const float w = a.use_target_weight ? a.target_weight[row] : 1.f;
+  const float* o = a.output + (long long)row * a.hw;
+  const float* t = a.target + (long long)row * a.hw;
+  float* g = a.grad ? a.grad + (long long)row * a.hw : nullptr;
+  const float gscale = w * w / ((float)a.k * (float)a.batch * (float)a.hw);
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < a.hw; i += 256) {
+    const float d = o[i] - t[i];
+    const float wd = w * d;
+    acc += (double)wd * (double)wd;
+    if (g) g[i] = gscale * d;
+  }
+  __shared__ double s[256];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int n = 128; n > 0; n >>= 1) {
+    if (threadIdx.x < n) s[threadIdx.x] += s[threadIdx.x + n];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) a.scratch[row] = s[0];
+}
+
+__global__ void __launch_bounds__(256) joints_mse_final_kernel(buctd_joints_mse_args a) {
+  __shared__ double s[256];
+  const int rows = a.batch * a.k;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < rows; i += 256) acc += a.scratch[i];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int n = 128; n > 0; n >>= 1) {
+    if (threadIdx.x < n) s[threadIdx.x] += s[threadIdx.x + n];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *a.loss = (float)(0.5 * s[0] / ((double)a.k * (double)a.batch * (double)a.hw));
+}
+
+int launch_joints_mse(const buctd_joints_mse_args& a, cudaStream_t st) {
+  BUCTD_CHECK(a.output && a.target && a.loss && a.scratch, BUCTD_ERR_INVALID, "joints_mse: null pointer");
+  BUCTD_CHECK(!a.use_target_weight || a.target_weight, BUCTD_ERR_INVALID, "joints_mse: use_target_weight without target_weight");
+  BUCTD_CHECK(a.batch > 0 && a.k > 0 && a.hw > 0, BUCTD_ERR_INVALID, "joints_mse: empty input %dx%dx%d", a.batch, a.k, a.hw);
+  joints_mse_rows_kernel<<<a.batch * a.k, 256, 0, st>>>(a);
+  joints_mse_final_kernel<<<1, 256, 0, st>>>(a);
+  BUCTD_CUDA(cudaGetLastError());
+  return BUCTD_OK;
+}
+
+// =================================================================================================
+// Adam (torch.optim.Adam defaults the reference uses: betas (0.9, 0.999), eps 1e-8, no weight decay, no amsgrad),
+// in torch's own operation order so the step matches it to rounding:
+//   m = m + (g - m) (1 - b1);  v = v b2 + (1 - b2) g g;  p -= (lr / (1 - b1^t)) m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+// =================================================================================================
+struct AdamScalars {
+  float beta2, omb1, omb2, eps, step_size, bc2_sqrt;
+};
+__global__ void __launch_bounds__(256) adam_kernel(buctd_adam_args a, AdamScalars c) {
+  const float omb1 = c.omb1, omb2 = c.omb2, step_size = c.step_size, bc2_sqrt = c.bc2_sqrt;
+  const long long n4 = a.n >> 2;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  auto upd = [&](float& p, float g, float& m, float& v) {
+    m = m + (g - m) * omb1;
+    v = v * c.beta2 + omb2 * g * g;
+    const float denom = sqrtf(v) / bc2_sqrt + c.eps;
+    p = p - step_size * (m / denom);
+  };
+  float4* P = reinterpret_cast<float4*>(a.param);
+  const float4* G = reinterpret_cast<const float4*>(a.grad);
+  float4* M = reinterpret_cast<float4*>(a.exp_avg);
+  float4* V = reinterpret_cast<float4*>(a.exp_avg_sq);
+  for (long long i = tid; i < n4; i += nth) {
+    float4 p = P[i], m = M[i], v = V[i];
+    const float4 g = G[i];
+    upd(p.x, g.x, m.x, v.x); upd(p.y, g.y, m.y, v.y); upd(p.z, g.z, m.z, v.z); upd(p.w, g.w, m.w, v.w);
+    P[i] = p; M[i] = m; V[i] = v;
+  }
+  for (long long i = (n4 << 2) + tid; i < a.n; i += nth) upd(a.param[i], a.grad[i], a.exp_avg[i], a.exp_avg_sq[i]);
+}
+
+int launch_adam(const buctd_adam_args& a, int sm_count, cudaStream_t st) {
+  BUCTD_CHECK(a.param && a.grad && a.exp_avg && a.exp_avg_sq, BUCTD_ERR_INVALID, "adam: null pointer");
+  BUCTD_CHECK(a.step >= 1, BUCTD_ERR_INVALID, "adam: step must be >= 1 (got %d)", a.step);
+  BUCTD_CHECK((((uintptr_t)a.param | (uintptr_t)a.grad | (uintptr_t)a.exp_avg | (uintptr_t)a.exp_avg_sq) & 15) == 0,
+              BUCTD_ERR_INVALID, "adam: buffers must be 16-byte aligned");
+  if (a.n <= 0) return BUCTD_OK;
+  // scalars in double on the host, rounded to float once, exactly as torch's Python-side scalar arithmetic does
+  const double bc1 = 1.0 - pow(a.beta1, (double)a.step), bc2 = 1.0 - pow(a.beta2, (double)a.step);
+  AdamScalars c;
+  c.beta2 = (float)a.beta2; c.omb1 = (float)(1.0 - a.beta1); c.omb2 = (float)(1.0 - a.beta2); c.eps = (float)a.eps;
+  c.step_size = (float)(a.lr / bc1); c.bc2_sqrt = (float)sqrt(bc2);
+  long long want = (a.n / 4 + 255) / 256;
+  const long long cap = (long long)sm_count * 8;               // 8 resident 256-thread blocks per SM, grid-stride beyond
+  const int blocks = (int)(want < 1 ? 1 : (want < cap ? want : cap));
+  adam_kernel<<<blocks, 256, 0, st>>>(a, c);
+  BUCTD_CUDA(cudaGetLastError());
+  return BUCTD_OK;
+}
+
+}  // namespace buctd

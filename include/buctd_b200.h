@@ -209,6 +209,56 @@ typedef struct {
 } buctd_raster_args;
 int buctd_rasterize_condition(buctd_ctx* ctx, const buctd_raster_args* args, buctd_stream stream);
 
+/* ------------------------------------------------------------------------------------------
+ * The callers either side of the forward (a-L, a-T).
+ * ------------------------------------------------------------------------------------------ */
+#define BUCTD_MAX_FLIP_CHANNELS 64
+/* Mirror + channel permutation of an nchw32 tensor: out[b][c][y][x] = x[b][perm[c]][y][W-1-x].
+ * With perm = identity on the RGB planes and the dataset's flip_pairs swapped on the stacked condition planes
+ * this is the flip-test input of validate(): input[:, :3].flip(3) ++ flip_hm(input[:, 3:]),
+ * lib/core/function.py:213-217 and lib/utils/transforms.py:49-55 (which goes through host NumPy). */
+typedef struct {
+  int32_t batch, channels, h, w;
+  int32_t perm[BUCTD_MAX_FLIP_CHANNELS];
+  const float* x; float* out;
+} buctd_flip_args;
+int buctd_flip_channels(buctd_ctx* ctx, const buctd_flip_args* args, buctd_stream stream);
+
+/* Flip-test merge: out = (hm + S) * 0.5 with F = flip_back(hm_flipped, flip_pairs) (mirror + joint swap,
+ * perm[k] = partner of k) and S = F shifted one column to the right when shift != 0 (column 0 keeps F[0]:
+ * "output_flipped[:, :, :, 1:] = output_flipped.clone()[:, :, :, 0:-1]").  out may alias hm.
+ * Replaces flip_back + SHIFT_HEATMAP + average, lib/core/function.py:226-236, lib/utils/transforms.py:16-30
+ * (a D2H + H2D round trip of the heat-maps in the reference). */
+typedef struct {
+  int32_t batch, k, h, w, shift, reserved;
+  int32_t perm[BUCTD_MAX_FLIP_CHANNELS];
+  const float* hm; const float* hm_flipped; float* out;
+} buctd_flip_merge_args;
+int buctd_flip_merge(buctd_ctx* ctx, const buctd_flip_merge_args* args, buctd_stream stream);
+
+/* JointsMSELoss: *loss = 0.5 / (K B HW) * sum (w[b][k] (output - target))^2 (w = 1 without use_target_weight)
+ * and, if grad != NULL, grad = d loss / d output = w^2 (output - target) / (K B HW).  output, target, grad:
+ * float32 [B][K][HW]; target_weight float32 [B][K]; scratch: B*K doubles.  Fixed-order reduction in float64
+ * (bit-reproducible).  Replaces JointsMSELoss.forward (+ its autograd backward), lib/core/loss.py:17-41. */
+typedef struct {
+  int32_t batch, k, hw, use_target_weight;
+  const float* output; const float* target; const float* target_weight;
+  float* loss; float* grad; double* scratch;
+} buctd_joints_mse_args;
+int buctd_joints_mse(buctd_ctx* ctx, const buctd_joints_mse_args* args, buctd_stream stream);
+
+/* One Adam step over a flat float32 buffer of n parameters (torch.optim.Adam as get_optimizer builds it,
+ * lib/utils/utils.py:268-272: only lr is passed, so betas (0.9, 0.999), eps 1e-8, no weight decay, no amsgrad):
+ *   m += (g - m)(1 - beta1);  v = v beta2 + (1 - beta2) g^2;  p -= lr/(1 - beta1^step) * m / (sqrt(v)/sqrt(1 - beta2^step) + eps)
+ * step counts from 1.  All four buffers 16-byte aligned. */
+typedef struct {
+  int64_t n;
+  double lr, beta1, beta2, eps;
+  int32_t step, reserved;
+  float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
+} buctd_adam_args;
+int buctd_adam_step(buctd_ctx* ctx, const buctd_adam_args* args, buctd_stream stream);
+
 /* Utility kernels used by the host mirror: zero-fill, and act16 -> nchw32 export for tests. */
 int buctd_act16_to_nchw32(buctd_ctx* ctx, int dtype, const void* act, int batch, int h, int w, int c, int cs,
                           float* out, buctd_stream stream);
