@@ -198,6 +198,77 @@ __device__ __forceinline__ void epi_compute_fast(const TapGemmKParams& p, const 
   }
 }
 
+// ---- direct path: no shared-memory staging at all ---------------------------------------------------
+// The SS-mode tcgen05.mma of these layers is bound by shared-memory operand bandwidth, so every byte
+// the epilogue moves through shared memory (stage write, TMA-store read, residual TMA write + read) is taken from the
+// tensor core.  Here a thread owns one output row and writes it with 16-byte st.global (every 32-byte sector of the
+// row is completely written by two of them); only the residual tile still comes through a TMA-filled stage.
+// one full 32-byte sector per thread and instruction (sm_100 256-bit store)
+__device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+               "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+__device__ __forceinline__ void stg128(void* p, const uint4& v) {
+  asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <typename T, int BN, bool RES>
+__device__ __forceinline__ void epi_compute_direct(const TapGemmKParams& p, const EpiTile& tile, int n0, uint32_t tmem_acc,
+                                                   const uint8_t* stage, const float* s_bias, int q, int lane) {
+  const int row = q * 32 + lane;
+  const EpiRow me = epi_row(p, tile, row);
+  const bool zero = me.pad;
+  const long long r = tile.m0 + row;
+  const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
+  const uint32_t bias_addr = smem_u32(s_bias);
+  const uint32_t lo2 = Finish<T>::lo(p.relu != 0);
+  T* orow = reinterpret_cast<T*>(p.out) + r * p.out_cs + n0;
+  // the residual tile was prefetched by TMA into the SWIZZLE_128B stage (its latency is off the critical path; a
+  // per-thread ld.global of the row measured 20-80 % slower kernels)
+  const uint32_t srow = smem_u32(stage) + (uint32_t)row * 128u;
+  const uint32_t sw = (uint32_t)row & 7u;
+  constexpr int CW = 64;                                    // columns per TMEM round trip
+#pragma unroll
+  for (int c0 = 0; c0 < BN; c0 += CW) {
+    constexpr int kMaxW = BN < CW ? BN : CW;
+    const int cw = (BN - c0) < CW ? (BN - c0) : CW;          // compile-time after unrolling
+    uint32_t acc[kMaxW];
+#pragma unroll
+    for (int i = 0; i < kMaxW / 16; ++i)
+      if (i * 16 < cw) tmem_ld16(taddr + c0 + i * 16, &acc[i * 16]);
+    tmem_ld_wait();
+    const uint32_t blk = srow + (uint32_t)(c0 >> 6) * kEpiBlockBytes;
+    uint4 prev = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int u = 0; u < kMaxW / 8; ++u) {
+      if (u * 8 < cw) {
+        const uint4 b0 = lds128(bias_addr + (uint32_t)(c0 + u * 8) * 4u), b1 = lds128(bias_addr + (uint32_t)(c0 + u * 8 + 4) * 4u);
+        float v[8];
+        v[0] = __uint_as_float(acc[u * 8 + 0]) + __uint_as_float(b0.x); v[1] = __uint_as_float(acc[u * 8 + 1]) + __uint_as_float(b0.y);
+        v[2] = __uint_as_float(acc[u * 8 + 2]) + __uint_as_float(b0.z); v[3] = __uint_as_float(acc[u * 8 + 3]) + __uint_as_float(b0.w);
+        v[4] = __uint_as_float(acc[u * 8 + 4]) + __uint_as_float(b1.x); v[5] = __uint_as_float(acc[u * 8 + 5]) + __uint_as_float(b1.y);
+        v[6] = __uint_as_float(acc[u * 8 + 6]) + __uint_as_float(b1.z); v[7] = __uint_as_float(acc[u * 8 + 7]) + __uint_as_float(b1.w);
+        if (RES) {
+          const uint4 rs = lds128(blk + ((((uint32_t)u) ^ sw) << 4));
+          float2 f;
+          f = T16<T>::unpack2(rs.x); v[0] += f.x; v[1] += f.y;
+          f = T16<T>::unpack2(rs.y); v[2] += f.x; v[3] += f.y;
+          f = T16<T>::unpack2(rs.z); v[4] += f.x; v[5] += f.y;
+          f = T16<T>::unpack2(rs.w); v[6] += f.x; v[7] += f.y;
+        }
+        uint4 o;
+        o.x = Finish<T>::run(v[0], v[1], lo2); o.y = Finish<T>::run(v[2], v[3], lo2);
+        o.z = Finish<T>::run(v[4], v[5], lo2); o.w = Finish<T>::run(v[6], v[7], lo2);
+        if (zero) o = make_uint4(0, 0, 0, 0);
+        // BN % 16 == 0: units pair up into 32-byte sectors (rows and N tiles are 32-byte aligned, checked on the host)
+        if (u & 1) { if (me.valid) stg256(orow + c0 + (u - 1) * 8, prev, o); }
+        else prev = o;
+      }
+    }
+  }
+}
+
 // TMEM -> (+bias, +residual from stage, ReLU, mask) -> 16-bit -> stage (in place).  Work unit = 8
 // columns (one 16-byte chunk); warp group `grp` of `ngrp` takes every ngrp-th unit of its rows.  The
 // next unit's tcgen05.ld is issued before the current one is processed.

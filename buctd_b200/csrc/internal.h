@@ -42,6 +42,7 @@ struct SlabParams {
   int num_super, num_items;
   int tmem_cols, smem_bytes;
   int desc_mode;
+  int direct;        // epilogue writes rows straight to global memory (no stage buffers, no DMA warp)
   int jmajor;        // resident weights + one K chunk: sub-tile-major MMA order (per-sub-tile hand-off to the epilogue)
 };
 

@@ -243,7 +243,7 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   // Epilogue organisation.  Two groups of 4 warps (one warp per TMEM lane quarter).  With two stage buffers
   // each group owns one buffer and takes every other sub-tile (whole tiles in parallel); with one stage
   // buffer (shared memory is tight) both groups work on the same tile and split its columns.
-  const bool split = sp.stage_bufs == 1;
+  const bool split = sp.stage_bufs == 1 && !sp.direct;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -254,19 +254,30 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     for (int s = 0; s < 2; ++s) { mbar_init(&st_ready[s], 1); mbar_init(&st_done[s], split ? 8 : 4); }
     tma_prefetch_desc(&map_out);
     fence_mbar_init();
+    if (sp.w_resident) {
+      // Start the pipeline before the CTA-wide sync (the TMA engine only needs the barriers this thread has just
+      // initialised): the weights are constants and go first, then -- once the previous kernel of the stream has
+      // completed -- the first slabs.  Their latency overlaps the TMEM allocation and the prologue of the other warps.
+      mbar_expect_tx(&w_full[0], (uint32_t)(sp.w_tiles * kWTileBytes));
+      for (int kc = 0; kc < p.num_kc; ++kc)
+        for (int t = 0; t < p.ntaps; ++t)
+          tma_load_2d(wbuf + (size_t)(kc * p.ntaps + t) * kWTileBytes, &map_b, &w_full[0], kc * 64, t * p.n_alloc);
+      pdl_wait();
+      const long long r0 = (long long)((int)blockIdx.x % sp.num_super) * (MSUB * kBlockM) - sp.halo;
+      const int npre = p.num_kc < sp.sa ? p.num_kc : sp.sa;
+      for (int kc = 0; kc < npre; ++kc) {
+        mbar_expect_tx(&slab_full[kc], (uint32_t)sp.slab_bytes);
+        for (int i = 0; i < sp.nboxes; ++i)
+          tma_load_2d(slabs + (size_t)kc * sp.slab_bytes + (size_t)i * sp.box_rows * 128, &map_a, &slab_full[kc], kc * 64,
+                      (int)(r0 + (long long)i * sp.box_rows));
+      }
+    }
   }
   if (warp == 1) tmem_alloc(tmem_slot, sp.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   pdl_launch_dependents();
-  if (warp == 0 && lane == 0 && sp.w_resident) {
-    // the weights are constants: fetch them while the previous kernel of the stream drains
-    mbar_expect_tx(&w_full[0], (uint32_t)(sp.w_tiles * kWTileBytes));
-    for (int kc = 0; kc < p.num_kc; ++kc)
-      for (int t = 0; t < p.ntaps; ++t)
-        tma_load_2d(wbuf + (size_t)(kc * p.ntaps + t) * kWTileBytes, &map_b, &w_full[0], kc * 64, t * p.n_alloc);
-  }
   RT_DECL(t_pro); RT_DECL(t_pdl);
   RT_ADD(t_pro, t_cta_start);
   pdl_wait();                                   // activations are produced by the previous kernel
@@ -278,11 +289,17 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   if (warp == 0) {
     if (lane == 0) {
       uint32_t slot = 0, slot_ph = 1, ws = 0, ws_ph = 1;     // producer waits on the "empty" phase (starts free)
+      int pre = sp.w_resident ? (p.num_kc < sp.sa ? p.num_kc : sp.sa) : 0;    // slabs of the first item issued in the prologue
       SubIter it;
       it.init(sp.num_super);
       for (int k = 0; k < my_items; ++k, it.next_item()) {
         const long long r0 = (long long)it.s * R - sp.halo;
         for (int kc = 0; kc < p.num_kc; ++kc) {
+          if (pre > 0) {
+            --pre;
+            if (++slot == (uint32_t)sp.sa) { slot = 0; slot_ph ^= 1; }
+            continue;
+          }
           mbar_wait(&slab_empty[slot], slot_ph);
           mbar_expect_tx(&slab_full[slot], (uint32_t)sp.slab_bytes);
           for (int i = 0; i < sp.nboxes; ++i)
@@ -408,7 +425,7 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int SE = sp.stage_bufs;
     const int total_u = my_items * MSUB;
     if (warp == 10) {
-      if (!head && elect_one()) {
+      if (!head && (!sp.direct || has_res) && elect_one()) {
         SubIter st_it, pr_it;
         st_it.init(sp.num_super);
         pr_it.init(sp.num_super);
@@ -432,10 +449,10 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           EpiTile t;
           t.m0 = st_it.template m0<MSUB>();
           t.tb = t.ty0 = t.tx0 = 0;
-          epi_store<BN>(p, &map_out, t, st_it.nt * BN, stage + (size_t)e * epi_stage_bytes<BN>());
+          if (!sp.direct) epi_store<BN>(p, &map_out, t, st_it.nt * BN, stage + (size_t)e * epi_stage_bytes<BN>());
           st_it.template next<MSUB>();
           if (u + SE < total_u) {
-            tma_store_wait_read<0>();          // buffer e is free again once its store has read it
+            if (!sp.direct) tma_store_wait_read<0>();          // buffer e is free again once its store has read it
             prepare(u + SE);
           }
         }
@@ -471,6 +488,18 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const uint32_t acc = tmem_base + aslot * BN;
         if (head) {
           if (!split || grp == 0) epi_head_nchw32<BN>(p, tile, nt * BN, acc, q, lane);
+        } else if (sp.direct) {
+          if (has_res) {       // direct stores; the residual tile arrives by TMA in this group's stage buffer
+            uint8_t* st = stage + (size_t)grp * epi_stage_bytes<BN>();
+            { RT_BEGIN(t0); mbar_wait(&st_ready[grp], (u >> 1) & 1); RT_ADD(e_res, t0); }
+            { RT_BEGIN(t0); epi_compute_direct<T, BN, true>(p, tile, nt * BN, acc, st, my_bias, q, lane); RT_ADD(e_comp, t0); }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&st_done[grp]);
+          } else {
+            RT_BEGIN(t0);
+            epi_compute_direct<T, BN, false>(p, tile, nt * BN, acc, stage, my_bias, q, lane);
+            RT_ADD(e_comp, t0);
+          }
         } else {
           const int e = split ? 0 : grp;
           uint8_t* st = stage + (size_t)e * epi_stage_bytes<BN>();
@@ -585,7 +614,16 @@ static bool plan_slab_one(const buctd_tapgemm_args& a, int bn, int num_kc, int k
   const int n_tiles = ceil_div(a.n_alloc, bn);
   const int halo = a.ntaps == 9 ? a.out_w + 2 : 0;        // (W+1) + 1 rows on each side
   const int wtile = bn * 128;
-  const int stage = stage_bytes(bn);
+  // direct epilogue: 16-bit rows, every N tile full (no channel tail), 16-byte aligned rows
+  static const bool no_direct = getenv("BUCTD_NO_DIRECT") != nullptr;       // debug knob
+  // (measured: a win for rows of <= 128 bytes, a loss for wide tiles whose rows are many partial-sector writes)
+  // Opt-in (BUCTD_DIRECT_MAX_BN=256): isolated launches gain 3-18 % at bn <= 64, the whole forward does not
+  // (14.15 vs 14.20 ms per 64 crops), so the staged TMA-store epilogue stays the default.
+  static const int direct_max_bn = getenv("BUCTD_DIRECT_MAX_BN") ? atoi(getenv("BUCTD_DIRECT_MAX_BN")) : 0;
+  bool direct = !no_direct && bn <= direct_max_bn && bn % 16 == 0 && a.out_mode != BUCTD_OUT_NCHW32 && a.n % bn == 0 && a.n == a.n_alloc &&
+                a.out_cs % 16 == 0 && ((uintptr_t)a.out & 31) == 0;
+  const bool stage_needed = !direct || a.residual != nullptr;      // direct mode still prefetches the residual tile by TMA
+  const int stage = stage_needed ? stage_bytes(bn) : 0;
   const int fixed = 1024 + 2 * bn * 4 + 512;              // alignment slack + two bias tiles + barriers
   const long long total_w = (long long)a.ntaps * num_kc * wtile;
   const bool resident = n_tiles == 1 && total_w <= 80 * 1024;
@@ -604,16 +642,18 @@ static bool plan_slab_one(const buctd_tapgemm_args& a, int bn, int num_kc, int k
         if (need <= kSmemBudget) { sa = csa; sw = csw; se = cse; break; }
       }
   if (sa == 0) return false;
+  if (direct && a.residual != nullptr && se != 2) direct = false;  // direct + residual needs one stage buffer per epilogue group
   SlabParams c;
   memset(&c, 0, sizeof(c));
   const long long supers = (a.m_rows + (long long)msub * 128 - 1) / ((long long)msub * 128);
   c.msub = msub; c.halo = halo; c.nboxes = nboxes; c.box_rows = box_rows; c.slab_bytes = (int)slab;
-  c.sa = sa; c.sw = sw; c.stage_bufs = se; c.w_resident = resident; c.w_tiles = resident ? a.ntaps * num_kc : sw;
+  c.sa = sa; c.sw = sw; c.stage_bufs = stage_needed ? se : 0; c.w_resident = resident; c.w_tiles = resident ? a.ntaps * num_kc : sw;
   c.num_super = (int)supers; c.num_items = (int)supers * n_tiles; c.smem_bytes = (int)need;
   // sub-tile-major order serialises 9*ksteps MMAs on ONE accumulator (measured 71 instead of 47 clk per MMA at bn=48):
   // kept behind a knob, off by default
   static const bool want_jmajor = getenv("BUCTD_JMAJOR") != nullptr && atoi(getenv("BUCTD_JMAJOR")) != 0;
   c.jmajor = want_jmajor && resident && num_kc == 1;
+  c.direct = direct;
   const int cols = nacc * bn;
   c.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
   *out = c;
