@@ -25,7 +25,8 @@ def chan_att_scratch_floats(batch: int, h: int, w: int, c: int) -> int:
     nchunks = ((h + 1) * (w + 1) + CHAN_ATT_ROWS_PER_CHUNK - 1) // CHAN_ATT_ROWS_PER_CHUNK
     return batch * nchunks * c * c
 (OP_TAPGEMM, OP_STEM, OP_FUSE, OP_RESIZE, OP_CHAN_ATT, OP_POS_ATT, OP_DA_COMBINE, OP_PRENET, OP_DECODE,
- OP_RASTER) = range(1, 11)
+ OP_RASTER, OP_CHAIN) = range(1, 12)
+MAX_CHAIN = 8
 
 i32, i64, vp, fp = C.c_int32, C.c_int64, C.c_void_p, C.c_void_p
 
@@ -36,6 +37,10 @@ class TapGemmArgs(C.Structure):
                 ("k", i32), ("a_cs", i32), ("n", i32), ("n_alloc", i32), ("w_cs", i32), ("out_cs", i32),
                 ("res_cs", i32), ("relu", i32), ("out_mode", i32), ("reserved", i32),
                 ("a", vp), ("w", vp), ("bias", fp), ("residual", vp), ("out", vp)]
+
+
+class TapGemmChainArgs(C.Structure):
+    _fields_ = [("n_layers", i32), ("reserved", i32), ("layer", TapGemmArgs * MAX_CHAIN)]
 
 
 class StemArgs(C.Structure):
@@ -112,11 +117,11 @@ class AdamArgs(C.Structure):
 
 OP_STRUCT = {OP_TAPGEMM: TapGemmArgs, OP_STEM: StemArgs, OP_FUSE: FuseArgs, OP_RESIZE: ResizeArgs,
              OP_CHAN_ATT: ChanAttArgs, OP_POS_ATT: PosAttArgs, OP_DA_COMBINE: DaCombineArgs, OP_PRENET: PrenetArgs,
-             OP_DECODE: DecodeArgs, OP_RASTER: RasterArgs}
+             OP_DECODE: DecodeArgs, OP_RASTER: RasterArgs, OP_CHAIN: TapGemmChainArgs}
 
 # every symbol include/buctd_b200.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = ["buctd_abi_version", "buctd_last_error", "buctd_create", "buctd_destroy", "buctd_launch_count",
-           "buctd_tapgemm", "buctd_stem_conv", "buctd_hr_fuse", "buctd_cond_resize", "buctd_coam_channel_att",
+           "buctd_tapgemm", "buctd_tapgemm_chain", "buctd_stem_conv", "buctd_hr_fuse", "buctd_cond_resize", "buctd_coam_channel_att",
            "buctd_coam_position_att", "buctd_da_combine", "buctd_prenet", "buctd_decode_heatmaps",
            "buctd_rasterize_condition", "buctd_flip_channels", "buctd_flip_merge", "buctd_joints_mse", "buctd_adam_step",
            "buctd_act16_to_nchw32", "buctd_nchw32_to_act16", "buctd_plan_create",
@@ -126,7 +131,7 @@ EXPORTS = ["buctd_abi_version", "buctd_last_error", "buctd_create", "buctd_destr
 _IMMEDIATE = {OP_TAPGEMM: "buctd_tapgemm", OP_STEM: "buctd_stem_conv", OP_FUSE: "buctd_hr_fuse",
               OP_RESIZE: "buctd_cond_resize", OP_CHAN_ATT: "buctd_coam_channel_att",
               OP_POS_ATT: "buctd_coam_position_att", OP_DA_COMBINE: "buctd_da_combine", OP_PRENET: "buctd_prenet",
-              OP_DECODE: "buctd_decode_heatmaps", OP_RASTER: "buctd_rasterize_condition"}
+              OP_DECODE: "buctd_decode_heatmaps", OP_RASTER: "buctd_rasterize_condition", OP_CHAIN: "buctd_tapgemm_chain"}
 
 
 class BuctdError(RuntimeError):

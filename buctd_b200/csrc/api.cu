@@ -45,6 +45,8 @@ struct PlanOp {
   bool record = false;          // some op on another lane waits for this one
   TapGemmLaunch tg;     // kind == TAPGEMM
   buctd_tapgemm_args tga;
+  std::shared_ptr<ChainLaunch> chain;                       // kind == CHAIN
+  std::shared_ptr<buctd_tapgemm_chain_args> chain_args;
   union {
     buctd_stem_args stem;
     buctd_fuse_args fuse;
@@ -61,6 +63,7 @@ struct PlanOp {
 static int run_op(PlanOp& op, cudaStream_t st) {
   switch (op.kind) {
     case BUCTD_OP_TAPGEMM: return tapgemm_launch(op.tg, st);
+    case BUCTD_OP_CHAIN: return tapgemm_chain_launch(*op.chain, st);
     case BUCTD_OP_STEM: return launch_stem(op.u.stem, st);
     case BUCTD_OP_FUSE: return launch_fuse(op.u.fuse, st);
     case BUCTD_OP_RESIZE: return launch_resize(op.u.resize, st);
@@ -83,10 +86,20 @@ static int copy_args(A* dst, const void* src, size_t size, const char* name) {
   return BUCTD_OK;
 }
 
-static int make_op(int kind, const void* args, size_t size, PlanOp* op, int sm_count) {
+static int make_op(int kind, const void* args, size_t size, PlanOp* op, int sm_count, buctd_ctx* ctx) {
   BUCTD_CHECK(args != nullptr, BUCTD_ERR_INVALID, "null args");
   op->kind = kind;
   switch (kind) {
+    case BUCTD_OP_CHAIN: {
+      op->chain_args = std::make_shared<buctd_tapgemm_chain_args>();
+      int rc = copy_args(op->chain_args.get(), args, size, "tapgemm_chain");
+      if (rc) return rc;
+      BUCTD_CHECK(ctx != nullptr && ctx->barriers != nullptr, BUCTD_ERR_INVALID, "tapgemm_chain: handle has no barrier buffer");
+      op->chain = std::shared_ptr<ChainLaunch>(tapgemm_chain_new(), tapgemm_chain_delete);
+      unsigned int* counter = ctx->barriers + (ctx->next_barrier.fetch_add(1) % buctd_ctx::kBarriers);
+      op->nlaunch = 1;
+      return tapgemm_chain_prepare(*op->chain_args, op->chain.get(), sm_count, counter);
+    }
     case BUCTD_OP_TAPGEMM: {
       int rc = copy_args(&op->tga, args, size, "tapgemm");
       return rc ? rc : tapgemm_prepare(op->tga, &op->tg, sm_count);
@@ -118,6 +131,15 @@ static void op_spans(const PlanOp& op, std::vector<Span>* rd, std::vector<Span>*
   rd->clear();
   wr->clear();
   switch (op.kind) {
+    case BUCTD_OP_CHAIN: {
+      for (int l = 0; l < op.chain_args->n_layers; ++l) {
+        const buctd_tapgemm_args& a = op.chain_args->layer[l];
+        rd->push_back(span(a.a, 2ll * a.m_rows * a.a_cs));
+        if (a.residual) rd->push_back(span(a.residual, 2ll * a.m_rows * a.res_cs));
+        wr->push_back(span(a.out, 2ll * a.m_rows * a.out_cs));
+      }
+      break;
+    }
     case BUCTD_OP_TAPGEMM: {
       const buctd_tapgemm_args& a = op.tga;
       const bool flat = a.mode == BUCTD_TG_FLAT;
@@ -254,22 +276,30 @@ BUCTD_API int buctd_create(int device, buctd_ctx** out) {
   BUCTD_CUDA(cudaGetDevice(&prev));
   BUCTD_CUDA(cudaSetDevice(device));
   int rc = tapgemm_init_device();
+  if (!rc) rc = tapgemm_chain_init_device();
   if (!rc) rc = pos_att_init_device();
   if (!rc) rc = pos_att_tc_init_device();
   if (!rc && get_encode_tiled() == nullptr) {
     set_error("buctd_create: cuTensorMapEncodeTiled driver entry point not found");
     rc = BUCTD_ERR_NO_DEVICE;
   }
+  unsigned int* barriers = nullptr;
+  if (!rc && cudaMalloc(&barriers, sizeof(unsigned int) * buctd_ctx::kBarriers) != cudaSuccess) {
+    set_error("buctd_create: cudaMalloc of the barrier counters failed");
+    rc = BUCTD_ERR_CUDA;
+  }
   cudaSetDevice(prev);
   if (rc) return rc;
   buctd_ctx* c = new buctd_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
+  c->barriers = barriers;
   *out = c;
   return BUCTD_OK;
 }
 
 BUCTD_API int buctd_destroy(buctd_ctx* ctx) {
+  if (ctx && ctx->barriers) cudaFree(ctx->barriers);
   delete ctx;
   return BUCTD_OK;
 }
@@ -279,7 +309,7 @@ BUCTD_API long long buctd_launch_count(const buctd_ctx* ctx) { return ctx ? ctx-
 static int immediate(buctd_ctx* ctx, int kind, const void* args, size_t size, buctd_stream stream) {
   BUCTD_CHECK(ctx != nullptr, BUCTD_ERR_INVALID, "null ctx");
   PlanOp op;
-  int rc = make_op(kind, args, size, &op, ctx->sm_count);
+  int rc = make_op(kind, args, size, &op, ctx->sm_count, ctx);
   if (rc) return rc;
   rc = run_op(op, static_cast<cudaStream_t>(stream));
   if (!rc) ctx->launches += op.nlaunch;
@@ -288,6 +318,9 @@ static int immediate(buctd_ctx* ctx, int kind, const void* args, size_t size, bu
 
 BUCTD_API int buctd_tapgemm(buctd_ctx* c, const buctd_tapgemm_args* a, buctd_stream s) {
   return immediate(c, BUCTD_OP_TAPGEMM, a, sizeof(*a), s);
+}
+BUCTD_API int buctd_tapgemm_chain(buctd_ctx* c, const buctd_tapgemm_chain_args* a, buctd_stream s) {
+  return immediate(c, BUCTD_OP_CHAIN, a, sizeof(*a), s);
 }
 BUCTD_API int buctd_stem_conv(buctd_ctx* c, const buctd_stem_args* a, buctd_stream s) {
   return immediate(c, BUCTD_OP_STEM, a, sizeof(*a), s);
@@ -368,7 +401,7 @@ BUCTD_API int buctd_plan_add_lane(buctd_plan* plan, int kind, const void* args, 
   BUCTD_CHECK(plan->exec == nullptr, BUCTD_ERR_INVALID, "buctd_plan_add: plan already instantiated");
   PlanOp op;
   const int sms = plan->ctx->sm_count;
-  int rc = make_op(kind, args, size, &op, max_ctas > 0 && max_ctas < sms ? max_ctas : sms);
+  int rc = make_op(kind, args, size, &op, max_ctas > 0 && max_ctas < sms ? max_ctas : sms, plan->ctx);
   if (rc) return rc;
   op.lane = lane;
   plan->ops.push_back(op);

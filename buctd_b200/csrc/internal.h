@@ -12,6 +12,9 @@ struct buctd_ctx {
   int device = 0;
   int sm_count = 0;
   std::atomic<long long> launches{0};
+  unsigned int* barriers = nullptr;          // device: grid-barrier counters of the chain tap-GEMMs (owned by the handle)
+  std::atomic<int> next_barrier{0};
+  static constexpr int kBarriers = 4096;
 };
 
 namespace buctd {
@@ -88,6 +91,12 @@ int launch_flip_channels(const buctd_flip_args& a, cudaStream_t st);
 int launch_flip_merge(const buctd_flip_merge_args& a, cudaStream_t st);
 int launch_joints_mse(const buctd_joints_mse_args& a, cudaStream_t st);
 int launch_adam(const buctd_adam_args& a, int sm_count, cudaStream_t st);
+struct ChainLaunch;
+int tapgemm_chain_init_device();
+int tapgemm_chain_prepare(const buctd_tapgemm_chain_args& a, ChainLaunch* C, int sm_count, unsigned int* counter);
+int tapgemm_chain_launch(const ChainLaunch& C, cudaStream_t st);
+ChainLaunch* tapgemm_chain_new();
+void tapgemm_chain_delete(ChainLaunch* c);
 int pos_att_init_device();
 int pos_att_tc_init_device();
 bool pos_att_tc_supported(const buctd_pos_att_args& a);

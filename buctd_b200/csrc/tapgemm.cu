@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "epilogue.cuh"
 #include "internal.h"
+#include "slab_common.cuh"
 
 namespace buctd {
 
@@ -42,11 +43,8 @@ __device__ unsigned long long g_role_cycles[160 * 16];
 #define RT_STORE(slot, v)
 #endif
 
-constexpr int kBlockM = 128;
 constexpr int kATileBytes = kBlockM * 128;
 constexpr int kThreads = 192;          // patch kernel: producer + MMA + 4 epilogue warps
-constexpr int kSlabThreads = 352;      // slab kernel: producer + MMA + 8 epilogue warps (2 per TMEM lane quarter) + DMA warp
-constexpr int kSmemBudget = 227 * 1024;
 
 template <int BN> __host__ __device__ constexpr int patch_stages() { return BN <= 128 ? 4 : 3; }
 
@@ -171,47 +169,6 @@ tapgemm_patch_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 // =================================================================================================
 // SLAB kernel (FLAT mode): persistent, A-slab + row-shifted tap views, ring of TMEM accumulators
 // =================================================================================================
-constexpr int kMaxAcc = 8;   // accumulator ring slots (barrier array size)
-template <int BN> __host__ __device__ constexpr int slab_nacc() { return (512 / BN) < kMaxAcc ? (512 / BN) : kMaxAcc; }
-
-// Walks the 128-row sub-tiles of one CTA in processing order: work item k = blockIdx.x + k*gridDim.x is
-// (super-tile s, N tile nt) in mixed radix; every item has MSUB sub-tiles.  No division after init().
-struct SubIter {
-  int s, nt, j, ds, dn, num_super;
-  __device__ __forceinline__ void init(int num_super_) {
-    num_super = num_super_;
-    s = (int)blockIdx.x % num_super; nt = (int)blockIdx.x / num_super;
-    ds = (int)gridDim.x % num_super; dn = (int)gridDim.x / num_super;
-    j = 0;
-  }
-  __device__ __forceinline__ void next_item() {
-    s += ds; nt += dn;
-    if (s >= num_super) { s -= num_super; ++nt; }
-  }
-  template <int MSUB> __device__ __forceinline__ void next() {
-    if (++j == MSUB) { j = 0; next_item(); }
-  }
-  template <int MSUB> __device__ __forceinline__ long long m0() const {
-    return (long long)s * (MSUB * kBlockM) + (long long)j * kBlockM;
-  }
-};
-
-// all k-steps of one (sub-tile, tap, chunk): fully unrolled, every descriptor is base + immediate
-template <int BN, int KS>
-__device__ __forceinline__ void mma_ksteps(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t first) {
-#pragma unroll
-  for (int k = 0; k < KS; ++k) tc_mma_f16(d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k == 0 ? first : 1u);
-}
-template <int BN>
-__device__ __forceinline__ void mma_ksteps_rt(int ksteps, uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t first) {
-  switch (ksteps) {
-    case 1: mma_ksteps<BN, 1>(d, adesc, bdesc, idesc, first); break;
-    case 2: mma_ksteps<BN, 2>(d, adesc, bdesc, idesc, first); break;
-    case 3: mma_ksteps<BN, 3>(d, adesc, bdesc, idesc, first); break;
-    default: mma_ksteps<BN, 4>(d, adesc, bdesc, idesc, first); break;
-  }
-}
-
 template <typename T, int BN, int MSUB>
 __global__ void __launch_bounds__(kSlabThreads, 1)
 tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,

@@ -321,11 +321,28 @@ class PoseHighResolutionNet(nn.Module):
             def append(t):
                 emit(*t)
 
+        # BasicBlock convolutions of one branch and module (identical geometry) go out as ONE chain launch
+        # (include/buctd_b200.h, buctd_tapgemm_chain) unless BUCTD_CHAIN=0 or the branches run on their own lanes.
+        use_chain = os.environ.get("BUCTD_CHAIN", "1") != "0" and not block_lanes
+        collect: List[Optional[list]] = [None]
+
         def conv(cv: Conv, src: Act, dst: Act, residual=None, relu=None, key=None):
             oh, ow = (src.h, src.w) if cv.stride == 1 else (src.h // 2, src.w // 2)
             assert (dst.h, dst.w) == (oh, ow), (cv.w, dst, oh, ow)
-            emit(L.OP_TAPGEMM, ("tg", key or cv.w, src, dst, dict(stride=cv.stride, relu=cv.relu if relu is None else relu,
-                                                                   residual=residual)), cv.w)
+            spec = ("tg", key or cv.w, src, dst, dict(stride=cv.stride, relu=cv.relu if relu is None else relu, residual=residual))
+            if collect[0] is not None:
+                collect[0].append((spec, cv.w))
+            else:
+                emit(L.OP_TAPGEMM, spec, cv.w)
+
+        def flush_chain(label):
+            items, collect[0] = collect[0], None
+            for lo in range(0, len(items), L.MAX_CHAIN):
+                part = items[lo:lo + L.MAX_CHAIN]
+                if len(part) == 1:
+                    emit(L.OP_TAPGEMM, part[0][0], part[0][1])
+                else:
+                    emit(L.OP_CHAIN, ("chain", [sp for sp, _ in part], [lb for _, lb in part]), label)
 
         # ---- stem ---------------------------------------------------------------------------
         s1 = act("stem1", arch.img_h // 2, arch.img_w // 2, 64)
@@ -393,6 +410,8 @@ class PoseHighResolutionNet(nn.Module):
             for mi, m in enumerate(mods):
                 for i in range(nb):
                     at(i, shares[i]) if block_lanes else at(0)
+                    if use_chain:
+                        collect[0] = []
                     for blk in m.branches[i]:
                         tmp = nxt(i)
                         conv(blk.convs[0], xs[i], tmp)
@@ -401,6 +420,8 @@ class PoseHighResolutionNet(nn.Module):
                             out = nxt(i)
                         conv(blk.convs[1], tmp, out, residual=xs[i], relu=True)
                         xs[i] = out
+                    if use_chain:
+                        flush_chain("%s.branches.%d:chain" % (m.prefix, i))
                 if not m.fuse:
                     continue
                 outs = []
@@ -509,6 +530,15 @@ class PoseHighResolutionNet(nn.Module):
                 oh, ow = dst.h, dst.w
                 args = self._tapgemm(key, fix(src), base + dst.ptr, dst.cs, oh, ow,
                                      residual=fix(res) if res is not None else None, **kw)
+            elif tag == "chain":
+                _, tgs, _labels = spec
+                args = L.TapGemmChainArgs()
+                args.n_layers = len(tgs)
+                for li, (_, key, src, dst, kw) in enumerate(tgs):
+                    kw = dict(kw)
+                    res = kw.pop("residual")
+                    args.layer[li] = self._tapgemm(key, fix(src), base + dst.ptr, dst.cs, dst.h, dst.w,
+                                                   residual=fix(res) if res is not None else None, **kw)
             elif tag == "lin_planar":
                 _, key, src_off, dst_off, rows, hw = spec
                 a = Act(base + src_off, 1, 0, 0, hw, hw)

@@ -98,6 +98,17 @@ typedef struct {
 } buctd_tapgemm_args;
 int buctd_tapgemm(buctd_ctx* ctx, const buctd_tapgemm_args* args, buctd_stream stream);
 
+/* Chain of up to BUCTD_MAX_CHAIN FLAT tap-GEMMs of identical geometry (same dtype, taps, rows, K, N, strides; bias,
+ * relu, residual and the buffers differ) in ONE persistent launch with a grid-wide barrier between layers: the eight
+ * 3x3 convolutions of the four BasicBlocks of one HRNet branch, lib/models/pose_hrnet_coam.py:31-60,142-165,254-255.
+ * Layer l+1 may read (as A or residual) anything layers <= l wrote.  act16 output only. */
+#define BUCTD_MAX_CHAIN 8
+typedef struct {
+  int32_t n_layers, reserved;
+  buctd_tapgemm_args layer[BUCTD_MAX_CHAIN];
+} buctd_tapgemm_chain_args;
+int buctd_tapgemm_chain(buctd_ctx* ctx, const buctd_tapgemm_chain_args* args, buctd_stream stream);
+
 /* Stem conv1: 3x3 stride 2, 3 -> 64, BN folded, ReLU, reading the nchw32 model input directly
  * (channels [0,3) of x[B][x_channels][H][W]) and writing act16 [B][H/2+1][W/2+1][64].
  * Replaces conv1/bn1/relu, lib/models/pose_hrnet_coam.py:505-507.  w: float32 [64][27] (ci,ky,kx). */
@@ -272,7 +283,7 @@ int buctd_nchw32_to_act16(buctd_ctx* ctx, int dtype, const float* x, int batch, 
  * ------------------------------------------------------------------------------------------ */
 enum { BUCTD_OP_TAPGEMM = 1, BUCTD_OP_STEM = 2, BUCTD_OP_FUSE = 3, BUCTD_OP_RESIZE = 4, BUCTD_OP_CHAN_ATT = 5,
        BUCTD_OP_POS_ATT = 6, BUCTD_OP_DA_COMBINE = 7, BUCTD_OP_PRENET = 8, BUCTD_OP_DECODE = 9,
-       BUCTD_OP_RASTER = 10 };
+       BUCTD_OP_RASTER = 10, BUCTD_OP_CHAIN = 11 };
 #define BUCTD_MAX_LANES 8
 int buctd_plan_create(buctd_ctx* ctx, buctd_plan** out);
 int buctd_plan_destroy(buctd_plan* plan);

@@ -290,3 +290,41 @@ def test_prenet_composed():
     x0 = bn("rgb_preNet.3", F.conv2d(t, sdc["rgb_preNet.2.weight"], sdc["rgb_preNet.2.bias"], padding=3))
     x1 = bn("cond_preNet.1", F.conv2d(x[:, 3:], sdc["cond_preNet.0.weight"], sdc["cond_preNet.0.bias"], padding=3))
     assert_close(out, x0 + x1, 2e-5, "prenet")
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("c,B,h,w,nblocks", [(48, 7, 24, 18, 2), (96, 5, 12, 9, 4), (192, 9, 12, 9, 2), (48, 40, 48, 36, 4)])
+def test_tapgemm_chain_basic_blocks(dt, c, B, h, w, nblocks):
+    """chain launch: nblocks BasicBlocks (conv-relu-conv-add-relu) in ONE persistent kernel with grid barriers,
+    against the same sequence in torch on 16-bit-rounded operands"""
+    x = q16(_rand(B, c, h, w, seed=61), dt)
+    ws = [q16(_rand(c, c, 3, 3, seed=62 + i, scale=1.0 / math.sqrt(9 * c)), dt) for i in range(2 * nblocks)]
+    bs = [_rand(c, seed=80 + i, scale=0.1).float().contiguous() for i in range(2 * nblocks)]
+    bufs = [to_act16(x, dt), torch.zeros(B, h + 1, w + 1, c, dtype=TDT[dt], device="cuda"),
+            torch.zeros(B, h + 1, w + 1, c, dtype=TDT[dt], device="cuda")]
+    packed = [pack_w(wt, dt) for wt in ws]
+    a = L.TapGemmChainArgs()
+    a.n_layers = 2 * nblocks
+    cur = 0
+    ref = x.cpu()
+    for blk in range(nblocks):
+        t, o = (cur + 1) % 3, (cur + 2) % 3
+        for j, (src, dst, res) in enumerate(((cur, t, None), (t, o, cur))):
+            li = 2 * blk + j
+            g = a.layer[li]
+            wp, n_alloc, k_cs = packed[li]
+            g.dtype, g.mode, g.ntaps, g.stride, g.batch = dt, L.TG_FLAT, 9, 1, B
+            g.out_h, g.out_w, g.in_h, g.in_w = h, w, h, w
+            g.m_rows = B * (h + 1) * (w + 1)
+            g.k, g.a_cs, g.n, g.n_alloc, g.w_cs = c, c, c, n_alloc, k_cs
+            g.out_cs, g.res_cs, g.relu, g.out_mode = c, (c if res is not None else 0), 1, L.OUT_ACT16
+            g.a, g.w, g.bias, g.out = bufs[src].data_ptr(), wp.data_ptr(), bs[li].data_ptr(), bufs[dst].data_ptr()
+            g.residual = bufs[res].data_ptr() if res is not None else None
+        # torch reference with the same 16-bit rounding between layers
+        mid = q16(F.relu(F.conv2d(ref, ws[2 * blk].cpu(), bs[2 * blk].cpu(), padding=1)), dt)
+        ref = q16(F.relu(F.conv2d(mid, ws[2 * blk + 1].cpu(), bs[2 * blk + 1].cpu(), padding=1) + ref), dt)
+        cur = o
+    ctx().run(L.OP_CHAIN, a, stream())
+    torch.cuda.synchronize()
+    assert_close(from_act16(bufs[cur], c), ref, 4 * TOL[dt], "chain of %d blocks C=%d" % (nblocks, c))
+    assert pads_are_zero(bufs[cur])
