@@ -96,9 +96,22 @@ static int make_op(int kind, const void* args, size_t size, PlanOp* op, int sm_c
       if (rc) return rc;
       BUCTD_CHECK(ctx != nullptr && ctx->barriers != nullptr, BUCTD_ERR_INVALID, "tapgemm_chain: handle has no barrier buffer");
       op->chain = std::shared_ptr<ChainLaunch>(tapgemm_chain_new(), tapgemm_chain_delete);
-      unsigned int* counter = ctx->barriers + (ctx->next_barrier.fetch_add(1) % buctd_ctx::kBarriers);
       op->nlaunch = 1;
-      return tapgemm_chain_prepare(*op->chain_args, op->chain.get(), sm_count, counter);
+      rc = tapgemm_chain_prepare(*op->chain_args, op->chain.get(), sm_count, ctx->barriers);
+      if (rc) return rc;
+      // a private range of flags [n_layers][num_super] out of the handle's pool (ranges are reused round-robin: chain
+      // launches of one handle are stream-ordered and each zeroes its range first)
+      const int need = (int)tapgemm_chain_flag_count(*op->chain);
+      BUCTD_CHECK(need <= buctd_ctx::kBarriers, BUCTD_ERR_INVALID, "tapgemm_chain: %d flags exceed the pool", need);
+      int start;
+      {
+        std::lock_guard<std::mutex> lock(ctx->barrier_mutex);
+        start = ctx->next_barrier;
+        if (start + need > buctd_ctx::kBarriers) start = 0;
+        ctx->next_barrier = start + need;
+      }
+      tapgemm_chain_set_flags(op->chain.get(), ctx->barriers + start);
+      return BUCTD_OK;
     }
     case BUCTD_OP_TAPGEMM: {
       int rc = copy_args(&op->tga, args, size, "tapgemm");

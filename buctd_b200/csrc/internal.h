@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "../../include/buctd_b200.h"
@@ -13,8 +14,9 @@ struct buctd_ctx {
   int sm_count = 0;
   std::atomic<long long> launches{0};
   unsigned int* barriers = nullptr;          // device: grid-barrier counters of the chain tap-GEMMs (owned by the handle)
-  std::atomic<int> next_barrier{0};
-  static constexpr int kBarriers = 4096;
+  int next_barrier = 0;
+  std::mutex barrier_mutex;
+  static constexpr int kBarriers = 1 << 21;   // 8 MB of flags: a W48 forward at B = 64 uses ~0.15 M
 };
 
 namespace buctd {
@@ -96,6 +98,8 @@ int tapgemm_chain_init_device();
 int tapgemm_chain_prepare(const buctd_tapgemm_chain_args& a, ChainLaunch* C, int sm_count, unsigned int* counter);
 int tapgemm_chain_launch(const ChainLaunch& C, cudaStream_t st);
 ChainLaunch* tapgemm_chain_new();
+size_t tapgemm_chain_flag_count(const ChainLaunch& C);
+void tapgemm_chain_set_flags(ChainLaunch* C, unsigned int* flags);
 void tapgemm_chain_delete(ChainLaunch* c);
 int pos_att_init_device();
 int pos_att_tc_init_device();

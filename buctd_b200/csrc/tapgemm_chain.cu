@@ -4,9 +4,15 @@
 // Why: a slab tap-GEMM launch costs ~8 us around its ~29 us of tensor work at B = 64 (inter-kernel gap ~4 us even with
 // programmatic dependent launch -- a CTA of the next kernel needs the whole SM -- plus prologue, pipeline fill and
 // drain; tools/conv_sweep.py).  Here the rings (slabs, weights, TMEM accumulators, stage buffers) keep
-// running across layers; between layer l and l+1 only the PRODUCER thread waits, on a grid-wide counter that every CTA
-// bumps once its layer-l output tiles have left by TMA store.  All CTAs are co-resident by construction (grid <= SM
-// count, one CTA per SM), so the spin cannot deadlock; it traps after ~4 s instead of hanging the device.
+// running across layers, and there is NO grid-wide barrier between them: the dependency of a 3x3 convolution is local,
+// super-tile s of layer l+1 reads rows of the super-tiles s-1, s, s+1 of layer l (halo W+2 < 128 rows) and, as residual,
+// super-tile s of an earlier layer.  Every layer has the same geometry, hence the same (super-tile -> CTA) assignment.
+// The DMA warp publishes flag[l][s] (+1 per N tile) once the TMA stores of that work item are complete; the producer
+// thread waits for the three flags of the previous layer before it loads a slab.  CTAs drift apart freely: a slow CTA
+// only delays its neighbours.  Writes are safe by the same argument: whoever overwrites rows of super-tile s at layer
+// l+1 has waited for every layer-l reader of those rows (buffers rotate as in a BasicBlock: in -> tmp -> out).
+// All CTAs are co-resident by construction (grid <= SM count, one CTA per SM) and dependencies only point to lower
+// layers, so the spins cannot deadlock; they trap after ~4 s instead of hanging the device.
 //
 // Same roles and pipeline as tapgemm_slab_kernel (tapgemm.cu); staged (TMA store) epilogue only.
 // Replaces the conv1/bn1/relu/conv2/bn2/+residual/relu sequences of HighResolutionModule._make_one_branch,
@@ -26,29 +32,38 @@ struct ChainParams {
   const float* bias[BUCTD_MAX_CHAIN];
   int has_res[BUCTD_MAX_CHAIN];
   int relu[BUCTD_MAX_CHAIN];
-  unsigned int* counter;     // grid barrier: += 1 per CTA and layer
+  unsigned int* flags;       // [n_layers][num_super]: N tiles of that super-tile whose output is in global memory
   int n_layers;
+  int n_tiles;               // N tiles per super-tile
 };
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-// wait until `target` CTA-layers have arrived; then order this thread's TMA (async proxy) reads after it
-__device__ __forceinline__ void grid_wait(const unsigned int* ctr, unsigned int target) {
+__device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
   unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// wait until super-tiles [s_lo, s_hi] of layer `row` are complete; then order this thread's TMA (async proxy) reads after it
+__device__ __forceinline__ void flags_wait(const unsigned int* row, int s_lo, int s_hi, unsigned int target) {
   const long long t0 = clock64();
   for (;;) {
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-    if (v >= target) break;
-    __nanosleep(64);
+    bool ok = true;
+    for (int s = s_lo; s <= s_hi; ++s) ok = ok && ld_acquire(row + s) >= target;
+    if (ok) break;
+    __nanosleep(32);
     if (clock64() - t0 > (8ll << 30)) __trap();      // ~4 s: a CTA of this grid never became resident
   }
   fence_proxy_async_all();
 }
-// this CTA's TMA stores of the layer are complete: publish
-__device__ __forceinline__ void grid_arrive(unsigned int* ctr) {
+// the TMA stores of one work item are complete: publish
+__device__ __forceinline__ void flag_publish(unsigned int* f) {
   fence_proxy_async_all();
   __threadfence();
-  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(f) : "memory");
+}
+template <int N> __device__ __forceinline__ void tma_store_wait_complete() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
 template <typename T, int BN, int MSUB>
@@ -116,10 +131,14 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
             for (int t = 0; t < p0.ntaps; ++t)
               tma_load_2d(wbuf + (size_t)(kc * p0.ntaps + t) * kWTileBytes, map_b, &w_full[0], kc * 64, t * p0.n_alloc);
         }
-        if (l > 0) grid_wait(cp.counter, gridDim.x * (unsigned)l);    // layer l-1 is in global memory, everywhere
         SubIter it;
         it.init(sp.num_super);
         for (int k = 0; k < my_items; ++k, it.next_item()) {
+          if (l > 0) {      // the rows this slab covers: super-tiles s-1 .. s+1 of the previous layer (s alone without halo)
+            const int reach = (sp.halo + R - 1) / R;
+            flags_wait(cp.flags + (size_t)(l - 1) * sp.num_super, max(it.s - reach, 0), min(it.s + reach, sp.num_super - 1),
+                       (unsigned)cp.n_tiles);
+          }
           const long long r0 = (long long)it.s * R - sp.halo;
           for (int kc = 0; kc < p0.num_kc; ++kc) {
             mbar_wait(&slab_empty[slot], slot_ph);
@@ -209,13 +228,15 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
     if (warp == 10) {
       if (elect_one()) {
         int ubase = 0;
+        int pending_s = -1, pending2_s = -1;    // super-tiles whose stores are committed but not yet published
         for (int l = 0; l < NL; ++l, ubase += total_u) {
           TapGemmKParams p = p0;
           p.residual = cp.has_res[l] ? reinterpret_cast<const void*>(1) : nullptr;      // epi_load_residual only reads geometry
           const bool has_res = cp.has_res[l] != 0;
           const CUtensorMap* map_out = &cp.m[l].out;
           const CUtensorMap* map_res = &cp.m[l].res;
-          if (l > 0 && has_res) grid_wait(cp.counter, gridDim.x * (unsigned)l);     // the residual may be an earlier layer's output
+          // the residual tile of super-tile s is an earlier layer's output of super-tile s: written, completed and
+          // published by THIS thread (same super-tile -> CTA assignment in every layer)
           SubIter st_it, pr_it;
           st_it.init(sp.num_super);
           pr_it.init(sp.num_super);
@@ -241,14 +262,28 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
             t.m0 = st_it.template m0<MSUB>();
             t.tb = t.ty0 = t.tx0 = 0;
             epi_store<BN>(p, map_out, t, st_it.nt * BN, stage + (size_t)e * epi_stage_bytes<BN>());
+            const int s_now = st_it.s;
+            const bool item_end = st_it.j == MSUB - 1;
             st_it.template next<MSUB>();
+            if (item_end && l + 1 < NL) {
+              // publish the item before the previous one: its MSUB store groups precede the 2 MSUB most recent ones, which
+              // stay in flight (waiting for the newest stores would stall this thread, and with it the stage buffers)
+              if (pending2_s >= 0) {
+                tma_store_wait_complete<2 * MSUB>();
+                flag_publish(cp.flags + (size_t)l * sp.num_super + pending2_s);
+              }
+              pending2_s = pending_s;
+              pending_s = s_now;
+            }
             if (u + SE < total_u) {
               tma_store_wait_read<0>();
               prepare(u + SE);
             }
           }
           tma_store_wait_all();                 // this CTA's layer-l tiles are in global memory
-          if (l + 1 < NL) grid_arrive(cp.counter);
+          if (pending2_s >= 0) flag_publish(cp.flags + (size_t)l * sp.num_super + pending2_s);
+          if (pending_s >= 0) flag_publish(cp.flags + (size_t)l * sp.num_super + pending_s);
+          pending_s = pending2_s = -1;
         }
       }
       __syncwarp();
@@ -347,6 +382,8 @@ int tapgemm_chain_init_device() {
   return rc ? rc : chain_set_attrs<__nv_bfloat16>();
 }
 
+size_t tapgemm_chain_flag_count(const ChainLaunch& C) { return (size_t)C.cp.n_layers * C.sp.num_super; }
+
 int tapgemm_chain_prepare(const buctd_tapgemm_chain_args& a, ChainLaunch* C, int sm_count, unsigned int* counter) {
   BUCTD_CHECK(a.n_layers >= 1 && a.n_layers <= BUCTD_MAX_CHAIN, BUCTD_ERR_INVALID, "tapgemm_chain: n_layers %d out of range [1,%d]",
               a.n_layers, BUCTD_MAX_CHAIN);
@@ -385,8 +422,9 @@ int tapgemm_chain_prepare(const buctd_tapgemm_chain_args& a, ChainLaunch* C, int
     if (g.residual == nullptr) C->cp.m[l].res = L.map_out;
   }
   C->kp.bias = nullptr; C->kp.residual = nullptr; C->kp.out = nullptr; C->kp.relu = 0;
-  C->cp.counter = counter;
+  C->cp.flags = counter;
   C->cp.n_layers = a.n_layers;
+  C->cp.n_tiles = C->sp.num_items / C->sp.num_super;
   return BUCTD_OK;
 }
 
@@ -422,12 +460,13 @@ static int chain_dispatch(const ChainLaunch& C, cudaStream_t st) {
 }
 
 int tapgemm_chain_launch(const ChainLaunch& C, cudaStream_t st) {
-  BUCTD_CUDA(cudaMemsetAsync(C.cp.counter, 0, sizeof(unsigned int), st));
+  BUCTD_CUDA(cudaMemsetAsync(C.cp.flags, 0, sizeof(unsigned int) * tapgemm_chain_flag_count(C), st));
   if (C.dtype == BUCTD_F16) return chain_dispatch<__half>(C, st);
   return chain_dispatch<__nv_bfloat16>(C, st);
 }
 
 ChainLaunch* tapgemm_chain_new() { return new ChainLaunch(); }
+void tapgemm_chain_set_flags(ChainLaunch* C, unsigned int* flags) { C->cp.flags = flags; }
 void tapgemm_chain_delete(ChainLaunch* c) { delete c; }
 
 }  // namespace buctd

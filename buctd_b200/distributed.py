@@ -1,4 +1,4 @@
-"""Multi-GPU plumbing for the inference path: one process per GPU, crops sharded over ranks, ONE
+"""Multi-GPU plumbing: one process per GPU, crops sharded over ranks, ONE
 collective per step (the decoded keypoints, 204 B per crop) -- replaces the reference's single-process
 ``torch.nn.DataParallel`` (tools/test.py:134), which re-broadcasts 463 MB of parameters and gathers the
 full heat-maps to GPU 0 on every forward.  torch.distributed does the plumbing (NCCL on GPUs, gloo in
@@ -36,3 +36,14 @@ def gather_keypoints(local: torch.Tensor, n_total: int | None = None) -> torch.T
     out = [torch.empty_like(padded) for _ in range(world)]
     dist.all_gather(out, padded.contiguous())
     return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(out, sizes)], 0)
+
+
+def allreduce_mean_(flat: torch.Tensor) -> torch.Tensor:
+    """The ONE collective of the data-parallel training step: in-place mean over ranks of the flat
+    gradient buffer (``buctd_b200.optim.Adam.flat_grad``: every parameter's gradient is a view into it).  Equal shard
+    sizes make the mean of the per-rank JointsMSELoss gradients the global-batch gradient, which is what the
+    reference's DataParallel reduce-add computes (tools/train.py:147).  No-op in a single-process group."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.div_(dist.get_world_size())
+    return flat

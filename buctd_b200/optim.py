@@ -8,9 +8,9 @@ from __future__ import annotations
 from typing import Iterable
 
 import torch
-import torch.distributed as dist
 
 from . import _lib as L
+from .distributed import allreduce_mean_
 
 
 class Adam:
@@ -47,9 +47,7 @@ class Adam:
 
     def allreduce_grads(self):
         """the ONE collective of the data-parallel training step: mean of the flat gradient buffer over ranks"""
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
-            self.flat_grad.div_(dist.get_world_size())
+        allreduce_mean_(self.flat_grad)
 
     @torch.no_grad()
     def step(self):

@@ -55,3 +55,42 @@ def test_gather_keypoints_world2(n_total):
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res), res
     assert all(shape == (n_total, 17, 3) for _, _, shape in res)
+
+
+def _grad_worker(rank, world, port, q):
+    """data-parallel training step: per-rank JointsMSELoss gradients (oracle closed form) averaged by the ONE
+    all-reduce == the gradient of the loss over the concatenated global batch (equal shards)"""
+    import numpy as np
+    from buctd_b200.distributed import allreduce_mean_
+    from oracle import loop_oracle as LO
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(3)
+        o = rng.standard_normal((4 * world, 17, 8, 6)).astype(np.float32)
+        t = rng.uniform(0, 1, o.shape).astype(np.float32)
+        w = (rng.uniform(size=(4 * world, 17, 1)) < 0.8).astype(np.float32)
+        lin = rng.standard_normal((5, 8 * 6)).astype(np.float32)          # a toy "model": param grad = lin @ dL/dout rows
+        lo, hi = shard_range(4 * world, rank, world)
+        g_local = LO.joints_mse_grad(o[lo:hi], t[lo:hi], w[lo:hi], True)
+        flat = torch.from_numpy((lin @ g_local.reshape(-1, 48).T).sum(1).copy())
+        allreduce_mean_(flat)
+        g_global = LO.joints_mse_grad(o, t, w, True)
+        want = (lin @ g_global.reshape(-1, 48).T).sum(1)
+        q.put((rank, float(np.abs(flat.numpy() - want).max())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allreduce_mean_matches_global_batch_gradient_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(err < 1e-6 for _, err in res), res
