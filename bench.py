@@ -10,10 +10,11 @@ One step = one forward of the network over one batch of synthetic crops + the fu
 `e2e`     : the same metric through the reference-facing call `model(x_host)` + decode with HOST
             buffers: the pinned-host -> device copy of every step's input and the device -> host
             read of the decoded keypoints are inside the timed region.
-`roofline`: fraction of the 3x3-conv tensor-core roofline: achieved =
-            crops/s/GPU x 70.34 GFLOP (all 3x3 convolutions of CoAM-W48 per crop) against the MEASURED
-            dense bf16/fp16 tensor peak in MEASURED_PEAKS.json (sustained figure: the kernels are timed
-            inside a long step), plus the dominant launch class timed alone with CUDA events.
+`roofline`: the dominant kernel (chain tap-GEMM of the BasicBlock 3x3 convolutions of branch 0): algorithmic
+            FLOPs per launch / its launch time measured live with CUDA events, against the MEASURED burst
+            bf16/fp16 peak of MEASURED_PEAKS.json; `traffic` = DRAM bytes per launch from the committed
+            ncu capture.  `roofline.path_3x3` = the whole path as the fraction of the 3x3-conv tensor-core
+            roofline BASELINE.json asks for: crops/s/GPU x 70.34 GFLOP over the measured SUSTAINED peak.
 `cpu_baseline`: the oracle port of the reference forward + decode on the host cores (bounded sample).
 Only the cpu_baseline / --impl reference legs import oracle/.
 """
@@ -233,12 +234,7 @@ def run_native(args):
         "config": {"workload": WORKLOAD % B, "global_batch": B * world, "parallelism": "crops sharded, dp%d" % world,
                    "weights": "random-init (buctd_b200.synth, seed 0)", "l2": "per-step input 566 MB > 126 MB L2",
                    "collective": "one NCCL all_gather of decoded [B,17,3] per step" if world > 1 else "none"},
-        "roofline": {"bound": "tensor", "achieved": round(ach, 2), "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": round(ach / peaks["tflops_sustained"], 4), "traffic": None,
-                     "peak_source": peaks["source"] + " (sustained bf16/fp16 dense)",
-                     "what": "crops/s/GPU x 70.34 GFLOP of 3x3 convs per crop (BASELINE.md)",
-                     "all_contractions_tflops": round(per_gpu * FTOTAL_GFLOP["coam"] / 1e3, 2),
-                     "dominant_kernel": kern},
+        "roofline": roofline(kern, peaks, ach, per_gpu),
         "e2e": {"value": round(crops / (ms_e2e / 1e3), 2), "unit": "crops/s",
                 "h2d_bytes_per_step": int(x.numel() * 4), "d2h_bytes_per_step": int(B * K * 3 * 4),
                 "ms_per_step": round(ms_e2e / args.steps, 4), "api": "model(x_host) + decode_device + .cpu()"},
@@ -249,6 +245,32 @@ def run_native(args):
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+# DRAM bytes per launch of the dominant kernel (tapgemm_chain_kernel<half,48,3>, 8 convolutions): dram__bytes_read.sum +
+# dram__bytes_write.sum of one `ncu --set full` capture at batch 64, profiles/r01_chain_full_details.csv
+DOMINANT_TRAFFIC_BYTES_B64 = 469.5e6
+
+
+def roofline(kern, peaks, path_tflops, per_gpu):
+    """`roofline` of the bench line: the dominant kernel (the BasicBlock 3x3 convolutions of branch 0: 17.5 % of a
+    forward, profiles/README.md) timed alone with CUDA events -> burst peak; plus the whole path against the
+    3x3-conv tensor-core roofline BASELINE.json asks for (kernels timed inside a long step -> sustained peak)."""
+    out = {"bound": "tensor", "unit": "TFLOP/s", "peak": peaks["tflops_burst"],
+           "peak_source": peaks["source"] + " (burst bf16/fp16 dense, MEASURED_PEAKS.json)", "achieved": None, "frac": None,
+           "traffic": None}
+    if kern is not None:
+        out.update({"achieved": kern["tflops"], "frac": kern["frac_of_burst_peak"], "kernel": kern["name"],
+                    "us_per_launch": kern["us_per_launch"], "us_per_conv": kern["us_per_conv"],
+                    "algorithmic_flops_per_launch": kern["flops_per_launch"],
+                    "traffic": DOMINANT_TRAFFIC_BYTES_B64 if kern["convs_per_launch"] == 8 and kern["batch"] == 64 else None,
+                    "traffic_source": "ncu --set full, profiles/r01_chain_full_details.csv (cold L2, isolated launch)",
+                    "hbm_bytes_min_per_launch": kern["hbm_bytes_min_per_conv"] * kern["convs_per_launch"]})
+    out["path_3x3"] = {"achieved": round(path_tflops, 2), "peak": peaks["tflops_sustained"],
+                       "frac": round(path_tflops / peaks["tflops_sustained"], 4),
+                       "what": "crops/s/GPU x 70.34 GFLOP of 3x3 convs per crop (BASELINE.md) over the sustained measured peak",
+                       "all_contractions_tflops": round(per_gpu * FTOTAL_GFLOP["coam"] / 1e3, 2)}
+    return out
 
 
 def time_dominant_conv(torch, net, B, local):
@@ -280,7 +302,7 @@ def time_dominant_conv(torch, net, B, local):
     flops = nconv * 2.0 * B * 96 * 72 * 48 * 48 * 9
     peaks = load_peaks()
     return {"name": "tap-GEMM 3x3 s1 48->48 @96x72 (BasicBlocks of branch 0), %d convolution(s) per launch" % nconv,
-            "convs_per_launch": nconv, "us_per_launch": round(us, 2), "us_per_conv": round(us / nconv, 2),
+            "convs_per_launch": nconv, "batch": B, "flops_per_launch": flops, "us_per_launch": round(us, 2), "us_per_conv": round(us / nconv, 2),
             "tflops": round(flops / us / 1e6, 2), "frac_of_burst_peak": round(flops / us / 1e6 / peaks["tflops_burst"], 4),
             "hbm_bytes_min_per_conv": int(2 * B * 97 * 73 * 48 * 2), "note": "back-to-back launches: activations stay in L2"}
 
