@@ -276,7 +276,9 @@ template <typename T, int BN>
 __device__ __forceinline__ void epi_compute(const TapGemmKParams& p, const EpiTile& tile, int n0, uint32_t tmem_acc,
                                             uint8_t* stage, const float* s_bias, bool has_res, int q, int lane, int grp,
                                             int ngrp) {
-  if (ngrp == 1 && n0 + BN <= p.n) {
+  // fast path: every column of the tile has weight rows behind it (rows >= n are zero by the packing contract, their
+  // bias is 0, so those columns come out as exact zeros and the TMA store clips whatever lies beyond out_cs)
+  if (ngrp == 1 && n0 + BN <= p.n_alloc) {
     if (has_res) epi_compute_fast<T, BN, true>(p, tile, tmem_acc, stage, s_bias, q, lane);
     else epi_compute_fast<T, BN, false>(p, tile, tmem_acc, stage, s_bias, q, lane);
     return;

@@ -10,7 +10,15 @@ constexpr int kSlabThreads = 352;      // producer + MMA + 8 epilogue warps (2 p
 constexpr int kSmemBudget = 227 * 1024;
 
 constexpr int kMaxAcc = 8;   // accumulator ring slots (barrier array size)
-template <int BN> __host__ __device__ constexpr int slab_nacc() { return (512 / BN) < kMaxAcc ? (512 / BN) : kMaxAcc; }
+// TMEM column stride of one accumulator slot: BN rounded up to a power of two (BUCTD_ACC_ALIGN experiment: an N = 48
+// accumulator that starts on a multiple of 64 columns)
+#ifndef BUCTD_ACC_PACKED
+__host__ __device__ constexpr int acc_stride_of(int bn) { return bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }
+#else
+__host__ __device__ constexpr int acc_stride_of(int bn) { return bn; }
+#endif
+template <int BN> __host__ __device__ constexpr int acc_stride() { return acc_stride_of(BN); }
+template <int BN> __host__ __device__ constexpr int slab_nacc() { return (512 / acc_stride<BN>()) < kMaxAcc ? (512 / acc_stride<BN>()) : kMaxAcc; }
 
 // Walks the 128-row sub-tiles of one CTA in processing order: work item k = blockIdx.x + k*gridDim.x is
 // (super-tile s, N tile nt) in mixed radix; every item has MSUB sub-tiles.  No division after init().

@@ -291,7 +291,47 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       for (int t = 0; t < 9; ++t) tap_shift[t] = sp.halo + (p.ntaps == 9 ? (t / 3 - 1) * p.wp + (t % 3 - 1) : 0);
       if (sp.w_resident) { mbar_wait(&w_full[0], 0); }
       tc_fence_after();
-      if (sp.jmajor) {
+      if (sp.desc_mode == 7 && sp.w_resident && p.num_kc == 1 && p.ntaps == 9) {
+        // TIMING EXPERIMENT ONLY (BUCTD_DESC_MODE=7; results are wrong): the issue order of the dx-fused formulation
+        //  -- for every (dy, sub-tile, k-step) three MMAs that share ONE A tile through the A collector
+        // (fill / use / lastuse) with the weights of dx = -1, 0, +1.
+        const int ksteps = p.k16 >> 4;
+        for (int k = 0; k < my_items; ++k) {
+          uint32_t d[MSUB], dslot[MSUB];
+#pragma unroll
+          for (int j = 0; j < MSUB; ++j) {
+            mbar_wait(&acc_empty[aslot], aph);
+            dslot[j] = aslot;
+            d[j] = tmem_base + aslot * acc_stride<BN>();
+            if (++aslot == NACC) { aslot = 0; aph ^= 1; }
+          }
+          { RT_BEGIN(t0); mbar_wait(&slab_full[slot], slot_ph); RT_ADD(t_slab, t0); }
+          tc_fence_after();
+          const uint32_t slab_addr = slab0_addr + slot * (uint32_t)sp.slab_bytes;
+          RT_BEGIN(t_i0);
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+            for (int j = 0; j < MSUB; ++j) {
+              const uint64_t adesc = umma_desc_sw128(slab_addr + (uint32_t)(tap_shift[dy * 3 + 1] + j * kBlockM) * 128);
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint32_t first = (dy | ks) == 0 ? 0u : 1u;
+                const uint64_t b0 = umma_desc_sw128(wbuf_addr + (dy * 3 + 0) * kWTileBytes) + (uint64_t)(2 * ks);
+                const uint64_t b1 = umma_desc_sw128(wbuf_addr + (dy * 3 + 1) * kWTileBytes) + (uint64_t)(2 * ks);
+                const uint64_t b2 = umma_desc_sw128(wbuf_addr + (dy * 3 + 2) * kWTileBytes) + (uint64_t)(2 * ks);
+                tc_mma_f16_coll<1>(d[j], adesc + (uint64_t)(2 * ks), b0, idesc, first);
+                tc_mma_f16_coll<2>(d[(j + 1) % MSUB], adesc + (uint64_t)(2 * ks), b1, idesc, first);
+                tc_mma_f16_coll<3>(d[(j + 2) % MSUB], adesc + (uint64_t)(2 * ks), b2, idesc, first);
+              }
+            }
+          }
+          RT_ADD(t_issue, t_i0);
+          tc_commit(&slab_empty[slot]);
+          if (++slot == (uint32_t)sp.sa) { slot = 0; slot_ph ^= 1; }
+#pragma unroll
+          for (int j = 0; j < MSUB; ++j) tc_commit(&acc_full[dslot[j]]);
+        }
+      } else if (sp.jmajor) {
         // resident weights, one K chunk: sub-tile-major order.  Sub-tile j is finished (and handed to the epilogue)
         // after its own taps, so the epilogue lags the tensor core by ONE sub-tile, not one super-tile.
         const int ksteps = p.k16 >> 4;
@@ -303,7 +343,7 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           for (int j = 0; j < MSUB; ++j) {
             { RT_BEGIN(t0); mbar_wait(&acc_empty[aslot], aph); RT_ADD(t_acc, t0); }
             tc_fence_after();
-            const uint32_t d = tmem_base + aslot * BN;
+            const uint32_t d = tmem_base + aslot * acc_stride<BN>();
             RT_BEGIN(t_i0);
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
@@ -328,7 +368,7 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           for (int j = 0; j < MSUB; ++j) {
             { RT_BEGIN(t0); mbar_wait(&acc_empty[aslot], aph); RT_ADD(t_acc, t0); }
             dslot[j] = aslot;
-            d[j] = tmem_base + aslot * BN;
+            d[j] = tmem_base + aslot * acc_stride<BN>();
             if (++aslot == NACC) { aslot = 0; aph ^= 1; }
           }
           tc_fence_after();
@@ -442,7 +482,7 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
         { RT_BEGIN(t0); mbar_wait(&acc_full[aslot], aph); RT_ADD(e_wait, t0); }
         tc_fence_after();
-        const uint32_t acc = tmem_base + aslot * BN;
+        const uint32_t acc = tmem_base + aslot * acc_stride<BN>();
         if (head) {
           if (!split || grp == 0) epi_head_nchw32<BN>(p, tile, nt * BN, acc, q, lane);
         } else if (sp.direct) {
@@ -566,7 +606,7 @@ static void pick_patch_tile(int oh, int ow, int* tw, int* th) {
 //   epilogue: ~700 + 9 bn clk per 128-row tile and group of 4 warps, two groups in parallel.
 static bool plan_slab_one(const buctd_tapgemm_args& a, int bn, int num_kc, int k16, int msub, int ctas, SlabParams* out,
                           double* t_est) {
-  const int nacc = (512 / bn) < kMaxAcc ? (512 / bn) : kMaxAcc;
+  const int nacc = (512 / acc_stride_of(bn)) < kMaxAcc ? (512 / acc_stride_of(bn)) : kMaxAcc;
   if (msub > nacc) return false;
   const int n_tiles = ceil_div(a.n_alloc, bn);
   const int halo = a.ntaps == 9 ? a.out_w + 2 : 0;        // (W+1) + 1 rows on each side
@@ -611,7 +651,7 @@ static bool plan_slab_one(const buctd_tapgemm_args& a, int bn, int num_kc, int k
   static const bool want_jmajor = getenv("BUCTD_JMAJOR") != nullptr && atoi(getenv("BUCTD_JMAJOR")) != 0;
   c.jmajor = want_jmajor && resident && num_kc == 1;
   c.direct = direct;
-  const int cols = nacc * bn;
+  const int cols = nacc * acc_stride_of(bn);
   c.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
   *out = c;
   // ---- time estimate (microseconds at 1.965 GHz) ----
@@ -645,7 +685,7 @@ static int plan_slab(const buctd_tapgemm_args& a, int num_kc, int k16, int ctas,
   bool have = false;
   double t = 0.0;
   for (int msub = 4; msub >= 1; --msub) {
-    if (forced > 0 ? msub > forced : 2 * msub * bn > 512) continue;
+    if (forced > 0 ? msub > forced : 2 * msub * acc_stride_of(bn) > 512) continue;   // double-buffered accumulators
     SlabParams c;
     if (!plan_slab_one(a, bn, num_kc, k16, msub, ctas, &c, &t)) continue;
     *sp = c;

@@ -177,7 +177,7 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
           for (int j = 0; j < MSUB; ++j) {
             mbar_wait(&acc_empty[aslot], aph);
             dslot[j] = aslot;
-            d[j] = tmem_base + aslot * BN;
+            d[j] = tmem_base + aslot * acc_stride<BN>();
             if (++aslot == NACC) { aslot = 0; aph ^= 1; }
           }
           tc_fence_after();
@@ -318,7 +318,7 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
           }
           mbar_wait(&acc_full[aslot], aph);
           tc_fence_after();
-          const uint32_t acc = tmem_base + aslot * BN;
+          const uint32_t acc = tmem_base + aslot * acc_stride<BN>();
           const int e = split ? 0 : grp;
           uint8_t* st = stage + (size_t)e * epi_stage_bytes<BN>();
           mbar_wait(&st_ready[e], (uint32_t)(split ? ug : (ug >> 1)) & 1u);

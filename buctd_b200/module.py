@@ -158,7 +158,9 @@ class PoseHighResolutionNet(nn.Module):
         def add_w(key, w4, bias, ):
             nonlocal woff, boff
             cout, cin, kh, kw = w4.shape
-            n_alloc, k_cs = _rup(cout, 16), _rup(cin, 8)
+            # rows per tap: a multiple of 16 (zero rows beyond cout).  BUCTD_PAD48=1 pads 48 output channels to a 64-wide N
+            # tile: measured neutral (37.4 vs 37.7 us per conv), the operand fetch is per 128-byte row, DESIGN.md 3.1
+            n_alloc, k_cs = (64 if cout == 48 and os.environ.get("BUCTD_PAD48", "0") == "1" else _rup(cout, 16)), _rup(cin, 8)
             p = torch.zeros(kh * kw, n_alloc, k_cs, dtype=torch.float32)
             p[:, :cout, :cin] = w4.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin).float()
             p = p.to(self._torch_dt).reshape(-1)

@@ -83,7 +83,7 @@ typedef struct {
   int32_t k;            /* valid input channels (cin) */
   int32_t a_cs;         /* A channel stride (elements) */
   int32_t n;            /* valid output channels (cout) */
-  int32_t n_alloc;      /* rows per tap in W (>= n, multiple of 16) */
+  int32_t n_alloc;      /* rows per tap in W (>= n, multiple of 16); rows n..n_alloc-1 of every tap MUST be zero */
   int32_t w_cs;         /* W row stride in elements (>= k, multiple of 8) */
   int32_t out_cs;       /* out channel stride (ACT16/ROWS16) */
   int32_t res_cs;       /* residual channel stride */

@@ -20,6 +20,7 @@ from gpu_utils import TDT, pack_w, to_act16  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--quick", action="store_true")
 ap.add_argument("--reps", type=int, default=20)
+ap.add_argument("--nk", action="store_true", help="N / K separation experiment: 64->48, 48->64, 32->32, 64->32, 32->64 at 96x72")
 args = ap.parse_args()
 lib = L.load()
 ctx = L.Context.get(0)
@@ -28,7 +29,10 @@ stream = torch.cuda.current_stream().cuda_stream
 CASES = [(48, 48, 3, 64, 96, 72, False), (48, 48, 3, 64, 96, 72, True), (96, 96, 3, 64, 48, 36, True),
          (192, 192, 3, 64, 24, 18, True), (384, 384, 3, 64, 12, 9, True), (64, 256, 1, 64, 96, 72, True),
          (256, 64, 1, 64, 96, 72, False), (64, 64, 3, 64, 96, 72, False)]
-if not args.quick:
+if args.nk:
+    CASES = [(48, 48, 3, 64, 96, 72, False), (64, 48, 3, 64, 96, 72, False), (48, 64, 3, 64, 96, 72, False), (64, 64, 3, 64, 96, 72, False),
+             (32, 32, 3, 64, 96, 72, False), (64, 32, 3, 64, 96, 72, False), (32, 64, 3, 64, 96, 72, False)]
+elif not args.quick:
     CASES += [(48, 48, 3, b, 96, 72, False) for b in (4, 8, 16, 32, 128)]
     CASES += [(96, 96, 3, b, 48, 36, False) for b in (8, 32, 128)]
     CASES += [(192, 192, 3, b, 24, 18, False) for b in (8, 32, 128)]
