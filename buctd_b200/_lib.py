@@ -60,6 +60,11 @@ class ResizeArgs(C.Structure):
                 ("x", fp), ("out", vp)]
 
 
+class Resize3Args(C.Structure):
+    _fields_ = [("dtype", i32), ("batch", i32), ("x_channels", i32), ("c_off", i32), ("cc", i32), ("h", i32), ("w", i32),
+                ("reserved", i32), ("out_cs", i32 * 3), ("reserved2", i32), ("x", fp), ("out", vp * 3)]
+
+
 class ChanAttArgs(C.Structure):
     _fields_ = [("dtype", i32), ("batch", i32), ("h", i32), ("w", i32), ("c", i32), ("y_cs", i32), ("yc_cs", i32),
                 ("reserved", i32), ("y", vp), ("yc", vp), ("scratch", fp), ("out", vp)]
@@ -121,7 +126,7 @@ OP_STRUCT = {OP_TAPGEMM: TapGemmArgs, OP_STEM: StemArgs, OP_FUSE: FuseArgs, OP_R
 
 # every symbol include/buctd_b200.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = ["buctd_abi_version", "buctd_last_error", "buctd_create", "buctd_destroy", "buctd_launch_count",
-           "buctd_tapgemm", "buctd_tapgemm_chain", "buctd_stem_conv", "buctd_hr_fuse", "buctd_cond_resize", "buctd_coam_channel_att",
+           "buctd_tapgemm", "buctd_tapgemm_chain", "buctd_stem_conv", "buctd_hr_fuse", "buctd_cond_resize", "buctd_cond_resize3", "buctd_coam_channel_att",
            "buctd_coam_position_att", "buctd_da_combine", "buctd_prenet", "buctd_decode_heatmaps",
            "buctd_rasterize_condition", "buctd_flip_channels", "buctd_flip_merge", "buctd_joints_mse", "buctd_adam_step",
            "buctd_act16_to_nchw32", "buctd_nchw32_to_act16", "buctd_plan_create",
@@ -157,7 +162,7 @@ def load():
         lib.buctd_launch_count.argtypes = [vp]
         lib.buctd_create.argtypes = [C.c_int, C.POINTER(vp)]
         lib.buctd_destroy.argtypes = [vp]
-        for name in list(_IMMEDIATE.values()) + ["buctd_flip_channels", "buctd_flip_merge", "buctd_joints_mse", "buctd_adam_step"]:
+        for name in list(_IMMEDIATE.values()) + ["buctd_cond_resize3", "buctd_flip_channels", "buctd_flip_merge", "buctd_joints_mse", "buctd_adam_step"]:
             getattr(lib, name).argtypes = [vp, vp, vp]
         lib.buctd_act16_to_nchw32.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
         lib.buctd_nchw32_to_act16.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -343,6 +343,136 @@ static int resize_dispatch(const buctd_resize_args& a, cudaStream_t st) {
   return BUCTD_OK;
 }
 
+// =================================================================================================
+// Fused condition pyramid: the three CoAM scales (1/4, 1/8, 1/16) of the antialiased resize in ONE pass over the
+// condition planes -- the three separate launches read the 7.5 MB per crop 3.75 times, this one 1.5 times.
+// Block = a band of 32 input rows (8 / 4 / 2 output rows of the three scales) x 8 channels x the full width;
+// thread = (channel, 4 consecutive input columns).  The vertical triangle filters of all three scales are
+// accumulated in registers while the 48 rows [32 i - 8, 32 i + 40) of the band stream by (128-bit loads, compile-time
+// tap weights); then, scale by scale, the vertical result goes through shared memory for the horizontal pass.
+// Same arithmetic (vertical in fp32, normalise, horizontal in fp32, normalise) as resize_int_kernel.
+// =================================================================================================
+constexpr int kPyrBand = 32;
+
+template <int S, int NR>
+__device__ __forceinline__ void pyr_accum(float4 (&acc)[NR], const float4& v, int r) {
+  // input row r (relative to band start - 8) feeds output row g of scale S with tap k = r - (S*g - S/2 + 8), 0 <= k < 2S
+#pragma unroll
+  for (int g = 0; g < NR; ++g) {
+    const int k = r - (S * g - S / 2 + 8);
+    if (k >= 0 && k < 2 * S) {
+      const float wt = aa_w<S>(k);
+      acc[g].x = fmaf(wt, v.x, acc[g].x); acc[g].y = fmaf(wt, v.y, acc[g].y);
+      acc[g].z = fmaf(wt, v.z, acc[g].z); acc[g].w = fmaf(wt, v.w, acc[g].w);
+    }
+  }
+}
+
+template <typename T, int S, int NR>
+__device__ __forceinline__ void pyr_emit(const buctd_resize3_args& a, int which, const float4 (&acc)[NR], float* s_v, T* so, int band,
+                                         int b, int c0, int cc, int x4, bool active) {
+  const int oh = a.h / S, ow = a.w / S;
+  const int oy0 = band * NR;
+  const int nrows = min(NR, oh - oy0);
+  // vertical normalisation: weights of the input rows that exist
+  if (active) {
+#pragma unroll
+    for (int g = 0; g < NR; ++g) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 2 * S; ++k) {
+        const int jrow = S * (oy0 + g) - S / 2 + k;
+        t += (jrow >= 0 && jrow < a.h) ? aa_w<S>(k) : 0.f;
+      }
+      const float rt = t > 0.f ? 1.f / t : 0.f;
+      float4 o = acc[g];
+      o.x *= rt; o.y *= rt; o.z *= rt; o.w *= rt;
+      reinterpret_cast<float4*>(s_v + (cc * NR + g) * a.w)[x4] = o;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nrows * ow; i += blockDim.x) {
+    const int g = i / ow, ox = i - g * ow;
+    const int lo = S * ox - S / 2;
+    float tot = 0.f;
+#pragma unroll
+    for (int t = 0; t < 2 * S; ++t) tot += ((unsigned)(lo + t) < (unsigned)a.w) ? aa_w<S>(t) : 0.f;
+    const float rt = 1.f / tot;
+    float o[8];
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+      const float* row = s_v + (ch * NR + g) * a.w;
+      float sum = 0.f;
+#pragma unroll
+      for (int t = 0; t < 2 * S; ++t) {
+        const int jx = lo + t;
+        sum = fmaf(aa_w<S>(t), ((unsigned)jx < (unsigned)a.w) ? row[jx] : 0.f, sum);
+      }
+      o[ch] = (c0 + ch < a.cc) ? sum * rt : 0.f;
+    }
+    uint4 u;
+    u.x = T16<T>::pack2(o[0], o[1]); u.y = T16<T>::pack2(o[2], o[3]);
+    u.z = T16<T>::pack2(o[4], o[5]); u.w = T16<T>::pack2(o[6], o[7]);
+    T* dst = reinterpret_cast<T*>(a.out[which]) + (((long long)b * (oh + 1) + oy0 + g) * (ow + 1) + ox) * a.out_cs[which] + c0;
+    *reinterpret_cast<uint4*>(dst) = u;
+  }
+  __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(576) resize_pyramid_kernel(buctd_resize3_args a) {
+  extern __shared__ __align__(16) float s_pyr[];             // [8 ch][8 rows][w] fp32 (the largest of the three scales)
+  const int b = blockIdx.z, c0 = blockIdx.y * 8, band = blockIdx.x;
+  const int w4 = a.w >> 2;
+  const int cc = threadIdx.x / w4, x4 = threadIdx.x - cc * w4;
+  const bool active = threadIdx.x < 8 * w4;
+  float4 a4[8], a8[4], a16[2];
+#pragma unroll
+  for (int g = 0; g < 8; ++g) a4[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) a8[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int g = 0; g < 2; ++g) a16[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (active && c0 + cc < a.cc) {
+    const int base = kPyrBand * band - 8;
+    const float4* ptr = reinterpret_cast<const float4*>(a.x + (((long long)b * a.x_channels + a.c_off + c0 + cc) * a.h) * a.w) +
+                        (long long)base * w4 + x4;
+#pragma unroll
+    for (int r = 0; r < kPyrBand + 16; ++r) {
+      const bool ok = (unsigned)(base + r) < (unsigned)a.h;
+      const float4 v = ok ? __ldg(ptr) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ptr += w4;
+      pyr_accum<4, 8>(a4, v, r);
+      pyr_accum<8, 4>(a8, v, r);
+      pyr_accum<16, 2>(a16, v, r);
+    }
+  }
+  T* so = nullptr;
+  pyr_emit<T, 4, 8>(a, 0, a4, s_pyr, so, band, b, c0, cc, x4, active);
+  pyr_emit<T, 8, 4>(a, 1, a8, s_pyr, so, band, b, c0, cc, x4, active);
+  pyr_emit<T, 16, 2>(a, 2, a16, s_pyr, so, band, b, c0, cc, x4, active);
+}
+
+int launch_resize3(const buctd_resize3_args& a, cudaStream_t st) {
+  BUCTD_CHECK(a.x && a.out[0] && a.out[1] && a.out[2], BUCTD_ERR_INVALID, "resize3: null pointer");
+  BUCTD_CHECK(a.cc > 0 && a.h % 16 == 0 && a.w % 16 == 0 && a.w <= kRzMaxW && ((uintptr_t)a.x & 15) == 0 && (a.w / 4) * 8 <= 576,
+              BUCTD_ERR_INVALID, "resize3: needs H, W multiples of 16, W <= %d, 16-byte aligned input (got %dx%d)", 288, a.h, a.w);
+  for (int i = 0; i < 3; ++i)
+    BUCTD_CHECK(a.out_cs[i] % 8 == 0 && a.cc <= a.out_cs[i], BUCTD_ERR_INVALID, "resize3: cc %d vs out_cs[%d] %d", a.cc, i, a.out_cs[i]);
+  if (a.batch == 0) return BUCTD_OK;
+  const size_t smem = (size_t)8 * 8 * a.w * 4;
+  dim3 grid(ceil_div(a.h, kPyrBand), ceil_div(a.cc, 8), a.batch);
+  if (a.dtype == BUCTD_F16) {
+    BUCTD_CUDA(cudaFuncSetAttribute(resize_pyramid_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    resize_pyramid_kernel<__half><<<grid, 576, smem, st>>>(a);
+  } else {
+    BUCTD_CUDA(cudaFuncSetAttribute(resize_pyramid_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    resize_pyramid_kernel<__nv_bfloat16><<<grid, 576, smem, st>>>(a);
+  }
+  BUCTD_CUDA(cudaGetLastError());
+  return BUCTD_OK;
+}
+
 int launch_resize(const buctd_resize_args& a, cudaStream_t st) {
   BUCTD_CHECK(a.cc > 0 && a.cc <= a.out_cs && a.out_cs % 8 == 0, BUCTD_ERR_INVALID, "resize: cc %d vs out_cs %d", a.cc, a.out_cs);
   BUCTD_CHECK(a.w <= kRzMaxW && a.ow <= kRzMaxOw, BUCTD_ERR_INVALID, "resize: width %d -> %d out of range", a.w, a.ow);

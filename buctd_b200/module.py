@@ -633,7 +633,19 @@ class PoseHighResolutionNet(nn.Module):
             sa.dtype, sa.batch, sa.x_channels, sa.h, sa.w, sa.out_cs = self._dt, B, stem_c, H, W, s1.cs
             sa.x, sa.weight, sa.bias, sa.out = stem_x.data_ptr(), f32["conv1.w"].data_ptr(), f32["conv1.b"].data_ptr(), s1.ptr
             ctx.run(L.OP_STEM, sa, stream)
-            if arch.use_attention:
+            conds = st["cond"] if arch.use_attention else {}
+            pyramid = (len(conds) == 3 and self.antialias and H % 16 == 0 and W % 16 == 0 and W <= 288
+                       and all((conds[i].h, conds[i].w) == (H >> (2 + i), W >> (2 + i)) for i in range(3))
+                       and os.environ.get("BUCTD_RESIZE3", "1") != "0")
+            if pyramid:                    # the three CoAM scales in one pass over the condition planes
+                r3 = L.Resize3Args()
+                r3.dtype, r3.batch, r3.x_channels, r3.c_off, r3.cc, r3.h, r3.w = self._dt, B, Cx, 3, conds[0].c, H, W
+                for i in range(3):
+                    r3.out_cs[i] = conds[i].cs
+                    r3.out[i] = conds[i].ptr
+                r3.x = x.data_ptr()
+                ctx.call("buctd_cond_resize3", r3, stream)
+            elif arch.use_attention:
                 for i, cond in st["cond"].items():
                     ra = L.ResizeArgs()
                     ra.dtype, ra.batch, ra.x_channels, ra.c_off, ra.cc = self._dt, B, Cx, 3, cond.c

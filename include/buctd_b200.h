@@ -139,6 +139,16 @@ typedef struct {
 } buctd_resize_args;
 int buctd_cond_resize(buctd_ctx* ctx, const buctd_resize_args* args, buctd_stream stream);
 
+/* The three CoAM scales of buctd_cond_resize (1/4, 1/8, 1/16 of an H x W input, H and W multiples of 16, antialiased)
+ * in one pass over the condition planes: out[i] is act16 [B][H/s_i + 1][W/s_i + 1][out_cs[i]], s = {4, 8, 16}.
+ * Same arithmetic and results as three buctd_cond_resize calls (CoAMBlock.forward, lib/models/pose_hrnet_coam.py:750-757). */
+typedef struct {
+  int32_t dtype, batch, x_channels, c_off, cc, h, w, reserved;
+  int32_t out_cs[3]; int32_t reserved2;
+  const float* x; void* out[3];
+} buctd_resize3_args;
+int buctd_cond_resize3(buctd_ctx* ctx, const buctd_resize3_args* args, buctd_stream stream);
+
 /* CoAM channel attention core: att = softmax_c2( yc^T y / sqrt(HW) ) [C x C] per crop, then
  * out[c1][p] = sum_c2 att[c1][c2] y[p][c2], written planar [B][C][HW] (the A operand of the
  * HW x HW fc_o tap-GEMM).  y, yc: act16 [B][H+1][W+1][cs].  scratch: float32 [B][nchunks][C][C] with

@@ -129,6 +129,36 @@ def test_tapgemm_head_nchw32(dt):
 
 
 @pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("B,cc,H,W", [(2, 17, 128, 96), (3, 3, 384, 288), (1, 1, 256, 192), (2, 20, 96, 64)])
+def test_cond_resize_pyramid(dt, B, cc, H, W):
+    """the fused three-scale resize == three single-scale launches (bit for bit) == torch antialiased bilinear"""
+    x = (_rand(B, 3 + cc, H, W, seed=25).abs() * 100).contiguous()
+    cs = rup(cc, 16)
+    outs = [torch.zeros(B, H // s + 1, W // s + 1, cs, dtype=TDT[dt], device="cuda") for s in (4, 8, 16)]
+    a = L.Resize3Args()
+    a.dtype, a.batch, a.x_channels, a.c_off, a.cc, a.h, a.w = dt, B, 3 + cc, 3, cc, H, W
+    for i in range(3):
+        a.out_cs[i] = cs
+        a.out[i] = outs[i].data_ptr()
+    a.x = x.data_ptr()
+    ctx().call("buctd_cond_resize3", a, stream())
+    torch.cuda.synchronize()
+    for i, s in enumerate((4, 8, 16)):
+        oh, ow = H // s, W // s
+        single = torch.zeros_like(outs[i])
+        r = L.ResizeArgs()
+        r.dtype, r.batch, r.x_channels, r.c_off, r.cc = dt, B, 3 + cc, 3, cc
+        r.h, r.w, r.oh, r.ow, r.out_cs, r.antialias = H, W, oh, ow, cs, 1
+        r.x, r.out = x.data_ptr(), single.data_ptr()
+        ctx().run(L.OP_RESIZE, r, stream())
+        torch.cuda.synchronize()
+        ref = F.interpolate(x[:, 3:].cpu(), size=(oh, ow), mode="bilinear", align_corners=False, antialias=True)
+        assert_close(from_act16(outs[i], cc), ref, TOL[dt], "pyramid x%d" % s)
+        assert torch.equal(outs[i], single), "pyramid scale %d differs from the single-scale kernel" % s
+        assert pads_are_zero(outs[i])
+
+
+@pytest.mark.parametrize("dt", DTS)
 @pytest.mark.parametrize("rows,k,n", [(96, 432, 432), (200, 768, 768), (130, 1728, 1728)])
 def test_tapgemm_linear_rows(dt, rows, k, n):
     x = q16(_rand(rows, k, seed=14), dt)
