@@ -74,6 +74,8 @@ struct TapGemmLaunch {
 
 int tapgemm_prepare(const buctd_tapgemm_args& a, TapGemmLaunch* L, int sm_count);
 int tapgemm_launch(const TapGemmLaunch& L, cudaStream_t st);
+// [rows][cs] 16-bit matrix seen through SWIZZLE_128B boxes of 64 channels x box_rows rows (inner = channels that exist)
+int tapgemm_encode_rows_map(CUtensorMap* m, int dtype, const void* base, int inner, int cs, long long rows, int box_rows);
 int tapgemm_init_device();
 
 // immediate launchers of the CUDA-core kernels (each returns a BUCTD_* code)

@@ -858,6 +858,20 @@ int tapgemm_prepare(const buctd_tapgemm_args& a, TapGemmLaunch* L, int sm_count)
   return BUCTD_OK;
 }
 
+int tapgemm_encode_rows_map(CUtensorMap* m, int dtype, const void* base, int inner, int cs, long long rows, int box_rows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  BUCTD_CHECK(enc != nullptr, BUCTD_ERR_NO_DEVICE, "cuTensorMapEncodeTiled entry point not available");
+  const CUtensorMapDataType dt = dtype == BUCTD_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cs * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult cr = enc(m, dt, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BUCTD_CHECK(cr == CUDA_SUCCESS, BUCTD_ERR_CUDA, "cuTensorMapEncodeTiled(rows map) failed: %d", (int)cr);
+  return BUCTD_OK;
+}
+
 #ifdef BUCTD_ROLE_TIMERS
 extern "C" __attribute__((visibility("default"))) int buctd_debug_role_cycles(unsigned long long* out, int n) {
   return (int)cudaMemcpyFromSymbol(out, g_role_cycles, sizeof(unsigned long long) * n);

@@ -323,10 +323,21 @@ def test_prenet_composed():
 
 
 @pytest.mark.parametrize("dt", DTS)
-@pytest.mark.parametrize("c,B,h,w,nblocks", [(48, 7, 24, 18, 2), (96, 5, 12, 9, 4), (192, 9, 12, 9, 2), (48, 40, 48, 36, 4)])
-def test_tapgemm_chain_basic_blocks(dt, c, B, h, w, nblocks):
+@pytest.mark.parametrize("c,B,h,w,nblocks,dxf", [
+    (48, 7, 24, 18, 2, "0"), (96, 5, 12, 9, 4, "1"), (192, 9, 12, 9, 2, "1"), (48, 40, 48, 36, 4, "0"),
+    # dx-fused plan (C <= 64: one N = 3C MMA per kernel row, 126-row tiles), default and pinned super-tile sizes
+    (48, 7, 24, 18, 2, "1"), (48, 40, 48, 36, 4, "1"), (48, 40, 48, 36, 4, "1:2"), (48, 3, 5, 4, 1, "1"), (48, 1, 96, 72, 1, "1:3"),
+    # > kLag + 1 items per CTA and layer: the publish FIFO runs across layer boundaries (no drain)
+    (48, 16, 96, 72, 2, "1"), (48, 40, 96, 72, 2, "0"),
+    (32, 9, 32, 24, 2, "1"), (32, 9, 32, 24, 2, "1:4"), (64, 6, 20, 15, 2, "2"), (64, 6, 20, 15, 2, "2:2")])
+def test_tapgemm_chain_basic_blocks(dt, c, B, h, w, nblocks, dxf, monkeypatch):
     """chain launch: nblocks BasicBlocks (conv-relu-conv-add-relu) in ONE persistent kernel with grid barriers,
     against the same sequence in torch on 16-bit-rounded operands"""
+    monkeypatch.setenv("BUCTD_DXF", dxf.split(":")[0])
+    if ":" in dxf:
+        monkeypatch.setenv("BUCTD_DXF_MSUB", dxf.split(":")[1])
+    else:
+        monkeypatch.delenv("BUCTD_DXF_MSUB", raising=False)
     x = q16(_rand(B, c, h, w, seed=61), dt)
     ws = [q16(_rand(c, c, 3, 3, seed=62 + i, scale=1.0 / math.sqrt(9 * c)), dt) for i in range(2 * nblocks)]
     bs = [_rand(c, seed=80 + i, scale=0.1).float().contiguous() for i in range(2 * nblocks)]

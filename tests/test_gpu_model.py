@@ -104,7 +104,9 @@ def test_batch_sizes_and_determinism():
 def test_schedules_are_bitwise_equivalent(monkeypatch, name):
     """The plan executor derives cross-lane dependencies from the buffers the ops touch; every schedule (one lane,
     CoAM + fuse lanes, all branches on lanes; serial launches, multi-stream launches, CUDA graph; chain launches on /
-    off) must therefore produce the SAME bits as the serial program."""
+    off) must therefore produce the SAME bits as the serial program.  (The dx-fused chain plan adds the nine taps in a
+    different fp32 order -- it is pinned off here and compared with a tolerance in test_dx_fused_chain_plan.)"""
+    monkeypatch.setenv("BUCTD_DXF", "0")
     x = torch.from_numpy(G.case_inputs(name))
     outs = {}
     for lanes, graph, chain in (("0", "0", "0"), ("0", "1", "1"), ("2", "0", "1"), ("2", "1", "1"), ("1", "1", "0"), ("1", "0", "0")):
@@ -120,3 +122,22 @@ def test_schedules_are_bitwise_equivalent(monkeypatch, name):
     ref = outs[("0", "0", "0")]
     for key, o in outs.items():
         assert np.array_equal(o, ref), "schedule lanes=%s graph=%s chain=%s differs from the serial program" % key
+
+
+@pytest.mark.parametrize("name", ["coam_w32_128x96_stacked", "coam_w48_384x288_stacked"])
+def test_dx_fused_chain_plan(monkeypatch, golden_dir, name):
+    """BasicBlock chains of the C <= 48 branch under the dx-fused plan (default) and the regular plan: same network
+    output up to the fp32 summation order of the nine taps (a few 16-bit roundings over the depth of the branch), and
+    both within the reference tolerance."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    x = torch.from_numpy(G.case_inputs(name))
+    outs = {}
+    for dxf in ("1", "0"):
+        monkeypatch.setenv("BUCTD_DXF", dxf)
+        cfg, net = _net(name, "fp16")
+        with torch.no_grad():
+            outs[dxf] = net(x).cpu().numpy()
+    assert not np.array_equal(outs["1"], outs["0"]), "BUCTD_DXF had no effect: the dx-fused plan was not selected"
+    assert np.abs(outs["1"] - outs["0"]).max() <= 3e-3
+    for dxf in outs:
+        assert np.abs(outs[dxf] - g["heatmaps"]).max() <= TOL["fp16"]
