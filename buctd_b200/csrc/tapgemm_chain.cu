@@ -35,6 +35,7 @@ struct ChainParams {
   unsigned int* flags;       // [n_layers][num_super]: N tiles of that super-tile whose output is in global memory
   int n_layers;
   int n_tiles;               // N tiles per super-tile
+  int lag;                   // items whose stores stay in flight before a flag is published (0, 1, 2 or 4)
   int debug;                 // BUCTD_CHAIN_DEBUG timing experiments (results are WRONG): 1 no dataflow flags, 2 dx-fused
                              // epilogue without the +-1 row exchange, 4 no MMAs
 };
@@ -452,11 +453,13 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
         unsigned int pushed = 0;
         int ubase = 0;
         // super-tiles whose stores are committed but not yet published (FIFO, newest last): an item is published once
-        // kLag younger items have been committed, so that waiting for ITS stores never waits for recent ones
-        // (about four 128-row tiles of stores stay in flight; layers that give a CTA only a few items drain at their end)
-        constexpr int kLag = MSUB == 1 ? 4 : 2;
-        const bool drain = sp.num_items / (int)gridDim.x <= kLag + 1;      // otherwise the FIFO runs across the layer boundary
-        int pend[kLag];
+        // `lag` younger items have been committed, so that waiting for ITS stores does not wait for recent ones.  The
+        // host sizes the lag to ~2.5 us of tiles: 4 items for the 0.5 us dx-fused tiles, 0 for the >= 6 us tiles of
+        // C >= 192, where a CTA has one or two items per layer and a late flag stalls the neighbours for a whole item.
+        constexpr int kLagMax = 4;
+        const int lag = cp.lag;
+        const bool drain = sp.num_items / (int)gridDim.x <= lag + 1;      // otherwise the FIFO runs across the layer boundary
+        int pend[kLagMax + 1];
         int npend = 0;
         for (int l = 0; l < NL; ++l, ubase += total_u) {
           TapGemmKParams p = p0;
@@ -483,6 +486,7 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
             }
             pr_it.template next<MSUB>();
           };
+          tma_store_wait_read<0>();               // (no drain at the previous layer's end) the stage buffers have been read
           for (int u = 0; u < SE && u < total_u; ++u) prepare(u);
           for (int u = 0; u < total_u; ++u) {
             const int ug = ubase + u;
@@ -497,19 +501,24 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
             const bool item_end = st_it.j == MSUB - 1;
             st_it.template next<MSUB>();
             if (item_end && l + 1 < NL && !(cp.debug & 1)) {
-              // publish the oldest pending item: its MSUB store groups precede the kLag * MSUB most recent ones, which
-              // stay in flight (waiting for the newest stores would stall this thread, and with it the stage buffers)
-              if (npend == kLag) {
-                tma_store_wait_complete<kLag * MSUB>();
-                pub_push(pub, pushed, (unsigned)pend[0]);
 #pragma unroll
-                for (int i = 0; i + 1 < kLag; ++i) pend[i] = pend[i + 1];
-                --npend;
-              }
-#pragma unroll
-              for (int i = 0; i < kLag; ++i)
+              for (int i = 0; i <= kLagMax; ++i)
                 if (i == npend) pend[i] = l * sp.num_super + s_now;
               ++npend;
+              // publish the oldest pending item: its MSUB store groups precede the lag * MSUB most recent ones, which
+              // stay in flight (waiting for the newest stores would stall this thread, and with it the stage buffers)
+              if (npend > lag) {
+                switch (lag) {
+                  case 0: tma_store_wait_complete<0>(); break;
+                  case 1: tma_store_wait_complete<MSUB>(); break;
+                  case 2: tma_store_wait_complete<2 * MSUB>(); break;
+                  default: tma_store_wait_complete<kLagMax * MSUB>(); break;
+                }
+                pub_push(pub, pushed, (unsigned)pend[0]);
+#pragma unroll
+                for (int i = 0; i < kLagMax; ++i) pend[i] = pend[i + 1];
+                --npend;
+              }
             }
             if (u + SE < total_u) {
               tma_store_wait_read<0>();
@@ -518,13 +527,13 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
           }
           if (drain || l + 2 >= NL) {
             // Few items per layer: publish everything now (a neighbour's next-layer item may need our LAST items while
-            // we would wait for kLag more commits that need ITS flags).  With more than kLag + 1 items per CTA and layer
+            // we would wait for `lag` more commits that need ITS flags).  With more than lag + 1 items per CTA and layer
             // the youngest items are published during the next layer's first ones, which only need flags of items that
             // were published inside this layer: no cycle, and no drain bubble at the layer boundary.  The last layer
             // pushes nothing (nobody reads its flags), so the layer before it drains as well.
             tma_store_wait_all();                 // this CTA's tiles so far are in global memory
 #pragma unroll
-            for (int i = 0; i < kLag; ++i)
+            for (int i = 0; i <= kLagMax; ++i)
               if (i < npend) pub_push(pub, pushed, (unsigned)pend[i]);
             npend = 0;
           }
@@ -744,14 +753,23 @@ int tapgemm_chain_prepare(const buctd_tapgemm_chain_args& a, ChainLaunch* C, int
     if (g.residual == nullptr) C->cp.m[l].res = C->cp.m[l].out;
   }
   if (C->dxf) { C->sp = dxf_sp; C->grid = dxf_grid; }
-  if (getenv("BUCTD_PLAN_DEBUG") != nullptr)
-    fprintf(stderr, "[buctd] chain plan: %d layers bn %d dxf %d msub %d sa %d stage_bufs %d slab %d B supers %d grid %u smem %d\n", a.n_layers, C->bn,
-            C->dxf, C->sp.msub, C->sp.sa, C->sp.stage_bufs, C->sp.slab_bytes, C->sp.num_super, C->grid.x, C->sp.smem_bytes);
   C->kp.bias = nullptr; C->kp.residual = nullptr; C->kp.out = nullptr; C->kp.relu = 0;
   C->cp.flags = counter;
   C->cp.n_layers = a.n_layers;
   C->cp.n_tiles = C->sp.num_items / C->sp.num_super;
+  {
+    // publish lag ~ 2.5 us of tiles, from the measured MMA issue interval (50 + 0.35 N clk per 128 x N x 16 MMA)
+    const int n_mma = (C->dxf ? 3 : f.ntaps) * (C->kp.k16 / 16);
+    const double tile_us = n_mma * (50.0 + 0.35 * (C->dxf ? 3 * C->bn : C->bn)) / 1965.0;
+    const int lag_tiles = (int)(2.5 / tile_us);
+    int lag = (lag_tiles + C->sp.msub - 1) / C->sp.msub;
+    if (getenv("BUCTD_CHAIN_LAG")) lag = atoi(getenv("BUCTD_CHAIN_LAG"));
+    C->cp.lag = lag <= 0 ? 0 : lag == 1 ? 1 : lag == 2 ? 2 : 4;
+  }
   C->cp.debug = getenv("BUCTD_CHAIN_DEBUG") ? atoi(getenv("BUCTD_CHAIN_DEBUG")) : 0;
+  if (getenv("BUCTD_PLAN_DEBUG") != nullptr)
+    fprintf(stderr, "[buctd] chain plan: %d layers bn %d dxf %d lag %d msub %d sa %d stage_bufs %d slab %d B supers %d grid %u smem %d\n", a.n_layers, C->bn,
+            C->dxf, C->cp.lag, C->sp.msub, C->sp.sa, C->sp.stage_bufs, C->sp.slab_bytes, C->sp.num_super, C->grid.x, C->sp.smem_bytes);
   return BUCTD_OK;
 }
 

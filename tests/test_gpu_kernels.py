@@ -329,6 +329,7 @@ def test_prenet_composed():
     (48, 7, 24, 18, 2, "1"), (48, 40, 48, 36, 4, "1"), (48, 40, 48, 36, 4, "1:2"), (48, 3, 5, 4, 1, "1"), (48, 1, 96, 72, 1, "1:3"),
     # > kLag + 1 items per CTA and layer: the publish FIFO runs across layer boundaries (no drain)
     (48, 16, 96, 72, 2, "1"), (48, 40, 96, 72, 2, "0"),
+    (192, 30, 24, 18, 4, "0"), (96, 33, 48, 36, 3, "0"),        # few items per CTA and layer (drain at every layer end), partial last round
     (32, 9, 32, 24, 2, "1"), (32, 9, 32, 24, 2, "1:4"), (64, 6, 20, 15, 2, "2"), (64, 6, 20, 15, 2, "2:2")])
 def test_tapgemm_chain_basic_blocks(dt, c, B, h, w, nblocks, dxf, monkeypatch):
     """chain launch: nblocks BasicBlocks (conv-relu-conv-add-relu) in ONE persistent kernel with grid barriers,

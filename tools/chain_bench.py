@@ -35,7 +35,7 @@ for (c, h, w, variants) in CASES:
     results = {}
     for var in variants:
         v0 = var
-        for key, sep in (("BUCTD_FORCE_MSUB", "@"), ("BUCTD_CHAIN_DEBUG", "/"), ("BUCTD_DXF_MSUB", ":")):
+        for key, sep in (("BUCTD_CHAIN_LAG", "g"), ("BUCTD_FORCE_MSUB", "@"), ("BUCTD_CHAIN_DEBUG", "/"), ("BUCTD_DXF_MSUB", ":")):
             if sep in v0:
                 v0, val = v0.split(sep)
                 os.environ[key] = val
