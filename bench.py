@@ -247,9 +247,20 @@ def run_native(args):
         dist.destroy_process_group()
 
 
-# DRAM bytes per launch of the dominant kernel (tapgemm_chain_kernel<half,48,3>, 8 convolutions): dram__bytes_read.sum +
-# dram__bytes_write.sum of one `ncu --set full` capture at batch 64, profiles/r01_chain_full_details.csv
-DOMINANT_TRAFFIC_BYTES_B64 = 469.5e6
+def dominant_traffic():
+    """DRAM bytes per launch of the dominant kernel (the dx-fused chain tap-GEMM of branch 0, 8 convolutions 48->48 at
+    batch 64): dram__bytes_read.sum + dram__bytes_write.sum of the committed `ncu --set full` capture, summarised by
+    tools/ncu_traffic.py into profiles/dominant_traffic.json.  None when the file is missing."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "dominant_traffic.json")
+    try:
+        with open(path) as f:
+            launches = json.load(f)["launches"]
+    except (OSError, ValueError, KeyError):
+        return None, None
+    for o in launches:
+        if "tapgemm_chain_kernel<__half, 48" in o["kernel"]:
+            return o["dram_read_bytes"] + o["dram_write_bytes"], o["kernel"]
+    return None, None
 
 
 def roofline(kern, peaks, path_tflops, per_gpu):
@@ -260,11 +271,12 @@ def roofline(kern, peaks, path_tflops, per_gpu):
            "peak_source": peaks["source"] + " (burst bf16/fp16 dense, MEASURED_PEAKS.json)", "achieved": None, "frac": None,
            "traffic": None}
     if kern is not None:
+        traffic, traffic_kernel = dominant_traffic()
         out.update({"achieved": kern["tflops"], "frac": kern["frac_of_burst_peak"], "kernel": kern["name"],
                     "us_per_launch": kern["us_per_launch"], "us_per_conv": kern["us_per_conv"],
                     "algorithmic_flops_per_launch": kern["flops_per_launch"],
-                    "traffic": DOMINANT_TRAFFIC_BYTES_B64 if kern["convs_per_launch"] == 8 and kern["batch"] == 64 else None,
-                    "traffic_source": "ncu --set full, profiles/r01_chain_full_details.csv (cold L2, isolated launch)",
+                    "traffic": traffic if kern["convs_per_launch"] == 8 and kern["batch"] == 64 else None,
+                    "traffic_source": "ncu --set full, profiles/dominant_traffic.json: %s (cold L2, isolated launch)" % traffic_kernel,
                     "hbm_bytes_min_per_launch": kern["hbm_bytes_min_per_conv"] * kern["convs_per_launch"]})
     out["path_3x3"] = {"achieved": round(path_tflops, 2), "peak": peaks["tflops_sustained"],
                        "frac": round(path_tflops / peaks["tflops_sustained"], 4),

@@ -120,6 +120,17 @@ class AdamArgs(C.Structure):
                 ("step", i32), ("reserved", i32), ("param", fp), ("grad", fp), ("exp_avg", fp), ("exp_avg_sq", fp)]
 
 
+class GenTargetArgs(C.Structure):
+    _fields_ = [("batch", i32), ("k", i32), ("h", i32), ("w", i32), ("tmp_size", i32), ("reserved", i32),
+                ("feat_stride_x", C.c_double), ("feat_stride_y", C.c_double),
+                ("joints", vp), ("joints_vis", vp), ("stamp", fp), ("joints_weight", fp), ("target", fp), ("target_weight", fp)]
+
+
+class PckArgs(C.Structure):
+    _fields_ = [("batch", i32), ("k", i32), ("h", i32), ("w", i32), ("thr", C.c_double),
+                ("pred", fp), ("target", fp), ("acc", vp), ("cnt", vp)]
+
+
 OP_STRUCT = {OP_TAPGEMM: TapGemmArgs, OP_STEM: StemArgs, OP_FUSE: FuseArgs, OP_RESIZE: ResizeArgs,
              OP_CHAN_ATT: ChanAttArgs, OP_POS_ATT: PosAttArgs, OP_DA_COMBINE: DaCombineArgs, OP_PRENET: PrenetArgs,
              OP_DECODE: DecodeArgs, OP_RASTER: RasterArgs, OP_CHAIN: TapGemmChainArgs}
@@ -129,7 +140,7 @@ EXPORTS = ["buctd_abi_version", "buctd_last_error", "buctd_create", "buctd_destr
            "buctd_tapgemm", "buctd_tapgemm_chain", "buctd_stem_conv", "buctd_hr_fuse", "buctd_cond_resize", "buctd_cond_resize3", "buctd_coam_channel_att",
            "buctd_coam_position_att", "buctd_da_combine", "buctd_prenet", "buctd_decode_heatmaps",
            "buctd_rasterize_condition", "buctd_flip_channels", "buctd_flip_merge", "buctd_joints_mse", "buctd_adam_step",
-           "buctd_act16_to_nchw32", "buctd_nchw32_to_act16", "buctd_plan_create",
+           "buctd_generate_target", "buctd_pck_accuracy", "buctd_act16_to_nchw32", "buctd_nchw32_to_act16", "buctd_plan_create",
            "buctd_plan_destroy", "buctd_plan_add", "buctd_plan_add_lane", "buctd_plan_num_lanes", "buctd_plan_instantiate",
            "buctd_plan_size", "buctd_plan_run", "buctd_plan_run_range"]
 
@@ -162,7 +173,8 @@ def load():
         lib.buctd_launch_count.argtypes = [vp]
         lib.buctd_create.argtypes = [C.c_int, C.POINTER(vp)]
         lib.buctd_destroy.argtypes = [vp]
-        for name in list(_IMMEDIATE.values()) + ["buctd_cond_resize3", "buctd_flip_channels", "buctd_flip_merge", "buctd_joints_mse", "buctd_adam_step"]:
+        for name in list(_IMMEDIATE.values()) + ["buctd_cond_resize3", "buctd_flip_channels", "buctd_flip_merge", "buctd_joints_mse", "buctd_adam_step",
+                                                     "buctd_generate_target", "buctd_pck_accuracy"]:
             getattr(lib, name).argtypes = [vp, vp, vp]
         lib.buctd_act16_to_nchw32.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
         lib.buctd_nchw32_to_act16.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

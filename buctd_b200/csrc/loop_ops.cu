@@ -176,4 +176,83 @@ int launch_adam(const buctd_adam_args& a, int sm_count, cudaStream_t st) {
   return BUCTD_OK;
 }
 
+// ---- training targets (JointsDataset.generate_target) ---------------------------------------------
+// One block per (crop, joint): zero the [H][W] plane and paste the clipped (6 sigma + 1)^2 stamp.  The stamp table is
+// computed by the caller with the reference's own float32 numpy expression, so the planes are bit-identical to the
+// reference's whatever libm the host has.
+__global__ void gen_target_kernel(buctd_gen_target_args a) {
+  const int bk = blockIdx.x, k = bk % a.k;
+  float* plane = a.target + (size_t)bk * a.h * a.w;
+  const double* j = a.joints + (size_t)bk * 3;
+  float wgt = (float)a.joints_vis[(size_t)bk * 3];
+  // mu = int(joint / feat_stride + 0.5): float64 arithmetic, truncation toward zero
+  const int mu_x = (int)(j[0] / a.feat_stride_x + 0.5), mu_y = (int)(j[1] / a.feat_stride_y + 0.5);
+  const int tmp = a.tmp_size, size = 2 * tmp + 1;
+  const int ul_x = mu_x - tmp, ul_y = mu_y - tmp, br_x = mu_x + tmp + 1, br_y = mu_y + tmp + 1;
+  const bool outside = ul_x >= a.w || ul_y >= a.h || br_x < 0 || br_y < 0;
+  if (outside) wgt = 0.f;
+  const bool paste = !outside && wgt > 0.5f;
+  const int x0 = max(0, ul_x), x1 = min(br_x, a.w), y0 = max(0, ul_y), y1 = min(br_y, a.h);
+  for (int i = threadIdx.x; i < a.h * a.w; i += blockDim.x) {
+    const int y = i / a.w, x = i - y * a.w;
+    float v = 0.f;
+    if (paste && x >= x0 && x < x1 && y >= y0 && y < y1) v = a.stamp[(y - ul_y) * size + (x - ul_x)];
+    plane[i] = v;
+  }
+  if (threadIdx.x == 0) a.target_weight[bk] = a.joints_weight != nullptr ? wgt * a.joints_weight[k] : wgt;
+}
+
+int launch_gen_target(const buctd_gen_target_args& a, cudaStream_t st) {
+  BUCTD_CHECK(a.joints && a.joints_vis && a.stamp && a.target && a.target_weight, BUCTD_ERR_INVALID, "gen_target: null pointer");
+  BUCTD_CHECK(a.batch >= 0 && a.k > 0 && a.h > 0 && a.w > 0 && a.tmp_size >= 0, BUCTD_ERR_INVALID, "gen_target: bad shape");
+  BUCTD_CHECK(a.feat_stride_x > 0 && a.feat_stride_y > 0, BUCTD_ERR_INVALID, "gen_target: bad feat_stride");
+  if (a.batch == 0) return BUCTD_OK;
+  gen_target_kernel<<<a.batch * a.k, 256, 0, st>>>(a);
+  BUCTD_CUDA(cudaGetLastError());
+  return BUCTD_OK;
+}
+
+// ---- PCK accuracy on arg-max coordinates (core.evaluate.accuracy after its two get_max_preds) ---------
+// One block, one thread per joint; the reference's float64 arithmetic without fused multiply-adds:
+//   dist = || pred / (h/10, w/10) - target / (h/10, w/10) ||   when target x > 1 and y > 1, else -1
+//   acc[1 + k] = #(dist < thr) / #(dist != -1)  (or -1), acc[0] = mean of the acc[1 + k] >= 0, cnt = how many.
+__global__ void pck_kernel(buctd_pck_args a) {
+  __shared__ double s_acc[BUCTD_MAX_FLIP_CHANNELS];
+  const int k = threadIdx.x;
+  if (k < a.k) {
+    const double nx = (double)a.h / 10.0, ny = (double)a.w / 10.0;     // norm = ones((B, 2)) * [h, w] / 10
+    int hit = 0, n = 0;
+    for (int b = 0; b < a.batch; ++b) {
+      const float* p = a.pred + ((size_t)b * a.k + k) * 2;
+      const float* t = a.target + ((size_t)b * a.k + k) * 2;
+      if (t[0] > 1.f && t[1] > 1.f) {
+        const double dx = __dsub_rn((double)p[0] / nx, (double)t[0] / nx), dy = __dsub_rn((double)p[1] / ny, (double)t[1] / ny);
+        const double d = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+        ++n;
+        if (d < a.thr) ++hit;
+      }
+    }
+    s_acc[k] = n > 0 ? (double)hit * 1.0 / (double)n : -1.0;
+    a.acc[1 + k] = s_acc[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sum = 0.0;
+    int cnt = 0;
+    for (int i = 0; i < a.k; ++i)
+      if (s_acc[i] >= 0.0) { sum = __dadd_rn(sum, s_acc[i]); ++cnt; }
+    a.acc[0] = cnt != 0 ? sum / (double)cnt : 0.0;
+    *a.cnt = cnt;
+  }
+}
+
+int launch_pck(const buctd_pck_args& a, cudaStream_t st) {
+  BUCTD_CHECK(a.pred && a.target && a.acc && a.cnt, BUCTD_ERR_INVALID, "pck_accuracy: null pointer");
+  BUCTD_CHECK(a.k > 0 && a.k <= BUCTD_MAX_FLIP_CHANNELS && a.batch >= 0, BUCTD_ERR_INVALID, "pck_accuracy: k %d out of range [1,%d]", a.k,
+              BUCTD_MAX_FLIP_CHANNELS);
+  pck_kernel<<<1, BUCTD_MAX_FLIP_CHANNELS, 0, st>>>(a);
+  BUCTD_CUDA(cudaGetLastError());
+  return BUCTD_OK;
+}
+
 }  // namespace buctd

@@ -280,6 +280,33 @@ typedef struct {
 } buctd_adam_args;
 int buctd_adam_step(buctd_ctx* ctx, const buctd_adam_args* args, buctd_stream stream);
 
+/* Training targets: target[b][k] = the (2 tmp_size + 1)^2 Gaussian stamp centred on
+ * mu = int(joint / feat_stride + 0.5), clipped to the [h][w] plane, pasted only when the (possibly zeroed) weight
+ * is > 0.5; target_weight[b][k] = joints_vis[b][k][0], zeroed when the stamp lies completely outside, times
+ * joints_weight[k] when given.  joints, joints_vis: float64 [B][K][3] (the reference keeps them in float64);
+ * stamp: float32 [(2 tmp_size + 1)^2] = exp(-((x - x0)^2 + (y - y0)^2) / (2 sigma^2)) as the caller's numpy computes
+ * it.  Replaces JointsDataset.generate_target, lib/dataset/JointsDataset.py:397-453 (CPU, DataLoader workers). */
+typedef struct {
+  int32_t batch, k, h, w, tmp_size, reserved;
+  double feat_stride_x, feat_stride_y;
+  const double* joints; const double* joints_vis; const float* stamp; const float* joints_weight; /* [K] or NULL */
+  float* target; float* target_weight;
+} buctd_gen_target_args;
+int buctd_generate_target(buctd_ctx* ctx, const buctd_gen_target_args* args, buctd_stream stream);
+
+/* PCK accuracy of core.evaluate.accuracy (lib/core/evaluate.py:14-70) on the arg-max coordinates of the output and
+ * target heat-maps (buctd_decode_heatmaps, post_process = 0, `coords`): acc float64 [1 + K] (acc[0] = average over
+ * the joints that have at least one labelled crop, acc[1 + k] = fraction of crops with normalised distance < thr,
+ * -1 when joint k is labelled nowhere), *cnt = number of such joints.  pred, target: float32 [B][K][2]; h, w: the
+ * heat-map size (normalisation (h/10, w/10) applied to (x, y) as the reference does). */
+typedef struct {
+  int32_t batch, k, h, w;
+  double thr;
+  const float* pred; const float* target;
+  double* acc; int32_t* cnt;
+} buctd_pck_args;
+int buctd_pck_accuracy(buctd_ctx* ctx, const buctd_pck_args* args, buctd_stream stream);
+
 /* Utility kernels used by the host mirror: zero-fill, and act16 -> nchw32 export for tests. */
 int buctd_act16_to_nchw32(buctd_ctx* ctx, int dtype, const void* act, int batch, int h, int w, int c, int cs,
                           float* out, buctd_stream stream);

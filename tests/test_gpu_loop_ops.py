@@ -141,3 +141,43 @@ def test_forward_flip_test_matches_manual_composition():
         o = net(x).cpu().numpy()
         of = net(torch.from_numpy(LO.flip_test_input(xn, function.COCO_FLIP_PAIRS, stacked=True)).cuda()).cpu().numpy()
     assert np.array_equal(out, LO.flip_test_merge(o, of, function.COCO_FLIP_PAIRS, True))
+
+
+@pytest.fixture(scope="module")
+def gt(golden_dir):
+    return np.load(os.path.join(golden_dir, "train_ops.npz"))
+
+
+@pytest.mark.parametrize("name", ["w48_384x288", "w32_256x192_s2", "odd_stride"])
+def test_generate_target_bit_exact(gt, name):
+    """device targets == the reference's JointsDataset.generate_target (golden written from the reference's own source)"""
+    from buctd_b200 import evaluate as E
+    img_w, img_h, hm_w, hm_h, sigma = gt["tg_%s_meta" % name].tolist()
+    jw = gt["tg_%s_jw" % name] if ("tg_%s_jw" % name) in gt.files else None
+    t, w = E.generate_target(gt["tg_%s_joints" % name], gt["tg_%s_vis" % name], (img_w, img_h), (hm_w, hm_h), sigma, jw)
+    assert t.is_cuda and t.dtype == torch.float32
+    assert np.array_equal(t.cpu().numpy(), gt["tg_%s_target" % name])
+    assert np.array_equal(w.cpu().numpy(), gt["tg_%s_weight" % name])
+
+
+def test_generate_target_random_vs_oracle():
+    from buctd_b200 import evaluate as E
+    from oracle import loop_oracle as LO
+    g = np.random.default_rng(77)
+    B, K = 32, 17
+    j = np.zeros((B, K, 3))
+    j[:, :, 0], j[:, :, 1] = g.uniform(-60, 350, (B, K)), g.uniform(-60, 450, (B, K))
+    v = np.repeat((g.uniform(size=(B, K, 1)) < 0.8).astype(np.float64), 3, axis=2)
+    t, w = E.generate_target(j, v, (288, 384), (72, 96), 3)
+    for b in range(B):
+        to, wo = LO.generate_target(j[b], v[b], (288, 384), (72, 96), 3)
+        assert np.array_equal(t[b].cpu().numpy(), to) and np.array_equal(w[b].cpu().numpy(), wo)
+
+
+def test_accuracy_bit_exact(gt):
+    from buctd_b200 import evaluate as E
+    acc, avg, cnt, pred = E.accuracy(gt["acc_output"], gt["acc_target"])
+    assert np.array_equal(acc, gt["acc_acc"]) and avg == float(gt["acc_avg"]) and cnt == int(gt["acc_cnt"])
+    assert np.array_equal(pred, gt["acc_pred"])
+    acc0, avg0, cnt0, _ = E.accuracy(gt["acc_output"][:2], np.zeros_like(gt["acc_target"][:2]))
+    assert np.array_equal(acc0, gt["acc0_acc"]) and avg0 == 0 and cnt0 == 0

@@ -53,3 +53,29 @@ def test_flip_back_live_reference(g):
     x = np.random.default_rng(5).standard_normal((2, 17, 6, 5)).astype(np.float32)
     pairs = g["flip_pairs"].tolist()
     assert np.array_equal(np.ascontiguousarray(T.flip_back(x.copy(), pairs)), LO.flip_back(x, pairs))
+
+
+@pytest.fixture(scope="module")
+def gt(golden_dir):
+    return np.load(os.path.join(golden_dir, "train_ops.npz"))
+
+
+@pytest.mark.parametrize("name", ["w48_384x288", "w32_256x192_s2", "odd_stride"])
+def test_generate_target_vs_reference_golden(gt, name):
+    """oracle restatement == the reference's JointsDataset.generate_target, bit for bit (clipped and outside stamps,
+    invisible joints, per-joint weights)"""
+    img_w, img_h, hm_w, hm_h, sigma = gt["tg_%s_meta" % name].tolist()
+    jw = gt["tg_%s_jw" % name] if ("tg_%s_jw" % name) in gt.files else None
+    j, v = gt["tg_%s_joints" % name], gt["tg_%s_vis" % name]
+    for b in range(j.shape[0]):
+        t, w = LO.generate_target(j[b], v[b], (img_w, img_h), (hm_w, hm_h), sigma, jw)
+        assert np.array_equal(t, gt["tg_%s_target" % name][b]) and np.array_equal(w, gt["tg_%s_weight" % name][b])
+    assert gt["tg_%s_weight" % name].min() == 0 and gt["tg_%s_target" % name].max() == 1.0
+
+
+def test_accuracy_vs_reference_golden(gt):
+    acc, avg, cnt, pred = LO.accuracy(gt["acc_output"], gt["acc_target"])
+    assert np.array_equal(acc, gt["acc_acc"]) and avg == float(gt["acc_avg"]) and cnt == int(gt["acc_cnt"])
+    assert np.array_equal(pred, gt["acc_pred"])
+    acc0, avg0, cnt0, _ = LO.accuracy(gt["acc_output"][:2], np.zeros_like(gt["acc_target"][:2]))
+    assert np.array_equal(acc0, gt["acc0_acc"]) and avg0 == float(gt["acc0_avg"]) and cnt0 == int(gt["acc0_cnt"]) == 0
