@@ -120,6 +120,12 @@ class AdamArgs(C.Structure):
                 ("step", i32), ("reserved", i32), ("param", fp), ("grad", fp), ("exp_avg", fp), ("exp_avg_sq", fp)]
 
 
+class CropWarpArgs(C.Structure):
+    _fields_ = [("batch", i32), ("h", i32), ("w", i32), ("out_channels", i32), ("c_off", i32), ("swap_rb", i32),
+                ("mean", C.c_float * 3), ("std", C.c_float * 3),
+                ("images", vp), ("img_h", vp), ("img_w", vp), ("img_stride", vp), ("inv_trans", vp), ("out", fp), ("out_u8", vp)]
+
+
 class GenTargetArgs(C.Structure):
     _fields_ = [("batch", i32), ("k", i32), ("h", i32), ("w", i32), ("tmp_size", i32), ("reserved", i32),
                 ("feat_stride_x", C.c_double), ("feat_stride_y", C.c_double),
@@ -140,7 +146,7 @@ EXPORTS = ["buctd_abi_version", "buctd_last_error", "buctd_create", "buctd_destr
            "buctd_tapgemm", "buctd_tapgemm_chain", "buctd_stem_conv", "buctd_hr_fuse", "buctd_cond_resize", "buctd_cond_resize3", "buctd_coam_channel_att",
            "buctd_coam_position_att", "buctd_da_combine", "buctd_prenet", "buctd_decode_heatmaps",
            "buctd_rasterize_condition", "buctd_flip_channels", "buctd_flip_merge", "buctd_joints_mse", "buctd_adam_step",
-           "buctd_generate_target", "buctd_pck_accuracy", "buctd_act16_to_nchw32", "buctd_nchw32_to_act16", "buctd_plan_create",
+           "buctd_crop_warp", "buctd_generate_target", "buctd_pck_accuracy", "buctd_act16_to_nchw32", "buctd_nchw32_to_act16", "buctd_plan_create",
            "buctd_plan_destroy", "buctd_plan_add", "buctd_plan_add_lane", "buctd_plan_num_lanes", "buctd_plan_instantiate",
            "buctd_plan_size", "buctd_plan_run", "buctd_plan_run_range"]
 
@@ -174,7 +180,7 @@ def load():
         lib.buctd_create.argtypes = [C.c_int, C.POINTER(vp)]
         lib.buctd_destroy.argtypes = [vp]
         for name in list(_IMMEDIATE.values()) + ["buctd_cond_resize3", "buctd_flip_channels", "buctd_flip_merge", "buctd_joints_mse", "buctd_adam_step",
-                                                     "buctd_generate_target", "buctd_pck_accuracy"]:
+                                                     "buctd_crop_warp", "buctd_generate_target", "buctd_pck_accuracy"]:
             getattr(lib, name).argtypes = [vp, vp, vp]
         lib.buctd_act16_to_nchw32.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
         lib.buctd_nchw32_to_act16.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -384,6 +384,9 @@ BUCTD_API int buctd_joints_mse(buctd_ctx* c, const buctd_joints_mse_args* a, buc
 BUCTD_API int buctd_adam_step(buctd_ctx* c, const buctd_adam_args* a, buctd_stream s) {
   return simple_call(c, a, 1, [&](const buctd_adam_args& x) { return launch_adam(x, c->sm_count, static_cast<cudaStream_t>(s)); });
 }
+BUCTD_API int buctd_crop_warp(buctd_ctx* c, const buctd_crop_warp_args* a, buctd_stream s) {
+  return simple_call(c, a, 1, [&](const buctd_crop_warp_args& x) { return launch_crop_warp(x, static_cast<cudaStream_t>(s)); });
+}
 BUCTD_API int buctd_generate_target(buctd_ctx* c, const buctd_gen_target_args* a, buctd_stream s) {
   return simple_call(c, a, 1, [&](const buctd_gen_target_args& x) { return launch_gen_target(x, static_cast<cudaStream_t>(s)); });
 }

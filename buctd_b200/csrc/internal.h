@@ -98,6 +98,7 @@ int launch_joints_mse(const buctd_joints_mse_args& a, cudaStream_t st);
 int launch_adam(const buctd_adam_args& a, int sm_count, cudaStream_t st);
 int launch_gen_target(const buctd_gen_target_args& a, cudaStream_t st);
 int launch_pck(const buctd_pck_args& a, cudaStream_t st);
+int launch_crop_warp(const buctd_crop_warp_args& a, cudaStream_t st);
 struct ChainLaunch;
 int tapgemm_chain_init_device();
 int tapgemm_chain_prepare(const buctd_tapgemm_chain_args& a, ChainLaunch* C, int sm_count, unsigned int* counter);

@@ -255,4 +255,56 @@ int launch_pck(const buctd_pck_args& a, cudaStream_t st) {
   return BUCTD_OK;
 }
 
+// ---- crop warp + normalise (cv2.warpAffine INTER_LINEAR, BORDER_CONSTANT 0; ToTensor; Normalize) -------------
+// OpenCV's 8-bit affine warp is fixed-point (imgwarp.cpp, WarpAffineInvoker + remapBilinear): the FORWARD matrix is
+// inverted in float64, source coordinates are built in 1/1024 px (round half even) + 16, reduced to 1/32 px, and the
+// four taps are combined with integer weights (32-fx)(32-fy)*32 ... that sum to 2^15, + 2^14, >> 15.  Restated here
+// operation for operation (no fused multiply-adds), so the 8-bit crop is bit-identical to cv2.warpAffine's, and the
+// float image after x/255, (x - mean)/std is bit-identical to torchvision's ToTensor + Normalize.
+__device__ __forceinline__ int cv_round(double v) {           // cv::saturate_cast<int>(double): lrint + saturation
+  v = fmin(fmax(v, -2147483648.0), 2147483647.0);
+  return __double2int_rn(v);
+}
+__global__ void crop_warp_kernel(buctd_crop_warp_args a) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+  if (x >= a.w) return;
+  const double* m = a.inv_trans + (size_t)b * 6;
+  const int h_img = a.img_h[b], w_img = a.img_w[b];
+  const long long stride = a.img_stride[b];
+  const uint8_t* img = a.images[b];
+  const int X0 = cv_round(__dmul_rn(__dadd_rn(__dmul_rn(m[1], (double)y), m[2]), 1024.0)) + 16;
+  const int Y0 = cv_round(__dmul_rn(__dadd_rn(__dmul_rn(m[4], (double)y), m[5]), 1024.0)) + 16;
+  const int X = (X0 + cv_round(__dmul_rn(__dmul_rn(m[0], (double)x), 1024.0))) >> 5;
+  const int Y = (Y0 + cv_round(__dmul_rn(__dmul_rn(m[3], (double)x), 1024.0))) >> 5;
+  const int sx = X >> 5, sy = Y >> 5, fx = X & 31, fy = Y & 31;
+  const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
+  const bool x0 = sx >= 0 && sx < w_img, x1 = sx + 1 >= 0 && sx + 1 < w_img;
+  const bool y0 = sy >= 0 && sy < h_img, y1 = sy + 1 >= 0 && sy + 1 < h_img;
+  const uint8_t* r0 = img + (long long)sy * stride + (long long)sx * 3;
+  const uint8_t* r1 = r0 + stride;
+  float* out = a.out + ((size_t)b * a.out_channels + a.c_off) * a.h * a.w + (size_t)y * a.w + x;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int p00 = (y0 && x0) ? r0[c] : 0, p01 = (y0 && x1) ? r0[3 + c] : 0;
+    const int p10 = (y1 && x0) ? r1[c] : 0, p11 = (y1 && x1) ? r1[3 + c] : 0;
+    const int v = (p00 * w00 + p01 * w01 + p10 * w10 + p11 * w11 + (1 << 14)) >> 15;
+    const int oc = a.swap_rb ? 2 - c : c;
+    if (a.out_u8 != nullptr) a.out_u8[(((size_t)b * a.h + y) * a.w + x) * 3 + oc] = (uint8_t)v;
+    out[(size_t)oc * a.h * a.w] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.f), a.mean[oc]), a.std[oc]);
+  }
+}
+
+int launch_crop_warp(const buctd_crop_warp_args& a, cudaStream_t st) {
+  BUCTD_CHECK(a.images && a.img_h && a.img_w && a.img_stride && a.inv_trans && a.out, BUCTD_ERR_INVALID, "crop_warp: null pointer");
+  BUCTD_CHECK(a.batch >= 0 && a.h > 0 && a.w > 0 && a.out_channels >= 3 && a.c_off >= 0 && a.c_off + 3 <= a.out_channels,
+              BUCTD_ERR_INVALID, "crop_warp: bad shape (batch %d, %dx%d, channels %d, c_off %d)", a.batch, a.h, a.w, a.out_channels, a.c_off);
+  BUCTD_CHECK(a.std[0] != 0.f && a.std[1] != 0.f && a.std[2] != 0.f, BUCTD_ERR_INVALID, "crop_warp: zero std");
+  if (a.batch == 0) return BUCTD_OK;
+  BUCTD_CHECK(a.batch <= 65535 && a.h <= 65535, BUCTD_ERR_INVALID, "crop_warp: batch / height above the grid limit");
+  dim3 grid((a.w + 127) / 128, a.h, a.batch);
+  crop_warp_kernel<<<grid, 128, 0, st>>>(a);
+  BUCTD_CUDA(cudaGetLastError());
+  return BUCTD_OK;
+}
+
 }  // namespace buctd

@@ -226,7 +226,7 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
   constexpr int TR = DXF ? kDxfRows : kBlockM;                       // output rows per accumulator tile
   constexpr int ASTRIDE = DXF ? dxf_acc_stride<BN>() : acc_stride<BN>();
   constexpr int NACC = DXF ? dxf_nacc<BN>() : slab_nacc<BN>();
-  static_assert(MSUB <= NACC, "a super-tile needs MSUB accumulators at once");
+  static_assert(DXF || MSUB <= NACC, "a super-tile needs MSUB accumulators at once");
   uint8_t* slabs = smem;
   uint8_t* wbuf = slabs + (size_t)sp.sa * sp.slab_bytes;
   uint8_t* stage = wbuf + (size_t)sp.w_tiles * kWTileBytes;
@@ -357,6 +357,37 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
         if (sp.w_resident) { mbar_wait(&w_full[0], (uint32_t)l & 1u); }
         tc_fence_after();
         for (int k = 0; k < my_items; ++k) {
+          if constexpr (DXF) {
+            // dx-fused: one slab (one K chunk, resident weights), sub-tile-major.  A sub-tile takes its accumulator
+            // when its turn comes and is handed to the epilogue after its own 3 x ksteps MMAs, so a super-tile may
+            // have as many sub-tiles as fit the slab ring, not as many as there are TMEM slots (3 at N = 144).
+            mbar_wait(&slab_full[slot], slot_ph);
+            tc_fence_after();
+            const uint32_t slab_addr = slab0_addr + slot * (uint32_t)sp.slab_bytes;
+            const int ksteps = min(64, p0.k16) >> 4;
+#pragma unroll
+            for (int j = 0; j < MSUB; ++j) {
+              mbar_wait(&acc_empty[aslot], aph);
+              tc_fence_after();
+              const uint32_t dj = tmem_base + aslot * ASTRIDE;
+              // one MMA per kernel row dy: B = the three dx weight tiles of that row stacked along N (they are
+              // contiguous in the resident weight buffer), A = the centre-column view of the slab, fetched ONCE
+              // for the three taps.  Accumulator columns [dx*BN, +BN) hold sum_dy A[g+(dy-1)wp] W(dy,dx) for the
+              // tile row g; the epilogue adds the dx = 0 block of row g-1 and the dx = 2 block of row g+1.
+#pragma unroll
+              for (int dy = 0; dy < 3; ++dy) {
+                if (cp.debug & 4) break;
+                const uint64_t bdesc = umma_desc_sw128(wbuf_addr + (uint32_t)(dy * 3) * kWTileBytes);
+                const uint64_t adesc = umma_desc_sw128(slab_addr + (uint32_t)(dy * p0.wp + j * TR) * 128);
+                mma_ksteps_rt<BN>(ksteps, dj, adesc, bdesc, idesc, dy == 0 ? 0u : 1u);
+              }
+              tc_commit(&acc_full[aslot]);
+              if (++aslot == NACC) { aslot = 0; aph ^= 1; }
+            }
+            tc_commit(&slab_empty[slot]);
+            if (++slot == (uint32_t)sp.sa) { slot = 0; slot_ph ^= 1; }
+            continue;
+          }
           uint32_t d[MSUB], dslot[MSUB];
 #pragma unroll
           for (int j = 0; j < MSUB; ++j) {
@@ -372,21 +403,7 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
             tc_fence_after();
             const uint32_t slab_addr = slab0_addr + slot * (uint32_t)sp.slab_bytes;
             const int ksteps = min(64, p0.k16 - kc * 64) >> 4;
-            if constexpr (DXF) {
-              // one MMA per kernel row dy: B = the three dx weight tiles of that row stacked along N (they are
-              // contiguous in the resident weight buffer), A = the centre-column view of the slab, fetched ONCE
-              // for the three taps.  Accumulator columns [dx*BN, +BN) hold sum_dy A[g+(dy-1)wp] W(dy,dx) for the
-              // tile row g; the epilogue adds the dx = 0 block of row g-1 and the dx = 2 block of row g+1.
-#pragma unroll
-              for (int dy = 0; dy < 3; ++dy) {
-                if (cp.debug & 4) break;
-                const uint64_t bdesc = umma_desc_sw128(wbuf_addr + (uint32_t)(dy * 3) * kWTileBytes);
-                const uint64_t adesc0 = umma_desc_sw128(slab_addr + (uint32_t)(dy * p0.wp) * 128);
-#pragma unroll
-                for (int j = 0; j < MSUB; ++j)
-                  mma_ksteps_rt<BN>(ksteps, d[j], adesc0 + (uint64_t)(j * (TR * 128 / 16)), bdesc, idesc, dy == 0 ? 0u : 1u);
-              }
-            } else {
+            {
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
               if (t < p0.ntaps) {
@@ -623,9 +640,7 @@ static int chain_set_attr() {
     BUCTD_CUDA(cudaFuncSetAttribute(tapgemm_chain_kernel<T, BN, MSUB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
   }
   if constexpr (BN <= 64) {
-    if constexpr (MSUB <= dxf_nacc<BN>()) {
-      BUCTD_CUDA(cudaFuncSetAttribute(tapgemm_chain_kernel<T, BN, MSUB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    }
+    BUCTD_CUDA(cudaFuncSetAttribute(tapgemm_chain_kernel<T, BN, MSUB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
   }
   return BUCTD_OK;
 }
@@ -653,8 +668,6 @@ int tapgemm_chain_init_device() {
   return rc ? rc : chain_set_attrs<__nv_bfloat16>();
 }
 
-static int dxf_nacc_of(int bn) { return bn == 32 ? dxf_nacc<32>() : bn == 48 ? dxf_nacc<48>() : dxf_nacc<64>(); }
-
 // Re-plan a chain whose layers qualify for the dx-fused kernel: 126-row tiles, slab = msub*126 + 2*halo rows, four
 // stage buffers, resident weights.  Returns false when the shape does not qualify (the regular plan stays).
 // BUCTD_DXF=0 disables it, BUCTD_DXF=2 also admits C = 64; BUCTD_DXF_MSUB pins the super-tile size (default 1).
@@ -667,29 +680,41 @@ static bool chain_plan_dxf(const buctd_tapgemm_args& f, const TapGemmLaunch& L, 
   const bool allow64 = e != nullptr && atoi(e) == 2;
   if (f.ntaps != 9 || L.kp.num_kc != 1 || !(bn == 32 || bn == 48 || (bn == 64 && allow64)) || f.n_alloc != bn || f.n != bn || !L.sp.w_resident)
     return false;
-  const int nacc = dxf_nacc_of(bn);
+  // super-tile: the slab of two 126-row tiles carries 1.59x its rows through TMA instead of 2.17x (one tile) --
+  // measured 32.5 / 33.1 us (C = 48 @96x72) and 22.4 / 23.8 us (C = 32 @96x72) -- as long as the four stage
+  // buffers still fit beside it; three tiles only fit with two stage buffers (41.4 us).  BUCTD_DXF_MSUB pins it.
   const char* em = getenv("BUCTD_DXF_MSUB");
-  int msub = em ? atoi(em) : 1;       // measured: 1 beats 2 at N = 96 and N = 144 (13.7 / 14.1 and 32.6 / 42.4 us)
-  if (msub < 1) msub = 1;
-  if (msub > nacc) msub = nacc;
-  if (msub > 4) msub = 4;
+  const char* eb = getenv("BUCTD_DXF_STAGES");
   SlabParams c = L.sp;
   const int halo = f.out_w + 2;
-  const int rows = msub * kDxfRows + 2 * halo;
-  const int nboxes = ceil_div(rows, 256);
-  const int box_rows = (ceil_div(rows, nboxes) + 7) / 8 * 8;
-  const long long slab = (long long)nboxes * box_rows * 128;
   const long long total_w = 9ll * bn * 128;
   const long long fixed = 1024 + 2 * bn * 4 + kDxfXchFloats * 4 + 512;
-  int sa = 0;
-  long long need = 0;
-  const char* eb = getenv("BUCTD_DXF_STAGES");
-  const int se = eb && atoi(eb) == 2 ? 2 : 4;
-  for (int csa = 3; csa >= 2 && sa == 0; --csa) {
-    need = fixed + (long long)se * kEpiBlockBytes + csa * slab + total_w;
-    if (need <= kSmemBudget) sa = csa;
+  int msub = 0, sa = 0, se = 0, nboxes = 0, box_rows = 0;
+  long long slab = 0, need = 0;
+  auto plan = [&](int m, int want_se) {
+    const int rows = m * kDxfRows + 2 * halo;
+    const int nb = ceil_div(rows, 256);
+    const int br = (ceil_div(rows, nb) + 7) / 8 * 8;
+    const long long sl = (long long)nb * br * 128;
+    for (int csa = 3; csa >= 2; --csa) {
+      const long long nd = fixed + (long long)want_se * kEpiBlockBytes + csa * sl + total_w;
+      if (nd <= kSmemBudget) {
+        msub = m; sa = csa; se = want_se; nboxes = nb; box_rows = br; slab = sl; need = nd;
+        return true;
+      }
+    }
+    return false;
+  };
+  if (em != nullptr) {
+    int m = atoi(em);
+    m = m < 1 ? 1 : m > 4 ? 4 : m;
+    if (!(eb && atoi(eb) == 2) && plan(m, 4)) {}
+    else if (!plan(m, 2)) return false;
+  } else if (eb && atoi(eb) == 2) {
+    if (!plan(2, 2) && !plan(1, 2)) return false;
+  } else if (!plan(2, 4) && !plan(1, 4) && !plan(1, 2)) {
+    return false;
   }
-  if (sa == 0) return false;
   const long long supers = (f.m_rows + (long long)msub * kDxfRows - 1) / ((long long)msub * kDxfRows);
   c.msub = msub; c.halo = halo; c.nboxes = nboxes; c.box_rows = box_rows; c.slab_bytes = (int)slab;
   c.sa = sa; c.sw = 0; c.stage_bufs = se; c.w_resident = 1; c.w_tiles = 9;
@@ -777,9 +802,7 @@ template <typename T, int BN, int MSUB>
 static void chain_launch_one(const ChainLaunch& C, cudaStream_t st) {
   if (C.dxf) {
     if constexpr (BN <= 64) {
-      if constexpr (MSUB <= dxf_nacc<BN>()) {
-        launch_pdl(tapgemm_chain_kernel<T, BN, MSUB, true>, C.grid, dim3(kChainThreads), C.sp.smem_bytes, st, C.cp, C.kp, C.sp);
-      }
+      launch_pdl(tapgemm_chain_kernel<T, BN, MSUB, true>, C.grid, dim3(kChainThreads), C.sp.smem_bytes, st, C.cp, C.kp, C.sp);
     }
     return;
   }

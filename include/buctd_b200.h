@@ -280,6 +280,25 @@ typedef struct {
 } buctd_adam_args;
 int buctd_adam_step(buctd_ctx* ctx, const buctd_adam_args* args, buctd_stream stream);
 
+/* Crop warp + normalise: for every crop b the 8-bit source image images[b]
+ * ([img_h][img_w][3], row pitch img_stride bytes, device memory) is warped to [h][w] exactly as
+ * cv2.warpAffine(img, trans, (w, h), flags=cv2.INTER_LINEAR) does (fixed-point bilinear, constant border 0), then
+ * ToTensor + Normalize: out[b][c_off + c][y][x] = (v / 255 - mean[c]) / std[c] in float32 (nchw32, out_channels
+ * planes per crop: the condition planes of the same tensor are written by buctd_rasterize_condition).
+ * inv_trans: float64 [B][6], the INVERSE of the reference's `trans` (cv2 inverts the forward matrix itself:
+ * cv::invertAffineTransform arithmetic, done once per crop by the caller, buctd_b200/crop.py).  swap_rb != 0 reads
+ * BGR and writes RGB planes (cv2.cvtColor(..., COLOR_BGR2RGB) before the warp, DATASET.COLOR_RGB).  out_u8 (optional):
+ * the 8-bit crop [B][h][w][3] itself.  Replaces cv2.warpAffine + transforms.ToTensor + Normalize,
+ * lib/dataset/JointsDataset.py:262-288, tools/inference.py:86-107 (CPU, DataLoader workers). */
+typedef struct {
+  int32_t batch, h, w, out_channels, c_off, swap_rb;
+  float mean[3], std[3];
+  const uint8_t* const* images; const int32_t* img_h; const int32_t* img_w; const int64_t* img_stride;
+  const double* inv_trans;
+  float* out; uint8_t* out_u8;
+} buctd_crop_warp_args;
+int buctd_crop_warp(buctd_ctx* ctx, const buctd_crop_warp_args* args, buctd_stream stream);
+
 /* Training targets: target[b][k] = the (2 tmp_size + 1)^2 Gaussian stamp centred on
  * mu = int(joint / feat_stride + 0.5), clipped to the [h][w] plane, pasted only when the (possibly zeroed) weight
  * is > 0.5; target_weight[b][k] = joints_vis[b][k][0], zeroed when the stamp lies completely outside, times
