@@ -77,7 +77,9 @@ def warp_crops(images, trans, output_size, out=None, c_off=0, out_channels=3, me
     if out is None:
         out = torch.zeros(B, out_channels, H, W, dtype=torch.float32, device=dev)
     assert out.is_contiguous() and out.shape[0] == B and out.shape[2] == H and out.shape[3] == W
-    inv = np.stack([_invert(t) for t in np.asarray(trans, np.float64).reshape(B, 6)]) if B else np.zeros((0, 6))
+    if B == 0:
+        return (out, torch.empty(0, H, W, 3, dtype=torch.uint8, device=dev)) if want_u8 else out
+    inv = np.stack([_invert(t) for t in np.asarray(trans, np.float64).reshape(B, 6)])
     ptrs = torch.tensor([im.data_ptr() for im in images], dtype=torch.int64).to(dev)
     hs = torch.tensor([im.shape[0] for im in images], dtype=torch.int32).to(dev)
     ws = torch.tensor([im.shape[1] for im in images], dtype=torch.int32).to(dev)

@@ -203,6 +203,7 @@ __global__ void gen_target_kernel(buctd_gen_target_args a) {
 }
 
 int launch_gen_target(const buctd_gen_target_args& a, cudaStream_t st) {
+  if (a.batch == 0) return BUCTD_OK;
   BUCTD_CHECK(a.joints && a.joints_vis && a.stamp && a.target && a.target_weight, BUCTD_ERR_INVALID, "gen_target: null pointer");
   BUCTD_CHECK(a.batch >= 0 && a.k > 0 && a.h > 0 && a.w > 0 && a.tmp_size >= 0, BUCTD_ERR_INVALID, "gen_target: bad shape");
   BUCTD_CHECK(a.feat_stride_x > 0 && a.feat_stride_y > 0, BUCTD_ERR_INVALID, "gen_target: bad feat_stride");
@@ -295,11 +296,11 @@ __global__ void crop_warp_kernel(buctd_crop_warp_args a) {
 }
 
 int launch_crop_warp(const buctd_crop_warp_args& a, cudaStream_t st) {
+  if (a.batch == 0) return BUCTD_OK;
   BUCTD_CHECK(a.images && a.img_h && a.img_w && a.img_stride && a.inv_trans && a.out, BUCTD_ERR_INVALID, "crop_warp: null pointer");
   BUCTD_CHECK(a.batch >= 0 && a.h > 0 && a.w > 0 && a.out_channels >= 3 && a.c_off >= 0 && a.c_off + 3 <= a.out_channels,
               BUCTD_ERR_INVALID, "crop_warp: bad shape (batch %d, %dx%d, channels %d, c_off %d)", a.batch, a.h, a.w, a.out_channels, a.c_off);
   BUCTD_CHECK(a.std[0] != 0.f && a.std[1] != 0.f && a.std[2] != 0.f, BUCTD_ERR_INVALID, "crop_warp: zero std");
-  if (a.batch == 0) return BUCTD_OK;
   BUCTD_CHECK(a.batch <= 65535 && a.h <= 65535, BUCTD_ERR_INVALID, "crop_warp: batch / height above the grid limit");
   dim3 grid((a.w + 127) / 128, a.h, a.batch);
   crop_warp_kernel<<<grid, 128, 0, st>>>(a);
