@@ -129,7 +129,8 @@ def get_cfg_defaults() -> CfgNode:
                   "GAMMA2": 0.0, "BEGIN_EPOCH": 0, "END_EPOCH": 140, "BATCH_SIZE_PER_GPU": 32,
                   "SHUFFLE": True},
         "TEST": {"BATCH_SIZE_PER_GPU": 32, "FLIP_TEST": False, "POST_PROCESS": False,
-                 "SHIFT_HEATMAP": False, "MODEL_FILE": "", "SCALE_THRE": 1.25},
+                 "SHIFT_HEATMAP": False, "MODEL_FILE": "", "SCALE_THRE": 1.25,
+                 "IN_VIS_THRE": 0.0},
         "DEBUG": {"DEBUG": False},
     })
 

@@ -45,6 +45,12 @@ def get_affine_transform(center, scale, rot, output_size, shift=np.array([0, 0],
     return cv2.getAffineTransform(np.float32(src), np.float32(dst))
 
 
+def affine_transform(pt, t):
+    """lib/utils/transforms.py:121-124"""
+    new_pt = np.array([pt[0], pt[1], 1.]).T
+    return np.dot(t, new_pt)[:2]
+
+
 def _invert(trans):
     # cv::invertAffineTransform as cv2.warpAffine applies it to the forward matrix (float64, D = 1 / det)
     m = np.array(trans, np.float64).reshape(6).copy()

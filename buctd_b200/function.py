@@ -9,7 +9,9 @@ from typing import List, Optional, Sequence
 
 import torch
 
-from . import condition, inference, transforms
+import numpy as np
+
+from . import condition, crop, inference, results, transforms
 
 COCO_FLIP_PAIRS = [[1, 2], [3, 4], [5, 6], [7, 8], [9, 10], [11, 12], [13, 14], [15, 16]]   # lib/dataset/coco.py:66-67
 
@@ -62,3 +64,73 @@ def iterative_refine(config, model, input: torch.Tensor, passes: int = 3, center
             kp = (coords * stride).contiguous()
             condition.rasterize_condition(kp, H, W, cond_mode, out=x, c_off=3)
     return outs if return_all else outs[-1]
+
+
+@torch.no_grad()
+def build_inputs_from_results(config, images, image_index, db, cond_mode: str = "stacked"):
+    """The model input of one refinement pass, built on the device from the previous pass's results the way the
+    reference's dataset does (lib/dataset/JointsDataset.py:217-288, 314-326 at test time: no flip, rot 0):
+    crop matrix from (center, scale) -> cv2.warpAffine + ToTensor + Normalize for the RGB planes, the previous
+    keypoints mapped into the crop (affine_transform) and rasterised for the condition planes.
+    images: list of CUDA uint8 [h, w, 3] RGB images; image_index[n] = which image person n lives in;
+    db: ``results.load_coco_pose_results`` entries.  Returns (x [N, 3 + Cc, H, W], center [N, 2], scale [N, 2], trans)."""
+    W, H = int(config.MODEL.IMAGE_SIZE[0]), int(config.MODEL.IMAGE_SIZE[1])
+    N = len(db)
+    K = db[0]["cond_joints"].shape[0] if N else int(config.MODEL.NUM_JOINTS)
+    cc = K if cond_mode == "stacked" else 3
+    dev = images[0].device
+    trans = np.zeros((N, 2, 3))
+    kp = np.zeros((N, K, 3), np.float32)
+    for n, e in enumerate(db):
+        trans[n] = crop.get_affine_transform(e["center"], e["scale"], 0, (W, H))
+        for i in range(K):
+            if e["cond_joints_vis"][i, 0] > 0.0:
+                # the rasteriser truncates toward zero like the reference's int(); truncating the float64 value here
+                # keeps that exact through the float32 hand-over
+                kp[n, i, 0:2] = np.trunc(crop.affine_transform(e["cond_joints"][i, 0:2], trans[n]))
+            else:
+                kp[n, i, 0:2] = np.trunc(e["cond_joints"][i, 0:2])
+    x = torch.zeros(N, 3 + cc, H, W, dtype=torch.float32, device=dev)
+    crop.warp_crops([images[image_index[n]] for n in range(N)], trans, (W, H), out=x, c_off=0)
+    condition.rasterize_condition(torch.from_numpy(kp).to(dev), H, W, cond_mode, out=x, c_off=3)
+    center = torch.from_numpy(np.stack([e["center"] for e in db]).astype(np.float32)).to(dev) if N else torch.zeros(0, 2, device=dev)
+    scale = torch.from_numpy(np.stack([e["scale"] for e in db]).astype(np.float32)).to(dev) if N else torch.zeros(0, 2, device=dev)
+    return x, center, scale, trans
+
+
+@torch.no_grad()
+def iterative_refine_recrop(config, model, images, image_ids, image_paths, proposals, passes: int = 3, cond_mode: str = "stacked",
+                            flip_pairs=COCO_FLIP_PAIRS, bu_bbox_margin=None, in_vis_thre=None):
+    """BASELINE.json configs[3] with the REFERENCE's semantics (SURVEY.md 8d "Config 4"): between passes the results go
+    through the COCO results list (rescored), the person box is re-derived from the new keypoints
+    (``_load_coco_pose_results``: min / max of the non-zero keypoints +- BU_BBOX_MARGIN, clipped, padded to the aspect
+    ratio, x SCALE_THRE) and the image is re-cropped -- the reference does this offline through a JSON file
+    (scripts/test/test_BUCTD_COAM_gen_sample.sh:21); here the list stays in memory and the crops never leave the GPU.
+    images: dict image_id -> CUDA uint8 [h, w, 3] RGB; proposals: a results list (``image_id``, ``keypoints`` [K*3],
+    ``score``) from the bottom-up model.  Returns the results list of every pass."""
+    K = int(config.MODEL.NUM_JOINTS)
+    W, H = int(config.MODEL.IMAGE_SIZE[0]), int(config.MODEL.IMAGE_SIZE[1])
+    margin = config.DATASET.BU_BBOX_MARGIN if bu_bbox_margin is None else bu_bbox_margin
+    thre = (config.TEST.get("IN_VIS_THRE", 0.0) if hasattr(config.TEST, "get") else getattr(config.TEST, "IN_VIS_THRE", 0.0)) \
+        if in_vis_thre is None else in_vis_thre
+    ids = sorted(images)
+    imgs = [images[i] for i in ids]
+    shapes = {i: (int(images[i].shape[0]), int(images[i].shape[1])) for i in ids}
+    scale_thre = getattr(config.TEST, "SCALE_THRE", 1.25)
+    cur, history = proposals, []
+    for _ in range(passes):
+        db = results.load_coco_pose_results(cur, shapes, K, margin, W * 1.0 / H, 200, scale_thre)
+        index = [ids.index(e["image_id"]) for e in db]
+        x, center, scale, _ = build_inputs_from_results(config, imgs, index, db, cond_mode)
+        preds, maxvals = validate_batch(config, model, x, center, scale, flip_pairs)
+        all_preds = torch.cat([preds, maxvals], 2).cpu().numpy()
+        c, s = center.cpu().numpy(), scale.cpu().numpy()
+        boxes = np.zeros((len(db), 7))
+        boxes[:, 0:2], boxes[:, 2:4] = c, s
+        boxes[:, 4] = np.prod(s * 200, 1)
+        boxes[:, 5] = [e["score"] for e in db]
+        boxes[:, 6] = [r.get("annotation_id", -1) for r in cur]
+        cur = results.coco_keypoint_results(all_preds, boxes, [e["image_id"] for e in db],
+                                            [image_paths[e["image_id"]] for e in db], thre)
+        history.append(cur)
+    return history
