@@ -7,14 +7,16 @@
 // running across layers, and there is NO grid-wide barrier between them: the dependency of a 3x3 convolution is local,
 // super-tile s of layer l+1 reads rows of the super-tiles s-1, s, s+1 of layer l (halo W+2 < 128 rows) and, as residual,
 // super-tile s of an earlier layer.  Every layer has the same geometry, hence the same (super-tile -> CTA) assignment.
-// The DMA warp publishes flag[l][s] (+1 per N tile) once the TMA stores of that work item are complete; the producer
-// thread waits for the three flags of the previous layer before it loads a slab.  CTAs drift apart freely: a slow CTA
-// only delays its neighbours.  Writes are safe by the same argument: whoever overwrites rows of super-tile s at layer
+// flag[l][s] is bumped (+1 per N tile) once the TMA stores of that work item are complete -- the DMA thread hands the
+// index to the publisher warp, which owns the gpu-scope release -- and the producer warp polls the flags of the previous
+// layer (all lanes, ten items ahead) before lane 0 loads a slab.  CTAs drift apart freely: a slow CTA only delays its
+// neighbours.  Writes are safe by the same argument: whoever overwrites rows of super-tile s at layer
 // l+1 has waited for every layer-l reader of those rows (buffers rotate as in a BasicBlock: in -> tmp -> out).
 // All CTAs are co-resident by construction (grid <= SM count, one CTA per SM) and dependencies only point to lower
 // layers, so the spins cannot deadlock; they trap after ~4 s instead of hanging the device.
 //
-// Same roles and pipeline as tapgemm_slab_kernel (tapgemm.cu); staged (TMA store) epilogue only.
+// Same roles and pipeline as tapgemm_slab_kernel (tapgemm.cu) plus the publisher warp (12 warps); staged (TMA store)
+// epilogue only.  Layers with C <= 48 run the dx-fused plan (DXF, below): one N = 3C MMA per kernel row.
 // Replaces the conv1/bn1/relu/conv2/bn2/+residual/relu sequences of HighResolutionModule._make_one_branch,
 // lib/models/pose_hrnet_coam.py:31-60, 142-165, 254-255.
 #include "common.cuh"
@@ -403,7 +405,6 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
             tc_fence_after();
             const uint32_t slab_addr = slab0_addr + slot * (uint32_t)sp.slab_bytes;
             const int ksteps = min(64, p0.k16 - kc * 64) >> 4;
-            {
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
               if (t < p0.ntaps) {
@@ -427,7 +428,6 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
                   if (++ws == (uint32_t)sp.sw) { ws = 0; ws_ph ^= 1; }
                 }
               }
-            }
             }
             tc_commit(&slab_empty[slot]);
             if (++slot == (uint32_t)sp.sa) { slot = 0; slot_ph ^= 1; }
