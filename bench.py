@@ -407,10 +407,17 @@ def main():
     ap.add_argument("--ref-crops", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # Exactly ONE line on stdout: libraries that write to file descriptor 1 themselves (NCCL prints its version banner
+    # there when a communicator is created) are sent to stderr; the JSON line goes to the original stdout.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_native(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
