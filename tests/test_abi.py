@@ -35,7 +35,9 @@ def test_struct_fields_match_header():
     pairs = {"buctd_tapgemm_args": L.TapGemmArgs, "buctd_stem_args": L.StemArgs, "buctd_fuse_args": L.FuseArgs,
              "buctd_resize_args": L.ResizeArgs, "buctd_chan_att_args": L.ChanAttArgs, "buctd_pos_att_args": L.PosAttArgs,
              "buctd_da_combine_args": L.DaCombineArgs, "buctd_prenet_args": L.PrenetArgs, "buctd_decode_args": L.DecodeArgs,
-             "buctd_raster_args": L.RasterArgs}
+             "buctd_raster_args": L.RasterArgs, "buctd_flip_args": L.FlipArgs, "buctd_flip_merge_args": L.FlipMergeArgs,
+             "buctd_joints_mse_args": L.JointsMseArgs, "buctd_adam_args": L.AdamArgs, "buctd_crop_warp_args": L.CropWarpArgs,
+             "buctd_gen_target_args": L.GenTargetArgs, "buctd_pck_args": L.PckArgs}
     for cname, st in pairs.items():
         body = re.search(r"typedef struct \{([^}]*)\}\s*%s;" % cname, h).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
@@ -45,7 +47,7 @@ def test_struct_fields_match_header():
             if not decl:
                 continue
             # "int32_t a, b, c" / "const void* term[4]" / "const float* x"
-            decl = re.sub(r"^(const\s+)?(int32_t|int64_t|float|void|double)\s*\**", "", decl)
+            decl = re.sub(r"^(const\s+)?(int32_t|int64_t|uint8_t|float|void|double)\s*\**(\s*const\s*\*)?", "", decl)
             for part in decl.split(","):
                 names.append(re.sub(r"\[.*\]", "", part).replace("*", "").strip())
         assert names == [f[0] for f in st._fields_], (cname, names, [f[0] for f in st._fields_])
