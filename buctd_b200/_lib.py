@@ -67,7 +67,7 @@ class Resize3Args(C.Structure):
 
 class ChanAttArgs(C.Structure):
     _fields_ = [("dtype", i32), ("batch", i32), ("h", i32), ("w", i32), ("c", i32), ("y_cs", i32), ("yc_cs", i32),
-                ("reserved", i32), ("y", vp), ("yc", vp), ("scratch", fp), ("out", vp)]
+                ("out_stride", i32), ("y", vp), ("yc", vp), ("scratch", fp), ("out", vp)]
 
 
 class PosAttArgs(C.Structure):
@@ -77,7 +77,7 @@ class PosAttArgs(C.Structure):
 
 class DaCombineArgs(C.Structure):
     _fields_ = [("dtype", i32), ("batch", i32), ("h", i32), ("w", i32), ("c", i32), ("x_cs", i32), ("p_cs", i32),
-                ("out_cs", i32), ("channel_only", i32), ("reserved", i32),
+                ("out_cs", i32), ("channel_only", i32), ("c_stride", i32),
                 ("x", vp), ("p_out", vp), ("c_out", vp), ("out", vp)]
 
 

@@ -184,8 +184,9 @@ def _stages(width: int) -> dict:
 
 
 def make_cfg(variant: str = "coam", width: int = 48, image_size=(288, 384), num_joints: int = 17,
-             cond: str = "stacked", post_process: bool = True) -> CfgNode:
-    """variant: 'plain' | 'prenet' | 'coam'; cond: 'stacked' | 'colored' | 'plain' (1-ch)."""
+             cond: str = "stacked", post_process: bool = True, att_modules=(False, True, False, False)) -> CfgNode:
+    """variant: 'plain' | 'prenet' | 'coam'; cond: 'stacked' | 'colored' | 'plain' (1-ch);
+    att_modules: MODEL.ATT_MODULES (the shipped scripts use [F,T,F,F]; lib/config/default.py:48 defaults to [F,F,T,T])."""
     cfg = get_cfg_defaults()
     w, h = int(image_size[0]), int(image_size[1])
     extra = {"USE_PRE_NET": variant == "prenet", "USE_ATTENTION": variant == "coam",
@@ -194,7 +195,7 @@ def make_cfg(variant: str = "coam", width: int = 48, image_size=(288, 384), num_
     cfg.merge_from_dict({
         "MODEL": {"NAME": "pose_hrnet_coam" if variant == "coam" else "pose_hrnet",
                   "NUM_JOINTS": num_joints, "IMAGE_SIZE": [w, h], "HEATMAP_SIZE": [w // 4, h // 4],
-                  "SIGMA": 3, "EXTRA": extra, "ATT_MODULES": [False, True, False, False],
+                  "SIGMA": 3, "EXTRA": extra, "ATT_MODULES": [bool(v) for v in att_modules],
                   "CONDITIONAL_TOPDOWN": variant != "plain"},
         "DATASET": {"STACKED_CONDITION": cond == "stacked" and variant != "plain",
                     "COLORED": cond == "colored" and variant != "plain"},

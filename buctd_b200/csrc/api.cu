@@ -176,7 +176,7 @@ static void op_spans(const PlanOp& op, std::vector<Span>* rd, std::vector<Span>*
       rd->push_back(span(a.yc, act_bytes(a.batch, a.h, a.w, a.yc_cs)));
       const long long nchunks = ((long long)(a.h + 1) * (a.w + 1) + BUCTD_CHAN_ATT_ROWS_PER_CHUNK - 1) / BUCTD_CHAN_ATT_ROWS_PER_CHUNK;
       wr->push_back(span(a.scratch, 4ll * a.batch * nchunks * a.c * a.c));
-      wr->push_back(span(a.out, 2ll * a.batch * a.c * a.h * a.w));
+      wr->push_back(span(a.out, 2ll * a.batch * a.c * (a.out_stride > 0 ? a.out_stride : a.h * a.w)));
       break;
     }
     case BUCTD_OP_POS_ATT: {
@@ -191,7 +191,7 @@ static void op_spans(const PlanOp& op, std::vector<Span>* rd, std::vector<Span>*
       const buctd_da_combine_args& a = op.u.da;
       rd->push_back(span(a.x, act_bytes(a.batch, a.h, a.w, a.x_cs)));
       if (a.p_out) rd->push_back(span(a.p_out, act_bytes(a.batch, a.h, a.w, a.p_cs)));
-      rd->push_back(span(a.c_out, 2ll * a.batch * a.c * a.h * a.w));
+      rd->push_back(span(a.c_out, 2ll * a.batch * a.c * (a.c_stride > 0 ? a.c_stride : a.h * a.w)));
       wr->push_back(span(a.out, act_bytes(a.batch, a.h, a.w, a.out_cs)));
       break;
     }
@@ -290,7 +290,6 @@ BUCTD_API int buctd_create(int device, buctd_ctx** out) {
   BUCTD_CUDA(cudaSetDevice(device));
   int rc = tapgemm_init_device();
   if (!rc) rc = tapgemm_chain_init_device();
-  if (!rc) rc = pos_att_init_device();
   if (!rc) rc = pos_att_tc_init_device();
   if (!rc && get_encode_tiled() == nullptr) {
     set_error("buctd_create: cuTensorMapEncodeTiled driver entry point not found");

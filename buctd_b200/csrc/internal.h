@@ -107,7 +107,6 @@ ChainLaunch* tapgemm_chain_new();
 size_t tapgemm_chain_flag_count(const ChainLaunch& C);
 void tapgemm_chain_set_flags(ChainLaunch* C, unsigned int* flags);
 void tapgemm_chain_delete(ChainLaunch* c);
-int pos_att_init_device();
 int pos_att_tc_init_device();
 bool pos_att_tc_supported(const buctd_pos_att_args& a);
 int launch_pos_att_tc(const buctd_pos_att_args& a, cudaStream_t st);

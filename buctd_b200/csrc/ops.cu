@@ -592,6 +592,7 @@ __global__ void __launch_bounds__(128) chan_apply_kernel(buctd_chan_att_args a) 
   float* s_y = s_dyn + kCaTile * a.c;           // [64][C+1]
   const int b = blockIdx.z, t1 = blockIdx.y;
   const int hw = a.h * a.w;
+  const int ps = a.out_stride > 0 ? a.out_stride : hw;      // planar row stride
   const int p0 = blockIdx.x * kCaPix;
   const int cs1 = a.c + 1;
   const int nchunks = (int)(((long long)(a.h + 1) * (a.w + 1) + BUCTD_CHAN_ATT_ROWS_PER_CHUNK - 1) / BUCTD_CHAN_ATT_ROWS_PER_CHUNK);
@@ -632,8 +633,8 @@ __global__ void __launch_bounds__(128) chan_apply_kernel(buctd_chan_att_args a) 
 #pragma unroll
   for (int j = 0; j < G; ++j) {
     const int p = p0 + pg * 4;
-    T* o = reinterpret_cast<T*>(a.out) + ((long long)b * a.c + t1 * kCaTile + cg * G + j) * hw + p;
-    if (p + 4 <= hw && ((hw & 3) == 0)) {
+    T* o = reinterpret_cast<T*>(a.out) + ((long long)b * a.c + t1 * kCaTile + cg * G + j) * ps + p;
+    if (p + 4 <= hw && ((ps & 3) == 0)) {
       uint2 u;
       u.x = T16<T>::pack2(acc[0][j], acc[1][j]);
       u.y = T16<T>::pack2(acc[2][j], acc[3][j]);
@@ -666,7 +667,7 @@ static int chan_att_run(const buctd_chan_att_args& a, cudaStream_t st) {
 int launch_chan_att(const buctd_chan_att_args& a, cudaStream_t st, int* nlaunch) {
   BUCTD_CHECK(a.c % 48 == 0 || a.c % 32 == 0, BUCTD_ERR_INVALID, "chan_att: C=%d must be a multiple of 48 or 32", a.c);
   BUCTD_CHECK(a.y && a.yc && a.scratch && a.out, BUCTD_ERR_INVALID, "chan_att: null pointer");
-  BUCTD_CHECK(a.c <= 256, BUCTD_ERR_INVALID, "chan_att: C=%d too large for the shared-memory tile", a.c);
+  BUCTD_CHECK(a.c <= 384, BUCTD_ERR_INVALID, "chan_att: C=%d too large for the shared-memory tile", a.c);
   if (nlaunch) *nlaunch = 3;
   const bool t48 = a.c % 48 == 0;
   if (a.dtype == BUCTD_F16) return t48 ? chan_att_run<__half, 48>(a, st) : chan_att_run<__half, 32>(a, st);
@@ -686,10 +687,11 @@ __global__ void __launch_bounds__(256) da_combine_kernel(buctd_da_combine_args a
   const int hw = a.h * a.w;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;   // 32 x 8
-  const T* cout = reinterpret_cast<const T*>(a.c_out) + (long long)b * a.c * hw;
+  const int ps = a.c_stride > 0 ? a.c_stride : hw;          // planar row stride of c_out
+  const T* cout = reinterpret_cast<const T*>(a.c_out) + (long long)b * a.c * ps;
   for (int cc = ty; cc < 32; cc += 8) {
     int c = c0 + cc, p = p0 + tx;
-    s_c[cc][tx] = (c < a.c && p < hw) ? T16<T>::to_f(cout[(long long)c * hw + p]) : 0.f;
+    s_c[cc][tx] = (c < a.c && p < hw) ? T16<T>::to_f(cout[(long long)c * ps + p]) : 0.f;
   }
   __syncthreads();
   for (int pp = ty; pp < 32; pp += 8) {

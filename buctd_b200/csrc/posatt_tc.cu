@@ -1,6 +1,8 @@
-// CoAM position attention on the sm_100a tensor cores (head dim C <= 64: the 96x72 branch of W48, and
-// every branch of W32 up to C = 64).  Same contract as pos_att_kernel (posatt.cu); this version keeps S = QK^T
-// and O in TMEM and issues both GEMMs with tcgen05.mma:
+// CoAM position attention on the sm_100a tensor cores, every head dim C = 16 .. 384 (multiple of 16): all branches of
+// W32 / W48 at every CoAM placement.  S = QK^T and O stay in TMEM and both GEMMs are tcgen05.mma; channels are handled
+// in 64-wide blocks (one SWIZZLE_128B block = [128 rows][64 channels]): Q is resident as ceil(C/64) blocks, the K and V
+// blocks of a key tile stream through one ring (K_0 .. K_n-1, V_0 .. V_n-1), S accumulates over the K blocks and V block i
+// feeds O columns [64 i, 64 i + 64).  TMEM: S 128 columns + O C columns (<= 512).
 //
 //   per CTA: 128 queries (one thread of the 4 soft-max warps per query row = TMEM lane), loop over 128-key tiles:
 //     warp 0  TMA: Q once, K/V tiles through a 2-stage ring (SWIZZLE_128B, 64-channel boxes, zero fill above C)
@@ -8,7 +10,8 @@
 //             MN-major B operand: the tile is [keys][channels], exactly as it lies in the act16 tensor)
 //     warps 2..5  soft-max: two passes over the S row in TMEM (max, then exp2 -> 16-bit P into shared memory),
 //             running max / sum in registers, O rescaled in TMEM only when a row maximum grows
-//   Two CTAs per SM interleave, so one CTA's soft-max overlaps the other's MMAs.
+//   C <= 64: two CTAs per SM interleave, so one CTA's soft-max overlaps the other's MMAs (C > 64: one CTA per SM; those
+//   branches are 12 % of the attention FLOPs).
 #include "common.cuh"
 #include "internal.h"
 
@@ -30,7 +33,11 @@ constexpr int kTcTile = 128;
 constexpr int kTcBlk = 128 * 128;      // one [128 rows][128 B] SWIZZLE_128B block
 
 struct PosAttTcParams {
-  int nrows, W, H, c, n2;              // rows per crop (padded), geometry, channels, channels rounded up to 16
+  int nrows, W, H, c, n2;              // rows per crop (padded), geometry, channels, O columns in TMEM (C, + the ones column)
+  int nkc, ns;                         // 64-channel blocks; K/V ring slots
+  int n_last;                          // MMA N of the last V block (its channels, + the ones column, rounded up to 16)
+  int ones;                            // row sums come from a column of ones planted in the last V block
+  int tmem_cols;
   int o_cs;
   float sc;                            // 1/sqrt(C) * log2(e)
   void* o;
@@ -97,15 +104,16 @@ pos_att_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                   const __grid_constant__ CUtensorMap map_v, const PosAttTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_q = smem;                       // [128][128 B]
-  uint8_t* s_kv = s_q + kTcBlk;              // ring of 3 tiles holding the stream K0 V0 K1 V1 ... (load n -> slot n % 3)
-  uint8_t* s_p = s_kv + 3 * kTcBlk;          // [2 blocks: keys 0..63 | 64..127][128 queries][128 B]
+  const int NKC = p.nkc, NS = p.ns;
+  uint8_t* s_q = smem;                       // [nkc blocks][128][128 B]
+  uint8_t* s_kv = s_q + NKC * kTcBlk;        // ring of ns blocks holding the stream K(0) V(0) K(1) V(1) ... (load n -> slot n % ns)
+  uint8_t* s_p = s_kv + NS * kTcBlk;         // [2 blocks: keys 0..63 | 64..127][128 queries][128 B]
   float* s_bias = reinterpret_cast<float*>(s_p + 2 * kTcBlk);   // [2][128] additive key mask (double buffered)
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_bias + 2 * kTcTile);   // [2][4] bit c%32 of word c/32: key c of the tile is masked
   uint64_t* q_full = reinterpret_cast<uint64_t*>(s_mask + 8);
-  uint64_t* kv_full = q_full + 1;            // [3]
-  uint64_t* kv_empty = kv_full + 3;          // [3]
-  uint64_t* s_full = kv_empty + 3;
+  uint64_t* kv_full = q_full + 1;            // [4]
+  uint64_t* kv_empty = kv_full + 4;          // [4]
+  uint64_t* s_full = kv_empty + 4;
   uint64_t* p_full = s_full + 1;
   uint64_t* o_done = p_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
@@ -119,11 +127,11 @@ pos_att_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 3; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_done, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -134,47 +142,59 @@ pos_att_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
   if (warp == 0) {
     if (elect_one()) {
-      mbar_expect_tx(q_full, kTcBlk);
-      tma_load_2d(s_q, &map_q, q_full, 0, row_base + m0);
-      for (int n = 0; n < 2 * ntiles; ++n) {                  // n even: K(n/2), n odd: V(n/2)
-        const int slot = n % 3;
-        mbar_wait(&kv_empty[slot], ((n / 3) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[slot], kTcBlk);
-        tma_load_2d(s_kv + slot * kTcBlk, (n & 1) ? &map_v : &map_k, &kv_full[slot], 0, row_base + (n >> 1) * kTcTile);
+      mbar_expect_tx(q_full, (uint32_t)(NKC * kTcBlk));
+      for (int kc = 0; kc < NKC; ++kc) tma_load_2d(s_q + kc * kTcBlk, &map_q, q_full, kc * 64, row_base + m0);
+      uint32_t slot = 0, ph = 1;                              // waits on "empty" (starts free)
+      for (int j = 0; j < ntiles; ++j) {
+        for (int i = 0; i < 2 * NKC; ++i) {                   // K blocks, then V blocks of key tile j
+          mbar_wait(&kv_empty[slot], ph);
+          mbar_expect_tx(&kv_full[slot], kTcBlk);
+          const bool is_v = i >= NKC;
+          tma_load_2d(s_kv + slot * kTcBlk, is_v ? &map_v : &map_k, &kv_full[slot], (is_v ? i - NKC : i) * 64, row_base + j * kTcTile);
+          if (++slot == (uint32_t)NS) { slot = 0; ph ^= 1; }
+        }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (elect_one()) {
       const uint32_t idesc_s = umma_idesc_f16(T16<T>::kFmt, 128, kTcTile);                 // S = Q K^T, both K-major
-      const uint32_t idesc_o = umma_idesc_f16(T16<T>::kFmt, 128, p.n2) | (1u << 16);       // O += P V, B (=V) MN-major
-      const uint64_t qd = umma_desc_sw128(smem_u32(s_q));
+      const uint32_t idesc_o64 = umma_idesc_f16(T16<T>::kFmt, 128, 64) | (1u << 16);       // O += P V, B (=V) MN-major
+      const uint32_t idesc_ol = umma_idesc_f16(T16<T>::kFmt, 128, p.n_last) | (1u << 16);  // last V block
+      const uint32_t q_addr = smem_u32(s_q);
       const uint64_t pd = umma_desc_sw128(smem_u32(s_p));
-      const int ks_qk = (p.c + 15) >> 4;
       mbar_wait(q_full, 0);
       const uint32_t kv_addr = smem_u32(s_kv);
       PT_DECL(m_k); PT_DECL(m_p); PT_DECL(m_v); PT_DECL(m_tot);
       PT_BEGIN(m_start);
+      uint32_t slot = 0, ph = 0;
       for (int j = 0; j < ntiles; ++j) {
-        const int nk = 2 * j, nv = 2 * j + 1;
-        const int sk = nk % 3, sv = nv % 3;
-        { PT_BEGIN(t0); mbar_wait(&kv_full[sk], (nk / 3) & 1); PT_ADD(m_k, t0); }
-        tc_fence_after();
-        const uint64_t kd = umma_desc_sw128(kv_addr + sk * kTcBlk);
-        for (int k = 0; k < ks_qk; ++k) tc_mma_f16(tm_s, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_s, k != 0);
-        tc_commit(&kv_empty[sk]);
+        for (int kc = 0; kc < NKC; ++kc) {                    // S = sum over channel blocks of Q_kc K_kc^T
+          { PT_BEGIN(t0); mbar_wait(&kv_full[slot], ph); PT_ADD(m_k, t0); }
+          tc_fence_after();
+          const uint64_t qd = umma_desc_sw128(q_addr + kc * kTcBlk);
+          const uint64_t kd = umma_desc_sw128(kv_addr + slot * kTcBlk);
+          const int ks = (min(64, p.c - kc * 64) + 15) >> 4;
+          for (int k = 0; k < ks; ++k) tc_mma_f16(tm_s, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_s, (kc | k) != 0);
+          tc_commit(&kv_empty[slot]);
+          if (++slot == (uint32_t)NS) { slot = 0; ph ^= 1; }
+        }
         tc_commit(s_full);
         { PT_BEGIN(t0); mbar_wait(p_full, j & 1); PT_ADD(m_p, t0); }
-        { PT_BEGIN(t0); mbar_wait(&kv_full[sv], (nv / 3) & 1); PT_ADD(m_v, t0); }
-        tc_fence_after();
-        const uint64_t vd = umma_desc_sw128_mn(kv_addr + sv * kTcBlk);
+        for (int kc = 0; kc < NKC; ++kc) {                    // O[:, 64 kc ..] += P V_kc
+          { PT_BEGIN(t0); mbar_wait(&kv_full[slot], ph); PT_ADD(m_v, t0); }
+          tc_fence_after();
+          const uint64_t vd = umma_desc_sw128_mn(kv_addr + slot * kTcBlk);
+          const uint32_t idesc_o = kc == NKC - 1 ? idesc_ol : idesc_o64;
 #pragma unroll
-        for (int k = 0; k < kTcTile / 16; ++k) {
-          // A: P block k/4 (64 keys each), 32 B per k-step inside the 128-byte row; B: 16 key rows = 2048 B further
-          const uint64_t pa = pd + (uint64_t)((k >> 2) * (kTcBlk >> 4) + (k & 3) * 2);
-          tc_mma_f16(tm_o, pa, vd + (uint64_t)(k * (2048 >> 4)), idesc_o, (j | k) != 0);
+          for (int k = 0; k < kTcTile / 16; ++k) {
+            // A: P block k/4 (64 keys each), 32 B per k-step inside the 128-byte row; B: 16 key rows = 2048 B further
+            const uint64_t pa = pd + (uint64_t)((k >> 2) * (kTcBlk >> 4) + (k & 3) * 2);
+            tc_mma_f16(tm_o + kc * 64, pa, vd + (uint64_t)(k * (2048 >> 4)), idesc_o, (j | k) != 0);
+          }
+          tc_commit(&kv_empty[slot]);
+          if (++slot == (uint32_t)NS) { slot = 0; ph ^= 1; }
         }
-        tc_commit(&kv_empty[sv]);
         tc_commit(o_done);
       }
 #ifdef BUCTD_ROLE_TIMERS
@@ -195,7 +215,7 @@ pos_att_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const int etid = threadIdx.x - 64;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const int Wp = p.W + 1;
-    const bool ones = p.n2 > p.c;                // a free channel slot exists for the ones column
+    const bool ones = p.ones != 0;               // a free channel slot exists for the ones column
     float m_run = -INFINITY, l_run = 0.f;
     uint8_t* prow = s_p + row * 128;
     const int sw = row & 7;
@@ -347,10 +367,11 @@ pos_att_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         break;
       }
       l_run += ls;
-      if (ones) {                                             // plant the ones column in this tile's V (one key row per thread)
-        const int nv = 2 * j + 1, sv = nv % 3;
-        { PT_BEGIN(t0); mbar_wait(&kv_full[sv], (nv / 3) & 1); PT_ADD(x_v, t0); }
-        *reinterpret_cast<T*>(s_kv + sv * kTcBlk + etid * 128 + ((((p.c >> 3)) ^ (etid & 7)) << 4) + (p.c & 7) * 2) = T16<T>::from_f(1.f);
+      if (ones) {                                             // plant the ones column in this tile's last V block (one key row per thread)
+        const int nv = (2 * j + 2) * NKC - 1, sv = nv % NS;
+        { PT_BEGIN(t0); mbar_wait(&kv_full[sv], (nv / NS) & 1); PT_ADD(x_v, t0); }
+        const int cl = p.c & 63;
+        *reinterpret_cast<T*>(s_kv + sv * kTcBlk + etid * 128 + ((((cl >> 3)) ^ (etid & 7)) << 4) + (cl & 7) * 2) = T16<T>::from_f(1.f);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       tc_fence_before();
@@ -400,7 +421,7 @@ pos_att_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 #ifdef BUCTD_ROLE_TIMERS
@@ -409,18 +430,25 @@ extern "C" __attribute__((visibility("default"))) int buctd_debug_pa_cycles(unsi
 }
 #endif
 
-static size_t tc_smem_bytes() { return 1024 + 6 * (size_t)kTcBlk + 2 * kTcTile * 4 + 256; }
+static size_t tc_smem_bytes(int nkc, int ns) { return 1024 + (size_t)(nkc + ns + 2) * kTcBlk + 2 * kTcTile * 4 + 256; }
 
 int pos_att_tc_init_device() {
-  BUCTD_CUDA(cudaFuncSetAttribute(pos_att_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes()));
-  BUCTD_CUDA(cudaFuncSetAttribute(pos_att_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes()));
+  BUCTD_CUDA(cudaFuncSetAttribute(pos_att_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(6, 4)));
+  BUCTD_CUDA(cudaFuncSetAttribute(pos_att_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(6, 4)));
   return BUCTD_OK;
 }
 
-bool pos_att_tc_supported(const buctd_pos_att_args& a) {
-  const char* off = getenv("BUCTD_POSATT_LEGACY");
-  if (off && atoi(off)) return false;
-  return a.c % 8 == 0 && a.c >= 16 && a.c <= 64;
+bool pos_att_tc_supported(const buctd_pos_att_args& a) { return a.c % 16 == 0 && a.c >= 16 && a.c <= 384; }
+
+int launch_pos_att(const buctd_pos_att_args& a, cudaStream_t st) {
+  BUCTD_CHECK(a.q && a.k && a.v && a.o, BUCTD_ERR_INVALID, "pos_att: null pointer");
+  BUCTD_CHECK(a.q_cs % 8 == 0 && a.k_cs % 8 == 0 && a.v_cs % 8 == 0 && a.o_cs % 8 == 0, BUCTD_ERR_INVALID,
+              "pos_att: channel strides must be multiples of 8");
+  BUCTD_CHECK((((uintptr_t)a.q | (uintptr_t)a.k | (uintptr_t)a.v | (uintptr_t)a.o) & 15) == 0, BUCTD_ERR_INVALID,
+              "pos_att: q/k/v/o must be 16-byte aligned");
+  BUCTD_CHECK(pos_att_tc_supported(a), BUCTD_ERR_INVALID, "pos_att: head dim C=%d must be a multiple of 16 in [16, 384]", a.c);
+  if (a.batch == 0) return BUCTD_OK;
+  return launch_pos_att_tc(a, st);
 }
 
 int launch_pos_att_tc(const buctd_pos_att_args& a, cudaStream_t st) {
@@ -444,13 +472,22 @@ int launch_pos_att_tc(const buctd_pos_att_args& a, cudaStream_t st) {
   }
   PosAttTcParams p;
   p.nrows = nrows; p.W = a.w; p.H = a.h; p.c = a.c; p.o_cs = a.o_cs;
-  p.n2 = a.c < 64 ? (a.c + 1 + 15) / 16 * 16 : 64;      // PV output columns: C (+ the ones column when a slot is free)
+  p.nkc = (a.c + 63) / 64;
+  p.ns = p.nkc == 1 ? 3 : 4;
+  // the ones column needs a free channel slot in the last 64-channel block, and the last V block of a tile must be able
+  // to land while the soft-max warps still hold P back (ring >= nkc + 2 slots): C = 16 .. 48, 80 .. 112
+  p.ones = (a.c % 64 != 0 && p.nkc + 2 <= p.ns) ? 1 : 0;
+  const int c_last = a.c - 64 * (p.nkc - 1);
+  p.n_last = p.ones ? (c_last + 1 + 15) / 16 * 16 : c_last;
+  p.n2 = 64 * (p.nkc - 1) + p.n_last;
+  p.tmem_cols = kTcTile + p.n2 <= 256 ? 256 : 512;
   p.sc = 1.4426950408889634f / sqrtf((float)a.c);
   p.o = a.o;
   dim3 grid((nrows + kTcTile - 1) / kTcTile, a.batch);
+  const size_t smem = tc_smem_bytes(p.nkc, p.ns);
   cudaError_t e;
-  if (a.dtype == BUCTD_F16) e = launch_pdl(pos_att_tc_kernel<__half>, grid, dim3(kTcThreads), tc_smem_bytes(), st, mq, mk, mv, p);
-  else e = launch_pdl(pos_att_tc_kernel<__nv_bfloat16>, grid, dim3(kTcThreads), tc_smem_bytes(), st, mq, mk, mv, p);
+  if (a.dtype == BUCTD_F16) e = launch_pdl(pos_att_tc_kernel<__half>, grid, dim3(kTcThreads), smem, st, mq, mk, mv, p);
+  else e = launch_pdl(pos_att_tc_kernel<__nv_bfloat16>, grid, dim3(kTcThreads), smem, st, mq, mk, mv, p);
   BUCTD_CHECK(e == cudaSuccess, BUCTD_ERR_CUDA, "pos_att_tc launch failed: %s", cudaGetErrorString(e));
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;

@@ -137,13 +137,13 @@ class PoseHighResolutionNet(nn.Module):
     def _fold(self, conv: Conv):
         """BN(conv(x)) = conv'(x) + b' with w' = w * g/sqrt(v+eps), b' = beta + (bias - mean) * g/sqrt(v+eps)
         (eval-mode nn.BatchNorm2d, eps 1e-5), all in float64 before the cast."""
-        w = self._get(conv.w + ".weight").detach().double().cpu()
-        b = self._get(conv.w + ".bias").detach().double().cpu() if conv.bias else torch.zeros(conv.cout, dtype=torch.float64)
+        w = self._get(conv.w + ".weight").detach().cpu().double()
+        b = self._get(conv.w + ".bias").detach().cpu().double() if conv.bias else torch.zeros(conv.cout, dtype=torch.float64)
         if conv.bn:
-            g = self._get(conv.bn + ".weight").detach().double().cpu()
-            beta = self._get(conv.bn + ".bias").detach().double().cpu()
-            mean = self._get(conv.bn + ".running_mean").detach().double().cpu()
-            var = self._get(conv.bn + ".running_var").detach().double().cpu()
+            g = self._get(conv.bn + ".weight").detach().cpu().double()
+            beta = self._get(conv.bn + ".bias").detach().cpu().double()
+            mean = self._get(conv.bn + ".running_mean").detach().cpu().double()
+            var = self._get(conv.bn + ".running_var").detach().cpu().double()
             s = g / torch.sqrt(var + BN_EPS)
             w = w * s.view(-1, 1, 1, 1)
             b = beta + (b - mean) * s
@@ -187,13 +187,13 @@ class PoseHighResolutionNet(nn.Module):
         for s in arch.coam:
             for da in arch.coam[s]:
                 for lin in ([da.fc_q, da.fc_o] if not arch.att_channel_only else []) + [da.chan_fc_o]:
-                    w = self._get(lin.w + ".weight").detach().double().cpu()
-                    add_w(lin.w, w.view(lin.fout, lin.fin, 1, 1), self._get(lin.w + ".bias").detach().double().cpu())
+                    w = self._get(lin.w + ".weight").detach().cpu().double()
+                    add_w(lin.w, w.view(lin.fout, lin.fin, 1, 1), self._get(lin.w + ".bias").detach().cpu().double())
                 if not arch.att_channel_only:
-                    wk = self._get(da.fc_k.w + ".weight").detach().double().cpu()
-                    wv = self._get(da.fc_v.w + ".weight").detach().double().cpu()
-                    bk = self._get(da.fc_k.w + ".bias").detach().double().cpu()
-                    bv = self._get(da.fc_v.w + ".bias").detach().double().cpu()
+                    wk = self._get(da.fc_k.w + ".weight").detach().cpu().double()
+                    wv = self._get(da.fc_v.w + ".weight").detach().cpu().double()
+                    bk = self._get(da.fc_k.w + ".bias").detach().cpu().double()
+                    bv = self._get(da.fc_v.w + ".bias").detach().cpu().double()
                     add_w(da.prefix + ":kv", torch.cat([wk, wv], 0).view(2 * da.c, da.c, 1, 1), torch.cat([bk, bv], 0))
         # stem conv1 runs on CUDA cores in fp32: [64][27]
         w, b = self._fold(arch.stem[0])
@@ -461,6 +461,12 @@ class PoseHighResolutionNet(nn.Module):
                 xs = new_xs
             mark("stage%d" % (si + 2), list(xs))
             ys = xs
+        # ATT_MODULES[3]: stage4_att on y_list[0] after stage4 (pose_hrnet_coam.py:560-562); nxt / shares are stage 4's
+        if 3 in arch.coam and arch.use_attention:
+            ys = self._build_coam(arch.coam[3], ys[:1], batch, act, raw, _Emit, head_ops, nxt, cond_acts,
+                                  lambda i: at(i, shares[i])) + list(ys[1:])
+            mark("stage4_att", list(ys[:1]))
+        at(0)
         final_src = ys[0]
         nbytes = bump.off
         return {"specs": specs, "acts": acts, "marks": marks, "bytes": nbytes, "final_src": final_src, "s1": s1,
@@ -484,11 +490,12 @@ class PoseHighResolutionNet(nn.Module):
             specs.append((L.OP_TAPGEMM, ("tg", da.chan_cnn.w, x, y, dict(stride=1, relu=False, residual=None)), da.chan_cnn.w))
             specs.append((L.OP_TAPGEMM, ("tg", da.chan_cnn_cond.w, cond, yc, dict(stride=1, relu=False, residual=None, k=cc)),
                           da.chan_cnn_cond.w))
-            planar = raw(batch * C_ * h * w * 2)
+            hws = _rup(h * w, 8)          # planar row stride: 16-byte multiples for TMA (H*W = 108 at the 1/32 scale of 384x288)
+            planar = raw(batch * C_ * hws * 2)
             scratch = raw(L.chan_att_scratch_floats(batch, h, w, C_) * 4)
-            c_out = raw(batch * C_ * h * w * 2)
-            specs.append((L.OP_CHAN_ATT, ("chan", y, yc, scratch, planar), p + ":chan_att"))
-            specs.append((L.OP_TAPGEMM, ("lin_planar", da.chan_fc_o.w, planar, c_out, batch * C_, h * w), da.chan_fc_o.w))
+            c_out = raw(batch * C_ * hws * 2)
+            specs.append((L.OP_CHAN_ATT, ("chan", y, yc, scratch, planar, hws), p + ":chan_att"))
+            specs.append((L.OP_TAPGEMM, ("lin_planar", da.chan_fc_o.w, planar, c_out, batch * C_, h * w, hws), da.chan_fc_o.w))
             p_out = None
             if not arch.att_channel_only:
                 yp = act(p + ":yp", h, w, C_)
@@ -507,7 +514,7 @@ class PoseHighResolutionNet(nn.Module):
             out = nxt(i)
             if out.ptr == x.ptr:
                 out = nxt(i)
-            specs.append((L.OP_DA_COMBINE, ("da", x, p_out, c_out, out), p + ":combine"))
+            specs.append((L.OP_DA_COMBINE, ("da", x, p_out, c_out, out, hws), p + ":combine"))
             outs.append(out)
         return outs
 
@@ -542,9 +549,9 @@ class PoseHighResolutionNet(nn.Module):
                     args.layer[li] = self._tapgemm(key, fix(src), base + dst.ptr, dst.cs, dst.h, dst.w,
                                                    residual=fix(res) if res is not None else None, **kw)
             elif tag == "lin_planar":
-                _, key, src_off, dst_off, rows, hw = spec
-                a = Act(base + src_off, 1, 0, 0, hw, hw)
-                args = self._tapgemm(key, a, base + dst_off, hw, 0, 0, out_mode=L.OUT_ROWS16, m_rows=rows, a_cs=hw)
+                _, key, src_off, dst_off, rows, hw, hws = spec
+                a = Act(base + src_off, 1, 0, 0, hw, hws)
+                args = self._tapgemm(key, a, base + dst_off, hws, 0, 0, out_mode=L.OUT_ROWS16, m_rows=rows, a_cs=hws)
                 args.batch = 1
             elif tag == "fuse":
                 _, terms, out = spec
@@ -557,10 +564,10 @@ class PoseHighResolutionNet(nn.Module):
                     args.term_shift[j] = sh
                 args.out = base + out.ptr
             elif tag == "chan":
-                _, y, yc, scratch, planar = spec
+                _, y, yc, scratch, planar, hws = spec
                 args = L.ChanAttArgs()
                 args.dtype, args.batch, args.h, args.w, args.c = self._dt, batch, y.h, y.w, y.c
-                args.y_cs, args.yc_cs = y.cs, yc.cs
+                args.y_cs, args.yc_cs, args.out_stride = y.cs, yc.cs, hws
                 args.y, args.yc, args.scratch, args.out = base + y.ptr, base + yc.ptr, base + scratch, base + planar
             elif tag == "pos":
                 _, q, kv, o, c = spec
@@ -569,8 +576,9 @@ class PoseHighResolutionNet(nn.Module):
                 args.q_cs, args.k_cs, args.v_cs, args.o_cs = q.cs, kv.cs, kv.cs, o.cs
                 args.q, args.k, args.v, args.o = base + q.ptr, base + kv.ptr, base + kv.ptr + 2 * c, base + o.ptr
             elif tag == "da":
-                _, x, p_out, c_out, out = spec
+                _, x, p_out, c_out, out, hws = spec
                 args = L.DaCombineArgs()
+                args.c_stride = hws
                 args.dtype, args.batch, args.h, args.w, args.c = self._dt, batch, x.h, x.w, x.c
                 args.x_cs, args.p_cs, args.out_cs = x.cs, (p_out.cs if p_out is not None else 0), out.cs
                 args.channel_only = int(self.arch.att_channel_only)

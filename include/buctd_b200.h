@@ -159,14 +159,16 @@ int buctd_cond_resize3(buctd_ctx* ctx, const buctd_resize3_args* args, buctd_str
  * lib/models/pose_hrnet_coam.py:673-689. */
 #define BUCTD_CHAN_ATT_ROWS_PER_CHUNK 256
 typedef struct {
-  int32_t dtype, batch, h, w, c, y_cs, yc_cs, reserved;
+  int32_t dtype, batch, h, w, c, y_cs, yc_cs;
+  int32_t out_stride;   /* planar row stride of out in elements (0 = H*W); a multiple of 8 lets the HW x HW fc_o read it by TMA */
   const void* y; const void* yc; float* scratch; void* out;
 } buctd_chan_att_args;
 int buctd_coam_channel_att(buctd_ctx* ctx, const buctd_chan_att_args* args, buctd_stream stream);
 
 /* CoAM position attention core (flash style, the [HW x HW] score matrix never leaves the SM):
  * o[t] = softmax_s( q[t].k[s] / sqrt(C) ) v[s] over the H*W valid pixels of each crop.
- * q, k, v, o: act16 [B][H+1][W+1][cs] with C valid channels (q/k/v may be slices of one tensor).
+ * q, k, v, o: act16 [B][H+1][W+1][cs] with C valid channels (q/k/v may be slices of one tensor); C a multiple of 16 in
+ * [16, 384] (every branch of W32 / W48 at every ATT_MODULES placement); tcgen05 for all of them.
  * Replaces ScaledDotProductAttention.forward between the projections,
  * lib/models/self_attention.py:78-86 (eval mode: dropout is the identity). */
 typedef struct {
@@ -178,7 +180,8 @@ int buctd_coam_position_att(buctd_ctx* ctx, const buctd_pos_att_args* args, buct
 /* DAModule output: out = x + (p_out + c_out), p_out act16, c_out planar [B][C][HW]; with
  * channel_only: out = x * c_out.  Replaces DAModule.forward, lib/models/pose_hrnet_coam.py:716-724. */
 typedef struct {
-  int32_t dtype, batch, h, w, c, x_cs, p_cs, out_cs, channel_only, reserved;
+  int32_t dtype, batch, h, w, c, x_cs, p_cs, out_cs, channel_only;
+  int32_t c_stride;     /* planar row stride of c_out in elements (0 = H*W) */
   const void* x; const void* p_out; const void* c_out; void* out;
 } buctd_da_combine_args;
 int buctd_da_combine(buctd_ctx* ctx, const buctd_da_combine_args* args, buctd_stream stream);

@@ -32,17 +32,24 @@ CASES = {
     "coam_w48_384x288_colored": ("coam", 48, (288, 384), "colored", 1),
     "coam_w32_128x96_stacked": ("coam", 32, (96, 128), "stacked", 2),    # small, for fast tests
     "coam_w32_128x96_plaincond": ("coam", 32, (96, 128), "plain", 1),    # 1-channel condition path
+    # every CoAM placement (MODEL.ATT_MODULES; pose_hrnet_coam.py:521,535,554,561): stage1_att (2 branches), the
+    # reference's default [F,F,T,T] (stage3_att on 4 branches incl. the 1/32 scale + stage4_att on branch 0), stage4_att alone
+    "coam_w32_128x96_att1000": ("coam", 32, (96, 128), "stacked", 2, (True, False, False, False)),
+    "coam_w32_128x96_att0011": ("coam", 32, (96, 128), "stacked", 2, (False, False, True, True)),
+    "coam_w32_128x96_att0001": ("coam", 32, (96, 128), "colored", 1, (False, False, False, True)),
+    "coam_w48_384x288_att0011": ("coam", 48, (288, 384), "stacked", 1, (False, False, True, True)),
 }
 
 
 def case_cfg(name):
-    variant, width, size, cond, batch = CASES[name]
-    return make_cfg(variant, width, size, cond=cond), batch
+    variant, width, size, cond, batch = CASES[name][:5]
+    att = CASES[name][5] if len(CASES[name]) > 5 else (False, True, False, False)
+    return make_cfg(variant, width, size, cond=cond, att_modules=att), batch
 
 
 def case_inputs(name, seed=1234):
     """x [B,3+Cc,H,W] float32 exactly as the golden run saw it."""
-    variant, width, (w, h), cond, batch = CASES[name]
+    variant, width, (w, h), cond, batch = CASES[name][:5]
     rgb = synth.synth_rgb(batch, w, h, seed)
     if variant == "plain":
         return rgb
@@ -87,7 +94,10 @@ def main():
         sys.exit("reference tree not found at %s" % R.REF_ROOT)
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]
     for name in CASES:
+        if only and name not in only:
+            continue
         cfg, batch = case_cfg(name)
         sd = case_state_dict(name)
         net = R.build_model(cfg, sd)
@@ -102,6 +112,8 @@ def main():
                             maxvals=maxvals.astype(np.float32), coords=coords.astype(np.float32),
                             center=center, scale=scale)
         print(name, hm.shape, "max|hm| %.4f" % np.abs(hm).max())
+    if only:
+        return
 
     hm, center, scale = decode_cases()
     cfg = make_cfg("plain", 32, (72, 96))

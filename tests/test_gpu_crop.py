@@ -93,8 +93,8 @@ def test_recrop_refinement_loop_matches_reference_composition():
     first = {r["annotation_id"]: r for r in hist[0]}
     for n, r in enumerate(proposals):
         k = np.array(first[r["annotation_id"]]["keypoints"]).reshape(17, 3)
-        # (the channel attention sums with float atomics: two forwards agree to ~1e-3, not bit for bit)
-        assert np.abs(k[:, 2:] - m1[n].cpu().numpy()).max() < 1e-2
-        assert (np.abs(k[:, :2] - p1[n].cpu().numpy()).max(1) < 1e-3).mean() >= 0.6
+        # same input, same plan => the same bits (the forward is run-to-run deterministic, tests/test_gpu_determinism.py)
+        assert np.array_equal(k[:, 2:].astype(np.float32), m1[n].cpu().numpy())
+        assert np.array_equal(k[:, :2].astype(np.float32), p1[n].cpu().numpy())
     db2 = results.load_coco_pose_results(hist[0], shapes, 17, 25, 96 * 1.0 / 128)
     assert all(np.all(np.isfinite(e["center"])) and np.all(e["scale"] > 0) for e in db2)

@@ -229,7 +229,7 @@ def test_cond_resize(dt, aa):
 
 
 @pytest.mark.parametrize("dt", DTS)
-@pytest.mark.parametrize("C,h,w", [(48, 24, 18), (96, 12, 9), (192, 6, 5), (32, 8, 6), (64, 4, 3)])
+@pytest.mark.parametrize("C,h,w", [(48, 24, 18), (96, 12, 9), (192, 6, 5), (32, 8, 6), (64, 4, 3), (384, 12, 9), (256, 4, 3)])
 def test_channel_attention(dt, C, h, w):
     B = 2
     y = q16(_rand(B, C, h, w, seed=25), dt)
@@ -250,7 +250,10 @@ def test_channel_attention(dt, C, h, w):
 
 
 @pytest.mark.parametrize("dt", DTS)
-@pytest.mark.parametrize("C,h,w", [(48, 24, 18), (96, 12, 9), (192, 7, 5), (32, 16, 12), (64, 8, 6), (128, 4, 3)])
+@pytest.mark.parametrize("C,h,w", [(48, 24, 18), (96, 12, 9), (192, 7, 5), (32, 16, 12), (64, 8, 6), (128, 4, 3),
+                                   # every head dim runs on tcgen05: channel blocks of 64 (1..6), several key tiles, with and
+                                   # without the ones column (C % 64 != 0 and <= 2 blocks)
+                                   (96, 48, 36), (192, 24, 18), (128, 16, 12), (256, 4, 3), (384, 12, 9), (16, 9, 7), (112, 20, 13)])
 def test_position_attention(dt, C, h, w):
     B = 2
     q = q16(_rand(B, C, h, w, seed=27, scale=1.5), dt)

@@ -31,7 +31,10 @@ def _net(name, dtype):
 
 @pytest.mark.parametrize("dtype", ["fp16", "bf16"])
 @pytest.mark.parametrize("name", ["plain_w32_256x192", "coam_w32_128x96_stacked", "coam_w32_128x96_plaincond",
-                                  "coam_w48_384x288_stacked", "coam_w48_384x288_colored", "prenet_w48_384x288"])
+                                  "coam_w48_384x288_stacked", "coam_w48_384x288_colored", "prenet_w48_384x288",
+                                  # every MODEL.ATT_MODULES placement, incl. the reference's default [F,F,T,T]
+                                  "coam_w32_128x96_att1000", "coam_w32_128x96_att0011", "coam_w32_128x96_att0001",
+                                  "coam_w48_384x288_att0011"])
 def test_heatmaps_match_reference_golden(golden_dir, name, dtype):
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     cfg, net = _net(name, dtype)
@@ -93,8 +96,9 @@ def test_batch_sizes_and_determinism():
         b1 = net(x[:1]).clone()           # different batch -> different plan
         a2 = net(x).clone()
     assert torch.equal(a, a2)
-    # the soft-max accumulation order in chan-att uses float atomics: compare with a tolerance
-    assert (a[:1] - b1).abs().max().item() < 2e-3
+    # a different batch size is a different plan (other tile / super-tile boundaries), but every output element is still
+    # the same fp32 sum in the same order: crop 0 alone gives the bits it gives inside the batch
+    assert torch.equal(a[:1], b1)
     # end to end through decode
     p, m = inference.decode_device(a, None, None, post_process=True)
     assert p.shape == (2, 17, 2) and m.shape == (2, 17, 1)

@@ -25,7 +25,8 @@ def _load(golden_dir, name):
 ORACLE_TOL = 1e-4
 
 
-@pytest.mark.parametrize("name", ["plain_w32_256x192", "coam_w32_128x96_stacked", "coam_w32_128x96_plaincond"])
+@pytest.mark.parametrize("name", ["plain_w32_256x192", "coam_w32_128x96_stacked", "coam_w32_128x96_plaincond",
+                                  "coam_w32_128x96_att1000", "coam_w32_128x96_att0011", "coam_w32_128x96_att0001"])
 def test_forward_matches_reference_small(golden_dir, name):
     cfg, _ = G.case_cfg(name)
     g = _load(golden_dir, name)
@@ -35,7 +36,8 @@ def test_forward_matches_reference_small(golden_dir, name):
 
 
 @pytest.mark.slow
-@pytest.mark.parametrize("name", ["coam_w48_384x288_stacked", "coam_w48_384x288_colored", "prenet_w48_384x288"])
+@pytest.mark.parametrize("name", ["coam_w48_384x288_stacked", "coam_w48_384x288_colored", "prenet_w48_384x288",
+                                  "coam_w48_384x288_att0011"])
 def test_forward_matches_reference_full(golden_dir, name):
     cfg, _ = G.case_cfg(name)
     g = _load(golden_dir, name)
