@@ -48,3 +48,30 @@ def test_colored_and_plain():
     assert c.shape == (3, 96, 72) and abs(c.max() - 255) < 1e-9
     p = C.plain_condition(kp, 96, 72)
     assert p.dtype.kind == "i" and p.shape == (3, 96, 72) and (p[0] == p[2]).all()
+
+
+@pytest.mark.parametrize("name", ["s128x96", "s384x288", "s40x30", "all_skipped", "single"])
+def test_oracle_matches_reference_rasteriser_source(golden_dir, name):
+    """tests/golden/condition.npz holds the outputs of the reference's OWN get_stacked_condition / get_condition_image /
+    get_condition_image_colored / generate_heatmap source (lib/dataset/JointsDataset.py:457-543, compiled in isolation by
+    oracle/make_golden_condition.py): the restatement must reproduce them, incl. borders, skips and duplicates."""
+    import os
+    g = np.load(os.path.join(golden_dir, "condition.npz"))
+    kp = g[name + ":kpts"]
+    h, w = [int(v) for v in g[name + ":size"]]
+    cols = [list(g["colors"][i % len(g["colors"])]) for i in range(len(kp))]
+    assert np.abs(C.stacked_condition(kp, h, w) - g[name + ":stacked"]).max() <= 3e-5        # the fixture is float32
+    assert np.abs(C.colored_condition(kp, h, w, cols) - g[name + ":colored"]).max() <= 3e-5
+    assert np.array_equal(C.plain_condition(kp, h, w), g[name + ":plain"])
+    assert g["colors"].tolist() == C.COCO_KPT_COLORS
+
+
+@pytest.mark.skipif(not __import__("oracle.refharness", fromlist=["x"]).available(), reason="reference tree not present (GPU box)")
+def test_condition_golden_is_current(golden_dir):
+    import os
+    from oracle import make_golden_condition as M
+    ref = M.reference_rasteriser()
+    g = np.load(os.path.join(golden_dir, "condition.npz"))
+    h, w, kp = M.cases()["s40x30"]
+    st = np.moveaxis(np.asarray(ref.get_stacked_condition(kp.copy(), (h, w), None)), -1, 0)
+    assert np.abs(st - g["s40x30:stacked"]).max() <= 3e-5

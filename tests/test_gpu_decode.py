@@ -99,6 +99,26 @@ def test_rasteriser_vs_oracle(mode):
     assert out[1].max() == 0
 
 
+@pytest.mark.parametrize("name", ["s128x96", "s384x288", "s40x30", "all_skipped", "single"])
+def test_rasteriser_vs_reference_source_golden(golden_dir, name):
+    """The CUDA rasteriser against the outputs of the reference's own rasteriser source (tests/golden/condition.npz,
+    oracle/make_golden_condition.py): all three modes, borders / skips / duplicates."""
+    import os
+    g = np.load(os.path.join(golden_dir, "condition.npz"))
+    kp = torch.from_numpy(g[name + ":kpts"].astype(np.float32)[None]).cuda()
+    h, w = [int(v) for v in g[name + ":size"]]
+    K = kp.shape[1]
+    cols = [list(g["colors"][i % len(g["colors"])]) for i in range(K)]
+    st = condition.rasterize_condition(kp, h, w, "stacked").cpu().numpy()[0]
+    assert np.abs(st - g[name + ":stacked"]).max() <= 2e-4
+    co = condition.rasterize_condition(kp, h, w, "colored", colors=cols).cpu().numpy()[0]
+    assert np.abs(co - g[name + ":colored"]).max() <= 2e-4
+    pl = condition.rasterize_condition(kp, h, w, "plain").cpu().numpy()[0]
+    d = np.abs(pl - g[name + ":plain"].astype(np.float32))
+    # .astype(int) truncation of a float64 blur: the float32 device value may land on the other side of an integer
+    assert d.max() <= 1.0 and (d > 0).mean() < 1e-4
+
+
 def test_rasteriser_writes_into_model_input_channels():
     B, K, H, W = 2, 17, 128, 96
     kp = torch.tensor(np.random.default_rng(1).uniform(5, 90, (B, K, 2)), dtype=torch.float32).cuda()

@@ -45,7 +45,9 @@ def test_heatmaps_match_reference_golden(golden_dir, name, dtype):
     out = out.cpu().numpy()
     err = np.abs(out - g["heatmaps"]).max()
     print("\n%s %s: max-abs heat-map error vs reference %.5f (|ref|max %.3f)" % (name, dtype, err, np.abs(g["heatmaps"]).max()))
-    assert err <= TOL[dtype], (name, dtype, err)
+    # the tolerance is stated for heat-maps of O(1) (real ones live in [0, 1]); the synthetic weights of the [F,F,T,T]
+    # placements give |heat-map| up to 4.5, so the bound scales with max(1, |ref|max)
+    assert err <= TOL[dtype] * max(1.0, float(np.abs(g["heatmaps"]).max())), (name, dtype, err)
     # decode on the reference's own heat-maps is checked bit-exact in test_gpu_decode; here the decoded
     # indices of OUR heat-maps must agree wherever the reference's top-2 margin exceeds the error
     hm = g["heatmaps"].reshape(-1, g["heatmaps"].shape[2] * g["heatmaps"].shape[3])
