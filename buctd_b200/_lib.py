@@ -12,7 +12,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BUCTD_LIB") or os.path.join(_HERE, "libbuctd_b200.so")   # BUCTD_LIB: debug builds (role timers)
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 F16, BF16 = 0, 1
 TG_FLAT, TG_PATCH = 0, 1
 OUT_ACT16, OUT_ROWS16, OUT_NCHW32 = 0, 1, 2
@@ -45,7 +45,7 @@ class TapGemmChainArgs(C.Structure):
 
 class StemArgs(C.Structure):
     _fields_ = [("dtype", i32), ("batch", i32), ("x_channels", i32), ("h", i32), ("w", i32), ("out_cs", i32),
-                ("x", fp), ("weight", fp), ("bias", fp), ("out", vp)]
+                ("x_half", i32), ("reserved", i32), ("x", fp), ("weight", fp), ("bias", fp), ("out", vp)]
 
 
 class FuseArgs(C.Structure):
@@ -63,6 +63,11 @@ class ResizeArgs(C.Structure):
 class Resize3Args(C.Structure):
     _fields_ = [("dtype", i32), ("batch", i32), ("x_channels", i32), ("c_off", i32), ("cc", i32), ("h", i32), ("w", i32),
                 ("reserved", i32), ("out_cs", i32 * 3), ("reserved2", i32), ("x", fp), ("out", vp * 3)]
+
+
+class CondKptsArgs(C.Structure):
+    _fields_ = [("dtype", i32), ("batch", i32), ("k", i32), ("kstride", i32), ("h", i32), ("w", i32),
+                ("out_cs", i32 * 3), ("reserved", i32), ("kpts", fp), ("out", vp * 3)]
 
 
 class ChanAttArgs(C.Structure):
@@ -143,7 +148,7 @@ OP_STRUCT = {OP_TAPGEMM: TapGemmArgs, OP_STEM: StemArgs, OP_FUSE: FuseArgs, OP_R
 
 # every symbol include/buctd_b200.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = ["buctd_abi_version", "buctd_last_error", "buctd_create", "buctd_destroy", "buctd_launch_count",
-           "buctd_tapgemm", "buctd_tapgemm_chain", "buctd_stem_conv", "buctd_hr_fuse", "buctd_cond_resize", "buctd_cond_resize3", "buctd_coam_channel_att",
+           "buctd_tapgemm", "buctd_tapgemm_chain", "buctd_stem_conv", "buctd_hr_fuse", "buctd_cond_resize", "buctd_cond_resize3", "buctd_cond_from_kpts", "buctd_coam_channel_att",
            "buctd_coam_position_att", "buctd_da_combine", "buctd_prenet", "buctd_decode_heatmaps",
            "buctd_rasterize_condition", "buctd_flip_channels", "buctd_flip_merge", "buctd_joints_mse", "buctd_adam_step",
            "buctd_crop_warp", "buctd_generate_target", "buctd_pck_accuracy", "buctd_act16_to_nchw32", "buctd_nchw32_to_act16", "buctd_plan_create",
@@ -179,7 +184,7 @@ def load():
         lib.buctd_launch_count.argtypes = [vp]
         lib.buctd_create.argtypes = [C.c_int, C.POINTER(vp)]
         lib.buctd_destroy.argtypes = [vp]
-        for name in list(_IMMEDIATE.values()) + ["buctd_cond_resize3", "buctd_flip_channels", "buctd_flip_merge", "buctd_joints_mse", "buctd_adam_step",
+        for name in list(_IMMEDIATE.values()) + ["buctd_cond_resize3", "buctd_cond_from_kpts", "buctd_flip_channels", "buctd_flip_merge", "buctd_joints_mse", "buctd_adam_step",
                                                      "buctd_crop_warp", "buctd_generate_target", "buctd_pck_accuracy"]:
             getattr(lib, name).argtypes = [vp, vp, vp]
         lib.buctd_act16_to_nchw32.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]

@@ -371,6 +371,9 @@ static int simple_call(buctd_ctx* c, const A* a, int nlaunch, F&& fn) {
 BUCTD_API int buctd_cond_resize3(buctd_ctx* c, const buctd_resize3_args* a, buctd_stream s) {
   return simple_call(c, a, 1, [&](const buctd_resize3_args& x) { return launch_resize3(x, static_cast<cudaStream_t>(s)); });
 }
+BUCTD_API int buctd_cond_from_kpts(buctd_ctx* c, const buctd_cond_kpts_args* a, buctd_stream s) {
+  return simple_call(c, a, 1, [&](const buctd_cond_kpts_args& x) { return launch_cond_from_kpts(x, static_cast<cudaStream_t>(s)); });
+}
 BUCTD_API int buctd_flip_channels(buctd_ctx* c, const buctd_flip_args* a, buctd_stream s) {
   return simple_call(c, a, 1, [&](const buctd_flip_args& x) { return launch_flip_channels(x, static_cast<cudaStream_t>(s)); });
 }

@@ -228,6 +228,109 @@ __global__ void __launch_bounds__(256) raster_sum_kernel(buctd_raster_args a, un
   }
 }
 
+// =================================================================================================
+// Condition pyramid straight from the proposals (stacked mode): rasterise (above) composed with the antialiased
+// resize to the three CoAM scales (ops.cu: triangle filter of 2S taps starting at S*o - S/2, weight 1 - |t - S + 0.5| / S,
+// normalised over the taps inside the image).  Both are separable, so per keypoint and scale there are two short
+// vectors ry[Y] = sum_y wY[Y][y] gy[y], rx[X] = sum_x wX[X][x] gx[x] (float64) and
+// out[b][Y][X][k] = (255 / (max gy max gx)) ry[Y] rx[X].  Grid (8 row slices, 3 scales, B); every CTA recomputes the
+// vectors of its scale (a few thousand FMAs) and writes its slice of rows with 16-byte stores.
+// lib/dataset/JointsDataset.py:457-498 + lib/models/pose_hrnet_coam.py:750-757.
+// =================================================================================================
+constexpr int kCkMaxK = 32;       // keypoint channels (act16 channel stride of the condition maps is 32 for K = 17)
+constexpr int kCkMaxDim = 160;    // largest H/4 or W/4 (640-pixel crops)
+
+__device__ __forceinline__ double aa_resampled(const double* k, int o, int S, int p, int n) {
+  // sum over the 2S taps of output index o of w[t] * g_p[S*o - S/2 + t], normalised by the in-range weights
+  const int lo = S * o - S / 2;
+  // g_p[j] != 0 needs |j - p| <= 7 (a reflected tap only folds back onto pixels within 7 of the border it left through)
+  if (lo > p + 7 || lo + 2 * S - 1 < p - 7) return 0.0;
+  double acc = 0, tot = 0;
+  for (int t = 0; t < 2 * S; ++t) {
+    const int j = lo + t;
+    if (j < 0 || j >= n) continue;
+    const double wt = 1.0 - fabs((double)t - S + 0.5) * (1.0 / S);
+    tot += wt;
+    if (abs(j - p) <= 7) acc += wt * folded(k, j, p, n);
+  }
+  return tot > 0 ? acc / tot : 0.0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) cond_from_kpts_kernel(buctd_cond_kpts_args a) {
+  __shared__ double s_k[15];
+  __shared__ float s_rx[kCkMaxK][kCkMaxDim];
+  __shared__ float s_ry[kCkMaxK][kCkMaxDim];
+  __shared__ int s_px[kCkMaxK], s_py[kCkMaxK];
+  __shared__ float s_amp[kCkMaxK];
+  const int b = blockIdx.z, sc = blockIdx.y;
+  const int S = 4 << sc;
+  const int oh = a.h / S, ow = a.w / S;
+  const int cs = a.out_cs[sc];
+  // rows of this slice
+  const int nrow = (oh + 1) * (ow + 1);
+  const int per = (nrow + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * per, r1 = min(nrow, r0 + per);
+  if (r0 >= r1) return;
+  if (threadIdx.x == 0) gauss15(s_k);
+  if (threadIdx.x < kCkMaxK) {
+    int px = -1, py = -1;
+    bool on = false;
+    if (threadIdx.x < a.k) on = kpt_pixel(a.kpts + ((long long)b * a.k + threadIdx.x) * a.kstride, a.w, a.h, &px, &py);
+    s_px[threadIdx.x] = on ? px : -1;
+    s_py[threadIdx.x] = py;
+  }
+  __syncthreads();
+  if (threadIdx.x < a.k && s_px[threadIdx.x] >= 0) {
+    const int px = s_px[threadIdx.x], py = s_py[threadIdx.x];
+    double mx = 0, my = 0;
+    for (int t = -7; t <= 7; ++t) {
+      if (px + t >= 0 && px + t < a.w) mx = fmax(mx, folded(s_k, px + t, px, a.w));
+      if (py + t >= 0 && py + t < a.h) my = fmax(my, folded(s_k, py + t, py, a.h));
+    }
+    s_amp[threadIdx.x] = (float)(1.0 / (mx * my));           // the rx vector carries the 255
+  }
+  for (int i = threadIdx.x; i < a.k * (ow + oh); i += blockDim.x) {
+    const int k = i / (ow + oh), o = i - k * (ow + oh);
+    if (s_px[k] < 0) continue;
+    if (o < ow) s_rx[k][o] = (float)(aa_resampled(s_k, o, S, s_px[k], a.w) * 255.0);
+    else s_ry[k][o - ow] = (float)aa_resampled(s_k, o - ow, S, s_py[k], a.h);
+  }
+  __syncthreads();
+  T* out = reinterpret_cast<T*>(a.out[sc]) + (long long)b * nrow * cs;
+  const int groups = cs >> 3;
+  for (int i = r0 * groups + threadIdx.x; i < r1 * groups; i += blockDim.x) {
+    const int r = i / groups, c0 = (i - r * groups) << 3;
+    const int Y = r / (ow + 1), X = r - Y * (ow + 1);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = c0 + j;
+      v[j] = (Y < oh && X < ow && k < a.k && s_px[k] >= 0) ? s_amp[k] * s_ry[k][Y] * s_rx[k][X] : 0.f;
+    }
+    uint4 u;
+    u.x = T16<T>::pack2(v[0], v[1]); u.y = T16<T>::pack2(v[2], v[3]);
+    u.z = T16<T>::pack2(v[4], v[5]); u.w = T16<T>::pack2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(out + (long long)r * cs + c0) = u;
+  }
+}
+
+int launch_cond_from_kpts(const buctd_cond_kpts_args& a, cudaStream_t st) {
+  BUCTD_CHECK(a.kpts && a.out[0] && a.out[1] && a.out[2], BUCTD_ERR_INVALID, "cond_from_kpts: null pointer");
+  BUCTD_CHECK(a.k >= 1 && a.k <= kCkMaxK && a.kstride >= 2, BUCTD_ERR_INVALID, "cond_from_kpts: K=%d out of range [1,%d] / kstride", a.k, kCkMaxK);
+  BUCTD_CHECK(a.h % 16 == 0 && a.w % 16 == 0 && a.h / 4 <= kCkMaxDim && a.w / 4 <= kCkMaxDim, BUCTD_ERR_INVALID,
+              "cond_from_kpts: needs H, W multiples of 16 and <= %d (got %dx%d)", 4 * kCkMaxDim, a.h, a.w);
+  for (int i = 0; i < 3; ++i)
+    BUCTD_CHECK(a.out_cs[i] % 8 == 0 && a.k <= a.out_cs[i] && (((uintptr_t)a.out[i]) & 15) == 0, BUCTD_ERR_INVALID,
+                "cond_from_kpts: K %d vs out_cs[%d] %d / alignment", a.k, i, a.out_cs[i]);
+  if (a.batch == 0) return BUCTD_OK;
+  dim3 grid(8, 3, a.batch);
+  if (a.dtype == BUCTD_F16) cond_from_kpts_kernel<__half><<<grid, 256, 0, st>>>(a);
+  else cond_from_kpts_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a);
+  BUCTD_CUDA(cudaGetLastError());
+  return BUCTD_OK;
+}
+
 int launch_raster(const buctd_raster_args& a, cudaStream_t st, int* nlaunch) {
   BUCTD_CHECK(a.kpts && a.out, BUCTD_ERR_INVALID, "raster: null pointer");
   BUCTD_CHECK(a.kstride >= 2 && a.w <= 512 && a.k >= 1, BUCTD_ERR_INVALID, "raster: bad kstride/width/k");

@@ -82,6 +82,7 @@ int tapgemm_init_device();
 int launch_stem(const buctd_stem_args& a, cudaStream_t st);
 int launch_fuse(const buctd_fuse_args& a, cudaStream_t st);
 int launch_resize(const buctd_resize_args& a, cudaStream_t st);
+int launch_cond_from_kpts(const buctd_cond_kpts_args& a, cudaStream_t st);
 int launch_resize3(const buctd_resize3_args& a, cudaStream_t st);
 int launch_chan_att(const buctd_chan_att_args& a, cudaStream_t st, int* nlaunch);
 int launch_pos_att(const buctd_pos_att_args& a, cudaStream_t st);

@@ -33,8 +33,10 @@ __global__ void __launch_bounds__(256) stem_kernel(buctd_stem_args a) {
     int yy = r / PW, xx = r % PW;
     int iy = iy0 + yy, ix = ix0 + xx;
     float v = 0.f;
-    if (iy >= 0 && iy < a.h && ix >= 0 && ix < a.w)
-      v = a.x[(((long long)b * a.x_channels + c) * a.h + iy) * a.w + ix];
+    if (iy >= 0 && iy < a.h && ix >= 0 && ix < a.w) {
+      const long long o = (((long long)b * a.x_channels + c) * a.h + iy) * a.w + ix;
+      v = a.x_half ? __half2float(reinterpret_cast<const __half*>(a.x)[o]) : reinterpret_cast<const float*>(a.x)[o];
+    }
     s_in[c][yy][xx] = v;
   }
   __syncthreads();

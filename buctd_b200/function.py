@@ -43,6 +43,74 @@ def validate_batch(config, model, input, center, scale, flip_pairs=COCO_FLIP_PAI
 
 
 @torch.no_grad()
+def predict_stream(config, model, batches, flip_pairs=COCO_FLIP_PAIRS):
+    """The evaluation loop's hot section over a stream of HOST batches, the way validate() walks its DataLoader
+    (lib/core/function.py:200-270) -- but what crosses PCIe per crop is the normalised RGB crop and 204 B of proposals,
+    not 17 rasterised float32 planes: ``batches`` yields (rgb [B,3,H,W] float32/float16 host tensor -- pinned for an
+    asynchronous copy --, kpts [B,K,>=2] float32 crop pixels, center [B,2], scale [B,2]); every batch goes through
+    ``model.forward_from_proposals`` + ``get_final_preds`` on the device and comes back as one pinned host tensor
+    [B, K, 3] = (x, y, maxval).  The host -> device copy of batch i+1 runs on a side stream under the forward of batch i
+    (two device slots); results are yielded one batch late so that the device -> host read never stalls the queue.
+    TEST.FLIP_TEST is not applied here (it needs the mirrored proposals: use validate_batch)."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    main = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(dev)
+    slots = [None, None]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    freed = [torch.cuda.Event(), torch.cuda.Event()]
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+    outs = [None, None]
+    pp = bool(config.TEST.POST_PROCESS)
+
+    def stage(i, batch):
+        b = i & 1
+        rgb, kp, c, s = batch
+        with torch.cuda.stream(side):
+            if i >= 2:
+                side.wait_event(freed[b])
+            if slots[b] is None or slots[b][0].shape != rgb.shape or slots[b][0].dtype != rgb.dtype or slots[b][1].shape != kp.shape:
+                slots[b] = (torch.empty(rgb.shape, dtype=rgb.dtype, device=dev), torch.empty(kp.shape, dtype=torch.float32, device=dev),
+                            torch.empty(c.shape, dtype=torch.float32, device=dev), torch.empty(s.shape, dtype=torch.float32, device=dev))
+            for d, h in zip(slots[b], (rgb, kp, c, s)):
+                d.copy_(torch.as_tensor(h), non_blocking=True)
+            ready[b].record(side)
+
+    it = iter(batches)
+    try:
+        nxt = next(it)
+    except StopIteration:
+        return
+    stage(0, nxt)
+    i = 0
+    pending = None
+    while nxt is not None:
+        b = i & 1
+        main.wait_event(ready[b])
+        try:
+            nxt = next(it)
+            stage(i + 1, nxt)
+        except StopIteration:
+            nxt = None
+        rgb_d, kp_d, c_d, s_d = slots[b]
+        hm = model.forward_from_proposals(rgb_d, kp_d)
+        preds, maxvals = inference.decode_device(hm, c_d, s_d, post_process=pp)
+        res = torch.cat([preds, maxvals], 2)
+        freed[b].record(main)
+        if outs[b] is None or outs[b].shape != res.shape:
+            outs[b] = torch.empty(res.shape, dtype=torch.float32).pin_memory()
+        outs[b].copy_(res, non_blocking=True)
+        done[b].record(main)
+        if pending is not None:
+            done[pending].synchronize()
+            yield outs[pending]
+        pending = b
+        i += 1
+    if pending is not None:
+        done[pending].synchronize()
+        yield outs[pending]
+
+
+@torch.no_grad()
 def iterative_refine(config, model, input: torch.Tensor, passes: int = 3, center=None, scale=None,
                      cond_mode: str = "stacked", return_all: bool = False):
     """BASELINE.json configs[3]: ``passes`` forwards; pass n+1's condition = rasterised keypoints decoded from pass n

@@ -599,9 +599,11 @@ class PoseHighResolutionNet(nn.Module):
 
     # ---- forward --------------------------------------------------------------------------------
     def forward(self, x: torch.Tensor, _stop_after: Optional[str] = None) -> torch.Tensor:
+        """The reference's ``forward(x[B, 3+Cc, H, W] float32)`` (pose_hrnet_coam.py:488-572, pose_hrnet.py:445-495):
+        RGB planes + condition planes in one tensor, any device."""
         if self.training:
-            raise NotImplementedError("buctd_b200 round 1 implements the inference forward (model.eval()); "
-                                      "the training step (SURVEY.md 8a-T) is not built yet")
+            raise NotImplementedError("model.train(): use buctd_b200.train.TrainStep (the training step has its own plan); "
+                                      "forward() is the inference path (model.eval())")
         if not torch.cuda.is_available():
             raise L.BuctdError("no CUDA device: buctd_b200 has no CPU path")
         arch = self.arch
@@ -616,6 +618,50 @@ class PoseHighResolutionNet(nn.Module):
         need = 3 + arch.in_cond
         if Cx < need or (arch.in_cond == 0 and Cx != 3):
             raise ValueError("expected %d input channels, got %d" % (need, Cx))
+        return self._run(x, Cx, None, _stop_after)
+
+    def forward_from_proposals(self, rgb: torch.Tensor, kpts: torch.Tensor, colors=None) -> torch.Tensor:
+        """Fast-path entry for the conditional top-down call: the normalised crop ``rgb`` [B, 3, H, W] (float32 or
+        float16, host -- ideally pinned -- or device) and the bottom-up proposals ``kpts`` [B, K, >=2] (float32 crop
+        pixels, the ``cond_joints`` the dataset rasterises, lib/dataset/JointsDataset.py:314-326).  The condition is
+        rasterised on the device: 204 B of keypoints per crop cross PCIe instead of 17 float32 planes (7.5 MB).  For the
+        stacked condition of CoAM the three CoAM scales are written directly from the keypoints
+        (buctd_cond_from_kpts); the other modes rasterise at full resolution on the device and take ``forward``.
+        Same result as ``forward(cat(rgb, rasterised condition))`` (heat-maps [B, K, H/4, W/4] float32 on CUDA)."""
+        if self.training:
+            raise NotImplementedError("forward_from_proposals is an inference entry point (model.eval())")
+        if not torch.cuda.is_available():
+            raise L.BuctdError("no CUDA device: buctd_b200 has no CPU path")
+        arch = self.arch
+        if not (arch.use_attention or arch.use_prenet):
+            raise ValueError("forward_from_proposals needs a conditional model (CoAM or preNet)")
+        if rgb.dim() != 4 or rgb.shape[1] != 3 or tuple(rgb.shape[2:]) != (arch.img_h, arch.img_w):
+            raise ValueError("rgb must be [B, 3, %d, %d], got %s" % (arch.img_h, arch.img_w, tuple(rgb.shape)))
+        if rgb.dtype not in (torch.float32, torch.float16):
+            raise ValueError("rgb must be float32 or float16")
+        B = rgb.shape[0]
+        if kpts.dim() != 3 or kpts.shape[0] != B or kpts.shape[2] < 2:
+            raise ValueError("kpts must be [B, K, >=2]")
+        rgb = rgb.cuda(non_blocking=True).contiguous()
+        kp = kpts.cuda(non_blocking=True).float().contiguous()
+        mode = "stacked" if arch.cond_stacked else ("colored" if arch.cond_colored or arch.use_prenet else "plain")
+        H, W = arch.img_h, arch.img_w
+        direct = (arch.use_attention and mode == "stacked" and self.antialias and H % 16 == 0 and W % 16 == 0
+                  and kp.shape[1] <= 32 and sorted(arch.coam) and max(len(v) for v in arch.coam.values()) <= 3
+                  and os.environ.get("BUCTD_COND_DIRECT", "1") != "0")
+        if direct:
+            return self._run(rgb, 3, kp, None)
+        from . import condition
+        x = torch.empty(B, 3 + arch.in_cond, H, W, dtype=torch.float32, device=rgb.device)
+        x[:, :3].copy_(rgb)
+        condition.rasterize_condition(kp, H, W, mode, colors=colors, out=x, c_off=3)
+        return self._run(x, x.shape[1], None, None)
+
+    def _run(self, x: torch.Tensor, Cx: int, kp: Optional[torch.Tensor], _stop_after: Optional[str]) -> torch.Tensor:
+        """x: device tensor whose planes [0, 3) are the RGB crop (float32, or float16 with kp given) and, when ``kp`` is
+        None, planes [3, 3 + Cc) the condition; kp: proposals for the direct condition pyramid."""
+        arch = self.arch
+        B, _, H, W = x.shape
         device = x.device
         key = (B, device.index)
         with torch.cuda.device(device):
@@ -639,14 +685,30 @@ class PoseHighResolutionNet(nn.Module):
             sa = L.StemArgs()
             s1: Act = st["s1"]
             sa.dtype, sa.batch, sa.x_channels, sa.h, sa.w, sa.out_cs = self._dt, B, stem_c, H, W, s1.cs
+            sa.x_half = int(stem_x.dtype == torch.float16)
             sa.x, sa.weight, sa.bias, sa.out = stem_x.data_ptr(), f32["conv1.w"].data_ptr(), f32["conv1.b"].data_ptr(), s1.ptr
             ctx.run(L.OP_STEM, sa, stream)
             conds = st["cond"] if arch.use_attention else {}
-            pyramid = (len(conds) == 3 and self.antialias and H % 16 == 0 and W % 16 == 0 and W <= 288
-                       and all((conds[i].h, conds[i].w) == (H >> (2 + i), W >> (2 + i)) for i in range(3))
-                       and os.environ.get("BUCTD_RESIZE3", "1") != "0")
-            if pyramid:                    # the three CoAM scales in one pass over the condition planes
-                r3 = L.Resize3Args()
+            three = (len(conds) == 3 and self.antialias and H % 16 == 0 and W % 16 == 0
+                     and all((conds[i].h, conds[i].w) == (H >> (2 + i), W >> (2 + i)) for i in range(3)))
+            if kp is not None:
+                # the CoAM scales straight from the proposals; a placement with fewer than three branches gets scratch maps
+                ck = L.CondKptsArgs()
+                ck.dtype, ck.batch, ck.k, ck.kstride, ck.h, ck.w = self._dt, B, kp.shape[1], kp.shape[2], H, W
+                spare = []
+                for i in range(3):
+                    if i in conds:
+                        ck.out_cs[i], ck.out[i] = conds[i].cs, conds[i].ptr
+                    else:
+                        cs = _rup(kp.shape[1], 16)
+                        t = torch.empty(B * ((H >> (2 + i)) + 1) * ((W >> (2 + i)) + 1) * cs, dtype=self._torch_dt, device=device)
+                        spare.append(t)
+                        ck.out_cs[i], ck.out[i] = cs, t.data_ptr()
+                ck.kpts = kp.data_ptr()
+                ctx.call("buctd_cond_from_kpts", ck, stream)
+                self._keepalive_kp = (kp, spare)
+            elif three and W <= 288 and os.environ.get("BUCTD_RESIZE3", "1") != "0":
+                r3 = L.Resize3Args()               # the three CoAM scales in one pass over the condition planes
                 r3.dtype, r3.batch, r3.x_channels, r3.c_off, r3.cc, r3.h, r3.w = self._dt, B, Cx, 3, conds[0].c, H, W
                 for i in range(3):
                     r3.out_cs[i] = conds[i].cs

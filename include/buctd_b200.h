@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BUCTD_ABI_VERSION 1
+#define BUCTD_ABI_VERSION 2
 
 #define BUCTD_OK 0
 #define BUCTD_ERR_INVALID (-1)   /* bad argument / unsupported shape */
@@ -114,7 +114,9 @@ int buctd_tapgemm_chain(buctd_ctx* ctx, const buctd_tapgemm_chain_args* args, bu
  * Replaces conv1/bn1/relu, lib/models/pose_hrnet_coam.py:505-507.  w: float32 [64][27] (ci,ky,kx). */
 typedef struct {
   int32_t dtype, batch, x_channels, h, w, out_cs;
-  const float* x; const float* weight; const float* bias; void* out;
+  int32_t x_half;       /* 0: x is float32 (the reference's tensor); 1: x is IEEE half [B][x_channels][H][W] (halves the H2D copy) */
+  int32_t reserved;
+  const void* x; const float* weight; const float* bias; void* out;
 } buctd_stem_args;
 int buctd_stem_conv(buctd_ctx* ctx, const buctd_stem_args* args, buctd_stream stream);
 
@@ -148,6 +150,22 @@ typedef struct {
   const float* x; void* out[3];
 } buctd_resize3_args;
 int buctd_cond_resize3(buctd_ctx* ctx, const buctd_resize3_args* args, buctd_stream stream);
+
+/* Condition pyramid straight from the proposals (stacked mode): what buctd_rasterize_condition (mode 0) followed by
+ * buctd_cond_resize3 produce, without the full-resolution planes ever existing.  The blurred impulse of keypoint k is
+ * separable, g_k[y][x] = gy_k[y] gx_k[x] 255 / (max gy_k max gx_k) (15-tap sigma-2.6 response with BORDER_REFLECT_101
+ * folding), and so is the antialiased resize, hence out_i[b][Y][X][k] = 255 / peak_k * (sum_y wY_i[Y][y] gy_k[y]) *
+ * (sum_x wX_i[X][x] gx_k[x]) -- two short vectors per keypoint and scale (float64), one 16-bit store per output element.
+ * kpts float32 [B][K][kstride] crop-pixel (x, y, ...), same drawing rule as the rasteriser (truncation, 0 < x < W,
+ * 0 < y < H, pixel (y-1, x-1)); out[i]: act16 [B][H/s_i + 1][W/s_i + 1][out_cs[i]], s = {4, 8, 16}, channels >= K zero.
+ * Replaces get_stacked_condition + the H2D copy of 17 float32 planes per crop + TF.resize x 3,
+ * lib/dataset/JointsDataset.py:471-498, lib/models/pose_hrnet_coam.py:750-757 (481 MB -> 13 KB per 64 crops over PCIe). */
+typedef struct {
+  int32_t dtype, batch, k, kstride, h, w;
+  int32_t out_cs[3]; int32_t reserved;
+  const float* kpts; void* out[3];
+} buctd_cond_kpts_args;
+int buctd_cond_from_kpts(buctd_ctx* ctx, const buctd_cond_kpts_args* args, buctd_stream stream);
 
 /* CoAM channel attention core: att = softmax_c2( yc^T y / sqrt(HW) ) [C x C] per crop, then
  * out[c1][p] = sum_c2 att[c1][c2] y[p][c2], written planar [B][C][HW] (the A operand of the

@@ -125,3 +125,50 @@ def test_rasteriser_writes_into_model_input_channels():
     x = torch.full((B, 3 + K, H, W), -1.0, device="cuda")
     condition.rasterize_condition(kp, H, W, "stacked", out=x, c_off=3)
     assert (x[:, :3] == -1).all() and x[:, 3:].max() > 254.9 and x[:, 3:].min() >= 0
+
+
+@pytest.mark.parametrize("dt", [0, 1])
+@pytest.mark.parametrize("H,W", [(384, 288), (128, 96), (256, 192)])
+def test_cond_pyramid_from_proposals(dt, H, W):
+    """buctd_cond_from_kpts == rasterise (stacked) -> antialiased resize to the three CoAM scales, without the planes:
+    against the device composition (same real values, independent float paths: <= 1 ulp of the 16-bit type at 255) and
+    against the oracle composition (condition_oracle -> hrnet_oracle.resize_aa) within 1e-3 of 255."""
+    from buctd_b200 import _lib as L
+    from oracle import hrnet_oracle as O
+    tdt = torch.float16 if dt == 0 else torch.bfloat16
+    g = np.random.default_rng(21)
+    B, K = 3, 17
+    kp = np.stack([g.uniform(-6, W + 6, (B, K)), g.uniform(-6, H + 6, (B, K)), g.uniform(0, 1, (B, K))], -1).astype(np.float32)
+    kp[0, 0] = (1.2, 1.7, 1); kp[0, 1] = (W - 0.5, H - 0.5, 1); kp[0, 2] = (0.5, 30, 1); kp[0, 3] = (3.3, H - 2.2, 1)
+    kp[0, 4] = (W - 3.0, 5.1, 1); kp[1, :] = 0
+    kpd = torch.from_numpy(kp).cuda()
+    ctx = L.Context.get(0)
+    st = torch.cuda.current_stream().cuda_stream
+    outs, refs = [], []
+    a = L.CondKptsArgs()
+    a.dtype, a.batch, a.k, a.kstride, a.h, a.w = dt, B, K, 3, H, W
+    r3 = L.Resize3Args()
+    x = condition.rasterize_condition(kpd, H, W, "stacked")
+    r3.dtype, r3.batch, r3.x_channels, r3.c_off, r3.cc, r3.h, r3.w = dt, B, K, 0, K, H, W
+    for i in range(3):
+        oh, ow = H >> (2 + i), W >> (2 + i)
+        outs.append(torch.full((B, oh + 1, ow + 1, 32), 7.0, dtype=tdt, device="cuda"))
+        refs.append(torch.zeros(B, oh + 1, ow + 1, 32, dtype=tdt, device="cuda"))
+        a.out_cs[i], a.out[i] = 32, outs[i].data_ptr()
+        r3.out_cs[i], r3.out[i] = 32, refs[i].data_ptr()
+    a.kpts, r3.x = kpd.data_ptr(), x.data_ptr()
+    ctx.call("buctd_cond_from_kpts", a, st)
+    ctx.call("buctd_cond_resize3", r3, st)
+    torch.cuda.synchronize()
+    ulp = 0.125 if dt == 0 else 1.0          # spacing of the 16-bit type in [128, 256)
+    xo = torch.from_numpy(np.stack([C.stacked_condition(kp[b], H, W) for b in range(B)]).astype(np.float32))
+    for i in range(3):
+        o, r = outs[i].float(), refs[i].float()
+        assert o[:, -1].abs().max() == 0 and o[:, :, -1].abs().max() == 0 and o[..., K:].abs().max() == 0     # pads, spare channels
+        assert (o - r).abs().max().item() <= ulp, (i, (o - r).abs().max().item())
+        assert ((o - r).abs() > 0).float().mean().item() < 0.02
+        oh, ow = H >> (2 + i), W >> (2 + i)
+        ora = O.resize_aa(xo, oh, ow).permute(0, 2, 3, 1)
+        tol = 1e-3 * 255 + (ulp / 2)
+        assert (o[:, :oh, :ow, :K].cpu() - ora).abs().max().item() <= tol
+    assert outs[0][1].abs().max() == 0                                       # no proposals: all-zero condition

@@ -147,3 +147,68 @@ def test_dx_fused_chain_plan(monkeypatch, golden_dir, name):
     assert np.abs(outs["1"] - outs["0"]).max() <= 3e-3
     for dxf in outs:
         assert np.abs(outs[dxf] - g["heatmaps"]).max() <= TOL["fp16"]
+
+
+@pytest.mark.parametrize("name", ["coam_w32_128x96_stacked", "coam_w48_384x288_stacked", "coam_w48_384x288_colored", "prenet_w48_384x288",
+                                  "coam_w32_128x96_att1000", "coam_w32_128x96_att0011"])
+@pytest.mark.parametrize("half_rgb", [False, True])
+def test_forward_from_proposals(golden_dir, name, half_rgb):
+    """The fast-path entry (RGB crop + 204 B of proposals per crop, condition rasterised on the device; stacked CoAM:
+    the three scales written directly from the keypoints) against the reference golden and against forward(x)."""
+    from buctd_b200 import synth
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    cfg, net = _net(name, "fp16")
+    xfull = torch.from_numpy(G.case_inputs(name))
+    B = xfull.shape[0]
+    w, h = cfg.MODEL.IMAGE_SIZE
+    kp = torch.from_numpy(synth.synth_keypoints(B, 17, w, h, 1234).astype(np.float32))
+    rgb = xfull[:, :3].contiguous()
+    if half_rgb:
+        rgb = rgb.half()
+    with torch.no_grad():
+        a = net.forward_from_proposals(rgb.pin_memory(), kp).cpu().numpy()
+        b = net(xfull).cpu().numpy()
+    scale = max(1.0, float(np.abs(g["heatmaps"]).max()))
+    assert np.abs(a - g["heatmaps"]).max() <= TOL["fp16"] * scale
+    # vs the planes path (condition planes rasterised by the oracle in float64): 16-bit roundings of the condition maps /
+    # of the half-precision crop apart
+    assert np.abs(a - b).max() <= 4e-3 * scale
+    if not half_rgb:
+        # the same planes rasterised on the device and handed to forward(): the non-direct modes run exactly that
+        from buctd_b200 import condition
+        mode = "stacked" if cfg.DATASET.STACKED_CONDITION else "colored"
+        xd = torch.empty(B, 3 + net.arch.in_cond, h, w, device="cuda")
+        xd[:, :3] = xfull[:, :3].cuda()
+        condition.rasterize_condition(kp.cuda(), h, w, mode, out=xd, c_off=3)
+        with torch.no_grad():
+            c = net(xd).cpu().numpy()
+        direct = bool(cfg.DATASET.STACKED_CONDITION) and net.arch.use_attention and max(len(v) for v in net.arch.coam.values()) <= 3
+        if direct:
+            assert np.abs(a - c).max() <= 2e-3 * scale
+        else:
+            assert np.array_equal(a, c)
+
+
+def test_predict_stream_matches_batch_calls():
+    """function.predict_stream (host batches, H2D of batch i+1 under the forward of batch i, results one batch late) returns
+    exactly what per-batch forward_from_proposals + decode_device return."""
+    from buctd_b200 import function, synth
+    name = "coam_w32_128x96_stacked"
+    cfg, net = _net(name, "fp16")
+    cfg.TEST.POST_PROCESS = True
+    w, h = cfg.MODEL.IMAGE_SIZE
+    batches = []
+    for i in range(5):
+        B = 3 if i != 3 else 2                     # a ragged batch in the middle
+        rgb = torch.from_numpy(synth.synth_rgb(B, w, h, 50 + i)).pin_memory()
+        kp = torch.from_numpy(synth.synth_keypoints(B, 17, w, h, 60 + i).astype(np.float32))
+        c, s = synth.synth_center_scale(B, w, h)
+        batches.append((rgb, kp, torch.from_numpy(c), torch.from_numpy(s)))
+    got = [r.clone() for r in function.predict_stream(cfg, net, batches)]
+    assert len(got) == 5
+    for (rgb, kp, c, s), r in zip(batches, got):
+        with torch.no_grad():
+            hm = net.forward_from_proposals(rgb, kp)
+            p, m = inference.decode_device(hm, c, s, post_process=True)
+        assert torch.equal(torch.cat([p, m], 2).cpu(), r)
+    assert list(function.predict_stream(cfg, net, [])) == []
