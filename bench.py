@@ -104,27 +104,54 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
+CONFIGS = {
+    # name: (variant, cond, batch/GPU, passes, workload label)           BASELINE.json configs[2] is the metric's configuration
+    "coam64": ("coam", "stacked", 64, 1, "BUCTD-CoAM-W48 384x288, 17 kpts, stacked condition, batch=%d/GPU, inference forward + decode"),
+    "prenet32": ("prenet", "colored", 32, 1, "BUCTD-preNet-W48 384x288, 17 kpts, coloured condition, batch=%d/GPU, inference forward + decode"),
+    "refine3": ("coam", "stacked", 32, 3, "BUCTD-CoAM-W48 384x288, 17 kpts, 3x iterative self-conditioning refinement (crop fixed), "
+                                          "batch=%d/GPU, 3 x (forward + decode + re-rasterise)"),
+}
+
+
 def make_inputs(torch, cfg, batch, device, seed):
-    """Synthetic crops on the device: RGB ~ N(0,1); condition = rasterised random proposals (0..255)."""
-    from buctd_b200 import condition
+    """Synthetic crops on the device: RGB ~ N(0,1); proposals uniform in the crop, ~10 % missing; centers / scales."""
     w, h = cfg.MODEL.IMAGE_SIZE
     k = cfg.MODEL.NUM_JOINTS
     g = torch.Generator(device=device).manual_seed(seed)
-    x = torch.empty(batch, 3 + k, h, w, dtype=torch.float32, device=device)
-    x[:, :3] = torch.randn(batch, 3, h, w, generator=g, device=device)
+    rgb = torch.randn(batch, 3, h, w, generator=g, device=device)
     kp = torch.rand(batch, k, 2, generator=g, device=device) * torch.tensor([w - 16.0, h - 16.0], device=device) + 8.0
     kp[torch.rand(batch, k, generator=g, device=device) < 0.1] = 0.0
-    condition.rasterize_condition(kp, h, w, "stacked", out=x, c_off=3)
     c = torch.tensor([w / 2.0, h / 2.0], device=device) + (torch.rand(batch, 2, generator=g, device=device) * 40 - 20)
     s = torch.tensor([w / 200.0, h / 200.0], device=device) * (0.8 + 0.45 * torch.rand(batch, 1, generator=g, device=device))
-    return x, c.contiguous(), s.contiguous()
+    return rgb.contiguous(), kp.contiguous(), c.contiguous(), s.contiguous()
+
+
+def bind_to_gpu_numa(torch, local):
+    """Run this rank (and allocate its pinned host buffers: first touch) on the CPUs of its GPU's NUMA node."""
+    try:
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        dev = torch.cuda.get_device_properties(local).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (dom, bus, dev)
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "numa-local cpus %d (%s)" % (len(cpus), path.split("/")[-2])
+    except Exception as e:                                   # noqa: BLE001 -- best effort
+        return "not bound (%s)" % type(e).__name__
+    return "not bound"
 
 
 def run_native(args):
     import torch
     import torch.distributed as dist
-    from buctd_b200 import inference, pose_hrnet_coam, synth
+    from buctd_b200 import condition, function, inference, pose_hrnet, pose_hrnet_coam, synth
     from buctd_b200.config import make_cfg
+    from buctd_b200.distributed import gather_keypoints
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -133,86 +160,130 @@ def run_native(args):
         raise SystemExit("WORLD_SIZE %d != --gpus %d" % (world, args.gpus))
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    numa = bind_to_gpu_numa(torch, local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
-    B = args.batch
-    cfg = make_cfg("coam", 48, (288, 384), cond="stacked")
-    net = pose_hrnet_coam.get_pose_net(cfg, is_train=False, dtype=args.dtype)
+    variant, cond, B0, passes, label = CONFIGS[args.config]
+    B = args.batch or B0
+    cfg = make_cfg(variant, 48, (288, 384), cond=cond)
+    cfg.TEST.POST_PROCESS = True
+    mod = pose_hrnet_coam if variant == "coam" else pose_hrnet
+    net = mod.get_pose_net(cfg, is_train=False, dtype=args.dtype)
     net.load_state_dict(synth.synth_state_dict(net.arch, 0), strict=True)     # random-init weights of the architecture
     net = net.cuda().eval()
-    x, center, scale = make_inputs(torch, cfg, B, device, 1234 + rank)
     K = cfg.MODEL.NUM_JOINTS
-    from buctd_b200.distributed import gather_keypoints
+    H, W = 384, 288
+    # two resident input sets, alternated: 2 x 85 MB of crops > 126 MB L2 (and every step streams ~2.7 GB of workspace)
+    sets = [make_inputs(torch, cfg, B, device, 1234 + rank + 1000 * j) for j in range(2)]
 
-    def step(xin):
-        hm = net(xin)
-        preds, maxvals = inference.decode_device(hm, center, scale, post_process=True)
-        res = torch.cat([preds, maxvals], -1)                 # [B,K,3] = 204 B per crop
-        if world > 1:                                          # the ONE collective: decoded keypoints only
-            return gather_keypoints(res, B * world)
-        return res
+    def post(res):
+        return gather_keypoints(res, B * world) if world > 1 else res       # the ONE collective: decoded keypoints only
+
+    def step(i):
+        rgb, kp, center, scale = sets[i & 1]
+        if passes > 1:
+            preds, maxvals = function.iterative_refine_from_proposals(cfg, net, rgb, kp, passes, center, scale)
+        else:
+            hm = net.forward_from_proposals(rgb, kp)
+            preds, maxvals = inference.decode_device(hm, center, scale, post_process=True)
+        return post(torch.cat([preds, maxvals], -1))          # [B,K,3] = 204 B per crop
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        fn(n)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1)
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     with torch.no_grad():
-        for _ in range(max(args.warmup, 3)):
-            step(x)
+        for i in range(max(args.warmup, 3)):
+            step(i)
         barrier()
         ctx = net._plans[(B, local)]["ctx"]
         l0 = ctx.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
         sampler.mark_begin()
-        e0.record()
-        for _ in range(args.steps):
-            step(x)
-        e1.record()
-        barrier()
+        ms = timed(lambda n: [step(i) for i in range(n)], args.steps)
         sampler.mark_end()
-        ms = e0.elapsed_time(e1)
         launches = ctx.launch_count() - l0
         clocks = sampler.stop() if rank == 0 else None
 
-        # ---- end to end: host buffers, H2D of every step's input + D2H of the decoded result ----------
-        xh = [x.cpu().pin_memory() for _ in range(1)][0]
-        out_h = torch.empty(B, K, 3).pin_memory()
-        copy_stream = torch.cuda.Stream(device)
-        xd = [torch.empty_like(x) for _ in range(2)]
-        ready = [torch.cuda.Event() for _ in range(2)]
-        freed = [torch.cuda.Event() for _ in range(2)]
+        # ---- end to end through the public API with HOST buffers ------------------------------------------
+        # function.predict_stream(cfg, model, host batches): pinned host crop + proposals -> device (side stream, under the
+        # previous batch's forward) -> forward_from_proposals + get_final_preds -> pinned host [B,K,3].
+        rgb_dt = torch.float16 if args.e2e_rgb == "f16" else torch.float32
+        host = []
+        for rgb, kp, c, s in sets:
+            host.append((rgb.to(rgb_dt).cpu().pin_memory(), kp.cpu().pin_memory(), c.cpu().pin_memory(), s.cpu().pin_memory()))
+        sink = torch.zeros(K, 3)
 
         def e2e_loop(n):
-            main = torch.cuda.current_stream(device)
-            for i in range(n):
-                b = i & 1
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(freed[b]) if i >= 2 else None
-                    xd[b].copy_(xh, non_blocking=True)          # 566 MB pinned host -> device
-                    ready[b].record(copy_stream)
-                main.wait_event(ready[b])
-                res = step(xd[b])
-                freed[b].record(main)
-                out_h.copy_(res[:B] if world == 1 else res[rank * B:(rank + 1) * B], non_blocking=True)   # 13 KB device -> host
-            main.synchronize()
+            if passes > 1:
+                out_h = torch.empty(B * world, K, 3).pin_memory()
+                for i in range(n):
+                    rgb, kp, c, s = host[i & 1]
+                    p, m = function.iterative_refine_from_proposals(cfg, net, rgb, kp, passes, c.cuda(non_blocking=True), s.cuda(non_blocking=True))
+                    out_h.copy_(post(torch.cat([p, m], -1)), non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                return
+            for res in function.predict_stream(cfg, net, (host[i & 1] for i in range(n)), post=post):
+                sink.add_(res[0])                               # the host consumes every result
 
-        e2e_loop(2)
-        barrier()
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0.record()
-        e2e_loop(args.steps)
-        t1.record()
-        barrier()
-        ms_e2e = t0.elapsed_time(t1)
+        e2e_loop(3)
+        ms_e2e = timed(e2e_loop, args.steps)
+        h2d = sum(int(t.numel() * t.element_size()) for t in host[0])
+        d2h = int(B * world * K * 3 * 4)
+        e2e_api = ("function.predict_stream(cfg, model, host batches) -> model.forward_from_proposals + decode_device"
+                   if passes == 1 else "function.iterative_refine_from_proposals(cfg, model, rgb_host, kpts_host, 3, center, scale)")
 
-        # ---- dominant launch class alone: BasicBlock conv 48->48 3x3 @96x72 (64 launches / forward) ---
-        kern = time_dominant_conv(torch, net, B, local)
+        # ---- the reference-shaped call: model(x[B, 3+Cc, H, W] float32) with the rasterised planes ------------
+        planes = None
+        if passes == 1 and world == 1 and not args.quick:
+            mode = "stacked" if cond == "stacked" else "colored"
+            xs = []
+            for rgb, kp, c, s in sets[:1]:
+                x = torch.empty(B, 3 + net.arch.in_cond, H, W, device=device)
+                x[:, :3] = rgb
+                condition.rasterize_condition(kp, H, W, mode, out=x, c_off=3)
+                xs.append(x)
+            xh = xs[0].cpu().pin_memory()
+            out_h = torch.empty(B, K, 3).pin_memory()
+
+            def planes_dev(n):
+                for i in range(n):
+                    hm = net(xs[0])
+                    p, m = inference.decode_device(hm, sets[0][2], sets[0][3], post_process=True)
+
+            def planes_host(n):
+                for i in range(n):
+                    hm = net(xh.cuda(non_blocking=True))
+                    p, m = inference.decode_device(hm, sets[0][2], sets[0][3], post_process=True)
+                    out_h.copy_(torch.cat([p, m], -1), non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+
+            nn_ = max(5, args.steps // 4)
+            planes_dev(2); planes_host(2)
+            t_dev, t_host = timed(planes_dev, nn_), timed(planes_host, nn_)
+            planes = {"api": "model(x[B,%d,H,W] float32) + decode_device (the reference's forward signature)" % xs[0].shape[1],
+                      "value": round(B * nn_ / (t_dev / 1e3), 2), "e2e_value": round(B * nn_ / (t_host / 1e3), 2), "unit": "crops/s",
+                      "h2d_bytes_per_step": int(xh.numel() * 4), "steps": nn_,
+                      "note": "e2e_value: pinned host tensor -> x.cuda() -> forward -> decode -> host, no overlap"}
+            del xs, xh
+
+        kern = time_dominant_conv(torch, net, B, local) if variant == "coam" else None
+        lib = None
+        if world == 1 and passes == 1 and not args.no_gpu_baseline and not args.quick:
+            lib = gpu_library_baseline(torch, cfg, net, sets[0], variant, args.lib_batch or B)
 
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=device)
@@ -226,25 +297,97 @@ def run_native(args):
     crops = B * world * args.steps
     value = crops / (ms / 1e3)
     per_gpu = value / world
-    ach = per_gpu * F3X3_GFLOP["coam"] / 1e3
+    ach = per_gpu * passes * F3X3_GFLOP[variant] / 1e3
     out = {
-        "metric": METRIC, "value": round(value, 2), "unit": "crops/s", "n_gpus": world, "steps": args.steps,
+        "metric": METRIC if args.config == "coam64" else "crops/sec at 384x288 (%s)" % args.config,
+        "value": round(value, 2), "unit": "crops/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": WORKLOAD % B, "global_batch": B * world, "parallelism": "crops sharded, dp%d" % world,
-                   "weights": "random-init (buctd_b200.synth, seed 0)", "l2": "per-step input 566 MB > 126 MB L2",
-                   "collective": "one NCCL all_gather of decoded [B,17,3] per step" if world > 1 else "none"},
-        "roofline": roofline(kern, peaks, ach, per_gpu),
+        "config": {"workload": label % B, "name": args.config, "global_batch": B * world, "parallelism": "crops sharded, dp%d" % world,
+                   "weights": "random-init (buctd_b200.synth, seed 0)",
+                   "api": "model.forward_from_proposals(rgb[B,3,H,W], kpts[B,K,2]) + decode_device, inputs resident in HBM",
+                   "l2": "two resident input sets alternate (2 x %d MB > 126 MB L2); each step streams ~GBs of workspace" % (B * 3 * H * W * 4 >> 20),
+                   "collective": "one NCCL all_gather of decoded [B,17,3] per step" if world > 1 else "none",
+                   "host_binding": numa},
+        "roofline": roofline(kern, peaks, ach, per_gpu * passes, variant),
         "e2e": {"value": round(crops / (ms_e2e / 1e3), 2), "unit": "crops/s",
-                "h2d_bytes_per_step": int(x.numel() * 4), "d2h_bytes_per_step": int(B * K * 3 * 4),
-                "ms_per_step": round(ms_e2e / args.steps, 4), "api": "model(x_host) + decode_device + .cpu()"},
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": round(ms_e2e / args.steps, 4), "api": e2e_api, "rgb_host_dtype": args.e2e_rgb},
         "gpu_launches": int(launches), "clocks": clocks,
     }
-    if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(sample_crops=4, iters=2)
+    if planes is not None:
+        out["planes_api"] = planes
+    if lib is not None:
+        out["gpu_library_baseline"] = lib["rates"]
+        out["parity"] = lib["parity"]
+    if world == 1 and not args.no_cpu_baseline and not args.quick:
+        out["cpu_baseline"] = cpu_baseline(sample_crops=4, iters=2, variant=variant, cond=cond)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def gpu_library_baseline(torch, cfg, net, inputs, variant, batch):
+    """The bar BASELINE.md section 3 names: the reference network on the SAME B200 through PyTorch eager (cuDNN / cuBLAS / ATen)
+    -- (fp32) TF32 off, the numerical oracle; (tf32) PyTorch's default for the reference's fp32 model (cuDNN TF32 convolutions);
+    (bf16_cl) autocast(bfloat16) + channels_last, the strongest library configuration.  /root/reference does not exist on the GPU
+    box, so the network is oracle/hrnet_oracle.forward (the functional torch restatement pinned to the reference by
+    tests/test_oracle_vs_golden.py) -- the same ATen/cuDNN calls the reference's nn.Modules make.  Forward only (the reference
+    then decodes on the host: cpu_baseline times that).  Also the parity of THIS run: max-abs heat-map error of the CUDA path
+    against the fp32 (TF32 off) library forward on the same crops."""
+    import contextlib
+    from buctd_b200 import condition
+    from oracle import hrnet_oracle
+    rgb, kp, c, s = inputs
+    B = min(batch, rgb.shape[0])
+    H, W = rgb.shape[2], rgb.shape[3]
+    mode = "stacked" if cfg.DATASET.STACKED_CONDITION else "colored"
+    x = torch.empty(B, 3 + net.arch.in_cond, H, W, device=rgb.device)
+    x[:, :3] = rgb[:B]
+    condition.rasterize_condition(kp[:B], H, W, mode, out=x, c_off=3)
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    rates, ref_hm = {}, None
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True                      # cfg.CUDNN.BENCHMARK, tools/test.py:84
+    try:
+        for name in ("fp32", "tf32", "bf16_cl"):
+            torch.backends.cudnn.allow_tf32 = name != "fp32"
+            torch.backends.cuda.matmul.allow_tf32 = False     # PyTorch default
+            xin, sdn, amp = x, sd, contextlib.nullcontext()
+            if name == "bf16_cl":
+                xin = x.contiguous(memory_format=torch.channels_last)
+                sdn = {k: (v.contiguous(memory_format=torch.channels_last) if v.dim() == 4 else v) for k, v in sd.items()}
+                amp = torch.autocast("cuda", dtype=torch.bfloat16)
+            with amp:
+                for _ in range(2):
+                    hm = hrnet_oracle.forward(sdn, cfg, xin)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n = 3
+                e0.record()
+                for _ in range(n):
+                    hm = hrnet_oracle.forward(sdn, cfg, xin)
+                e1.record()
+                torch.cuda.synchronize()
+            rates[name] = {"value": round(B * n / (e0.elapsed_time(e1) / 1e3), 2), "unit": "crops/s", "batch": B, "steps": n}
+            if name == "fp32":
+                ref_hm = hm.float().clone()
+            else:
+                rates[name]["max_abs_err_vs_fp32"] = float((hm.float() - ref_hm).abs().max())
+            del hm
+            torch.cuda.empty_cache()
+        mine = net.forward_from_proposals(rgb[:B], kp[:B])
+        mine2 = net(x)
+        parity = {"max_abs_err_vs_fp32_library": float((mine - ref_hm).abs().max()),
+                  "max_abs_err_planes_api": float((mine2 - ref_hm).abs().max()),
+                  "ref_abs_max": float(ref_hm.abs().max()), "crops": B, "dtype": net.compute_dtype,
+                  "argmax_agree": float((mine.flatten(2).argmax(-1) == ref_hm.flatten(2).argmax(-1)).float().mean()),
+                  "bound": "1e-2 for the 16-bit path (north_star), heat-maps of O(1)"}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+    rates["what"] = ("reference network through PyTorch eager on this GPU (oracle/hrnet_oracle.forward: functional restatement, same "
+                     "ATen/cuDNN calls), forward only, batch %d" % B)
+    return {"rates": rates, "parity": parity}
 
 
 def dominant_traffic():
@@ -263,7 +406,7 @@ def dominant_traffic():
     return None, None
 
 
-def roofline(kern, peaks, path_tflops, per_gpu):
+def roofline(kern, peaks, path_tflops, per_gpu, variant="coam"):
     """`roofline` of the bench line: the dominant kernel (the BasicBlock 3x3 convolutions of branch 0: 17.5 % of a
     forward, profiles/README.md) timed alone with CUDA events -> burst peak; plus the whole path against the
     3x3-conv tensor-core roofline BASELINE.json asks for (kernels timed inside a long step -> sustained peak)."""
@@ -280,8 +423,8 @@ def roofline(kern, peaks, path_tflops, per_gpu):
                     "hbm_bytes_min_per_launch": kern["hbm_bytes_min_per_conv"] * kern["convs_per_launch"]})
     out["path_3x3"] = {"achieved": round(path_tflops, 2), "peak": peaks["tflops_sustained"],
                        "frac": round(path_tflops / peaks["tflops_sustained"], 4),
-                       "what": "crops/s/GPU x 70.34 GFLOP of 3x3 convs per crop (BASELINE.md) over the sustained measured peak",
-                       "all_contractions_tflops": round(per_gpu * FTOTAL_GFLOP["coam"] / 1e3, 2)}
+                       "what": "forwards/s/GPU x %.2f GFLOP of 3x3 convs per crop (BASELINE.md) over the sustained measured peak" % F3X3_GFLOP[variant],
+                       "all_contractions_tflops": round(per_gpu * FTOTAL_GFLOP[variant] / 1e3, 2)}
     return out
 
 
@@ -319,7 +462,7 @@ def time_dominant_conv(torch, net, B, local):
             "hbm_bytes_min_per_conv": int(2 * B * 97 * 73 * 48 * 2), "note": "back-to-back launches: activations stay in L2"}
 
 
-def cpu_baseline(sample_crops=4, iters=2):
+def cpu_baseline(sample_crops=4, iters=2, variant="coam", cond="stacked"):
     """The oracle port of the reference forward + get_final_preds on the host cores (reported baseline only)."""
     import torch
     from buctd_b200 import synth
@@ -328,12 +471,15 @@ def cpu_baseline(sample_crops=4, iters=2):
     from oracle import condition_oracle, decode_oracle, hrnet_oracle
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = make_cfg("coam", 48, (288, 384), cond="stacked")
+    cfg = make_cfg(variant, 48, (288, 384), cond=cond)
     sd = synth.synth_state_dict(HRNetArch(cfg), 0)
     rgb = synth.synth_rgb(sample_crops, 288, 384)
     kp = synth.synth_keypoints(sample_crops, 17, 288, 384)
-    cond = np.stack([condition_oracle.stacked_condition(kp[b], 384, 288) for b in range(sample_crops)]).astype(np.float32)
-    x = torch.from_numpy(np.concatenate([rgb, cond], 1))
+    if cond == "stacked":
+        cnd = np.stack([condition_oracle.stacked_condition(kp[b], 384, 288) for b in range(sample_crops)]).astype(np.float32)
+    else:
+        cnd = np.stack([condition_oracle.colored_condition(kp[b], 384, 288, condition_oracle.default_colors()) for b in range(sample_crops)]).astype(np.float32)
+    x = torch.from_numpy(np.concatenate([rgb, cnd], 1))
     c, s = synth.synth_center_scale(sample_crops, 288, 384)
     with torch.no_grad():
         hrnet_oracle.forward(sd, cfg, x)                       # warm-up
@@ -390,7 +536,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "crops/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warm + 2, "ms_per_step": round(dt / steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD % args.batch, "sample_crops_per_step": n},
+        "config": {"workload": WORKLOAD % 64, "sample_crops_per_step": n},
         "cpu_baseline": {"value": v, "unit": "crops/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -403,7 +549,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--dtype", default=os.environ.get("BUCTD_DTYPE", "fp16"), choices=["fp16", "bf16"])
-    ap.add_argument("--batch", type=int, default=64, help="crops per GPU")
+    ap.add_argument("--config", default="coam64", choices=sorted(CONFIGS) + ["train"],
+                    help="coam64 = BASELINE.json's metric configuration (configs[2]); prenet32 / refine3 / train = configs[1] / [3] / [4]")
+    ap.add_argument("--batch", type=int, default=0, help="crops per GPU (0: the configuration's own)")
+    ap.add_argument("--e2e-rgb", default="f32", choices=["f32", "f16"], help="dtype of the host crop the e2e loop ships")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--lib-batch", type=int, default=0)
+    ap.add_argument("--quick", action="store_true", help="main + e2e numbers only (no baselines / planes API leg)")
     ap.add_argument("--ref-crops", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -415,6 +567,9 @@ def main():
     sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "train":
+        from buctd_b200 import train_bench
+        train_bench.run(args, ClockSampler, load_peaks)
     else:
         run_native(args)
     sys.stdout.flush()

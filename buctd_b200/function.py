@@ -43,7 +43,7 @@ def validate_batch(config, model, input, center, scale, flip_pairs=COCO_FLIP_PAI
 
 
 @torch.no_grad()
-def predict_stream(config, model, batches, flip_pairs=COCO_FLIP_PAIRS):
+def predict_stream(config, model, batches, post=None):
     """The evaluation loop's hot section over a stream of HOST batches, the way validate() walks its DataLoader
     (lib/core/function.py:200-270) -- but what crosses PCIe per crop is the normalised RGB crop and 204 B of proposals,
     not 17 rasterised float32 planes: ``batches`` yields (rgb [B,3,H,W] float32/float16 host tensor -- pinned for an
@@ -51,7 +51,8 @@ def predict_stream(config, model, batches, flip_pairs=COCO_FLIP_PAIRS):
     ``model.forward_from_proposals`` + ``get_final_preds`` on the device and comes back as one pinned host tensor
     [B, K, 3] = (x, y, maxval).  The host -> device copy of batch i+1 runs on a side stream under the forward of batch i
     (two device slots); results are yielded one batch late so that the device -> host read never stalls the queue.
-    TEST.FLIP_TEST is not applied here (it needs the mirrored proposals: use validate_batch)."""
+    ``post`` (optional) maps the device result [B, K, 3] before it is read back -- the multi-GPU loop passes the ONE
+    collective there (distributed.gather_keypoints).  TEST.FLIP_TEST is not applied here (use validate_batch)."""
     dev = torch.device("cuda", torch.cuda.current_device())
     main = torch.cuda.current_stream(dev)
     side = torch.cuda.Stream(dev)
@@ -95,6 +96,8 @@ def predict_stream(config, model, batches, flip_pairs=COCO_FLIP_PAIRS):
         hm = model.forward_from_proposals(rgb_d, kp_d)
         preds, maxvals = inference.decode_device(hm, c_d, s_d, post_process=pp)
         res = torch.cat([preds, maxvals], 2)
+        if post is not None:
+            res = post(res)
         freed[b].record(main)
         if outs[b] is None or outs[b].shape != res.shape:
             outs[b] = torch.empty(res.shape, dtype=torch.float32).pin_memory()
@@ -131,6 +134,31 @@ def iterative_refine(config, model, input: torch.Tensor, passes: int = 3, center
         if n + 1 < passes:
             kp = (coords * stride).contiguous()
             condition.rasterize_condition(kp, H, W, cond_mode, out=x, c_off=3)
+    return outs if return_all else outs[-1]
+
+
+@torch.no_grad()
+def iterative_refine_from_proposals(config, model, rgb: torch.Tensor, kpts: torch.Tensor, passes: int = 3, center=None, scale=None,
+                                    return_all: bool = False):
+    """``iterative_refine`` on the fast-path entry: pass 1 is conditioned on the bottom-up proposals ``kpts`` [B,K,>=2]
+    (crop pixels), pass n+1 on the keypoints decoded from pass n (kpt_crop = stride * (x_hm, y_hm), crop fixed); the
+    condition planes never exist at full resolution.  rgb [B,3,H,W] float32/float16, host or device."""
+    rgb = rgb.cuda(non_blocking=True)
+    kp = kpts.cuda(non_blocking=True).float()[:, :, :2].contiguous()
+    W = rgb.shape[3]
+    outs: List[tuple] = []
+    pp = bool(config.TEST.POST_PROCESS)
+    for n in range(passes):
+        hm = model.forward_from_proposals(rgb, kp)
+        stride = float(W) / float(hm.shape[3])
+        last = n + 1 == passes
+        if center is not None and (last or return_all):
+            outs.append(inference.decode_device(hm, center, scale, post_process=pp))
+        if not last or center is None:
+            coords, maxvals = inference.decode_device(hm, None, None, post_process=pp)
+            if center is None:
+                outs.append((coords, maxvals))
+            kp = (coords * stride).contiguous()
     return outs if return_all else outs[-1]
 
 

@@ -125,8 +125,8 @@ def resize_aa(cond: torch.Tensor, h: int, w: int) -> torch.Tensor:
             wt = (1.0 - ((js - center + 0.5) / (scale if scale >= 1.0 else 1.0)).abs()).clamp(min=0)
             m[i, lo:hi] = wt / wt.sum()
         return m
-    wh = weights(cond.shape[2], h).to(cond.dtype)
-    ww = weights(cond.shape[3], w).to(cond.dtype)
+    wh = weights(cond.shape[2], h).to(device=cond.device, dtype=cond.dtype)
+    ww = weights(cond.shape[3], w).to(device=cond.device, dtype=cond.dtype)
     # horizontal pass first, then vertical (ATen's separable order); fp32 like the reference
     t = torch.einsum("bchw,xw->bchx", cond, ww)
     return torch.einsum("bchx,yh->bcyx", t, wh)
