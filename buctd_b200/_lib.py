@@ -45,7 +45,7 @@ class TapGemmChainArgs(C.Structure):
 
 class StemArgs(C.Structure):
     _fields_ = [("dtype", i32), ("batch", i32), ("x_channels", i32), ("h", i32), ("w", i32), ("out_cs", i32),
-                ("x_half", i32), ("reserved", i32), ("x", fp), ("weight", fp), ("bias", fp), ("out", vp)]
+                ("x_half", i32), ("no_relu", i32), ("x", fp), ("weight", fp), ("bias", fp), ("out", vp)]
 
 
 class FuseArgs(C.Structure):
@@ -72,12 +72,14 @@ class CondKptsArgs(C.Structure):
 
 class ChanAttArgs(C.Structure):
     _fields_ = [("dtype", i32), ("batch", i32), ("h", i32), ("w", i32), ("c", i32), ("y_cs", i32), ("yc_cs", i32),
-                ("out_stride", i32), ("y", vp), ("yc", vp), ("scratch", fp), ("out", vp)]
+                ("out_stride", i32), ("drop_p", C.c_float), ("drop_seed", C.c_uint32),
+                ("y", vp), ("yc", vp), ("scratch", fp), ("out", vp)]
 
 
 class PosAttArgs(C.Structure):
     _fields_ = [("dtype", i32), ("batch", i32), ("h", i32), ("w", i32), ("c", i32), ("q_cs", i32), ("k_cs", i32),
-                ("v_cs", i32), ("o_cs", i32), ("reserved", i32), ("q", vp), ("k", vp), ("v", vp), ("o", vp)]
+                ("v_cs", i32), ("o_cs", i32), ("reserved", i32), ("drop_p", C.c_float), ("drop_seed", C.c_uint32),
+                ("q", vp), ("k", vp), ("v", vp), ("o", vp), ("lse2", fp)]
 
 
 class DaCombineArgs(C.Structure):
@@ -142,6 +144,93 @@ class PckArgs(C.Structure):
                 ("pred", fp), ("target", fp), ("acc", vp), ("cnt", vp)]
 
 
+f32c, u32, f64c = C.c_float, C.c_uint32, C.c_double
+
+
+class Gemm16Args(C.Structure):
+    _fields_ = [("dtype", i32), ("a_mn_major", i32), ("b_mn_major", i32), ("m", i32), ("n", i32), ("k", i32),
+                ("nbatch", i32), ("nsplit", i32), ("ntaps", i32), ("b_rows", i32),
+                ("lda", i32), ("ldb", i32), ("ldd", i32), ("out_f32", i32), ("accumulate", i32), ("reserved", i32),
+                ("a_batch_stride", i64), ("b_batch_stride", i64), ("d_t_stride", i64), ("d_s_stride", i64), ("d_b_stride", i64),
+                ("tap_off", i32 * 9), ("alpha", f32c), ("a", vp), ("b", vp), ("d", vp)]
+
+
+class WgradReduceArgs(C.Structure):
+    _fields_ = [("n", i32), ("k", i32), ("ntaps", i32), ("nsplit", i32), ("accumulate", i32), ("reserved", i32),
+                ("inv_scale", f32c), ("pad_", f32c), ("partial", fp), ("grad", fp)]
+
+
+BN_BLOCKS = 296
+
+
+class BnStatsArgs(C.Structure):
+    _fields_ = [("dtype", i32), ("batch", i32), ("h", i32), ("w", i32), ("c", i32), ("z_cs", i32), ("eps", f32c), ("momentum", f32c),
+                ("z", vp), ("mean_rstd", fp), ("running_mean", fp), ("running_var", fp), ("scratch", vp)]
+
+
+class BnApplyArgs(C.Structure):
+    _fields_ = [("dtype", i32), ("batch", i32), ("h", i32), ("w", i32), ("c", i32), ("z_cs", i32), ("res_cs", i32), ("out_cs", i32),
+                ("relu", i32), ("reserved", i32), ("z", vp), ("mean_rstd", fp), ("gamma", fp), ("beta", fp), ("residual", vp), ("out", vp)]
+
+
+class BnBwdArgs(C.Structure):
+    _fields_ = [("dtype", i32), ("batch", i32), ("h", i32), ("w", i32), ("c", i32), ("dy_cs", i32), ("y_cs", i32), ("z_cs", i32),
+                ("dz_cs", i32), ("dres_cs", i32), ("relu", i32), ("res_accumulate", i32), ("inv_scale", f32c), ("pad_", f32c),
+                ("dy", vp), ("y", vp), ("z", vp), ("mean_rstd", fp), ("gamma", fp), ("dgamma", fp), ("dbeta", fp), ("scratch", vp),
+                ("dz", vp), ("dres", vp)]
+
+
+class ColsumArgs(C.Structure):
+    _fields_ = [("dtype", i32), ("c", i32), ("cs", i32), ("accumulate", i32), ("rows", i64), ("inv_scale", f32c), ("pad_", f32c),
+                ("dy", vp), ("dbias", fp), ("scratch", vp)]
+
+
+class ZeroStuffArgs(C.Structure):
+    _fields_ = [("dtype", i32), ("batch", i32), ("h", i32), ("w", i32), ("cs", i32), ("reserved", i32), ("in_", vp), ("out", vp)]
+
+
+class FuseBwdArgs(C.Structure):
+    _fields_ = [("dtype", i32), ("batch", i32), ("h", i32), ("w", i32), ("c", i32), ("cs", i32), ("nterms", i32), ("relu", i32),
+                ("dout", vp), ("out", vp), ("dterm", vp * 4), ("term_cs", i32 * 4), ("term_shift", i32 * 4), ("term_accumulate", i32 * 4)]
+
+
+class Add16Args(C.Structure):
+    _fields_ = [("dtype", i32), ("cs_out", i32), ("cs_a", i32), ("c", i32), ("rows", i64), ("accumulate", i32), ("reserved", i32),
+                ("a", vp), ("out", vp)]
+
+
+class RelayoutArgs(C.Structure):
+    _fields_ = [("dtype", i32), ("batch", i32), ("h", i32), ("w", i32), ("c", i32), ("cs", i32), ("p_stride", i32), ("accumulate", i32),
+                ("in_", vp), ("out", vp)]
+
+
+class ChanSoftmaxBwdArgs(C.Structure):
+    _fields_ = [("dtype", i32), ("batch", i32), ("c", i32), ("ld", i32), ("prob_stride", i64), ("scale", f32c), ("drop_p", f32c),
+                ("seed", u32), ("reserved", i32), ("probs", fp), ("da_d", fp), ("ds", vp), ("probs_d", vp)]
+
+
+class PosSoftmaxBwdArgs(C.Structure):
+    _fields_ = [("dtype", i32), ("batch", i32), ("h", i32), ("w", i32), ("ld", i32), ("reserved", i32), ("inv_sqrt_c", f32c),
+                ("drop_p", f32c), ("seed", u32), ("reserved2", i32), ("s", fp), ("dpd", fp), ("lse2", fp), ("delta", fp), ("pd", vp), ("ds", vp)]
+
+
+class RowdotArgs(C.Structure):
+    _fields_ = [("dtype", i32), ("c", i32), ("a_cs", i32), ("b_cs", i32), ("rows", i64), ("a", vp), ("b", vp), ("out", fp)]
+
+
+class StemWgradArgs(C.Structure):
+    _fields_ = [("dtype", i32), ("batch", i32), ("x_channels", i32), ("h", i32), ("w", i32), ("dz_cs", i32), ("x_half", i32), ("reserved", i32),
+                ("x", vp), ("dz", vp), ("partial", fp)]
+
+
+class RepackArgs(C.Structure):
+    _fields_ = [("dtype", i32), ("n_entries", i32), ("param", fp), ("w16", vp), ("table", vp)]
+
+
+TRAIN_EXPORTS = ["buctd_gemm16", "buctd_wgrad_reduce", "buctd_bn_stats", "buctd_bn_apply", "buctd_bn_bwd", "buctd_colsum", "buctd_zero_stuff",
+                 "buctd_hr_fuse_bwd", "buctd_add16", "buctd_planar_to_act16", "buctd_act16_to_planar", "buctd_chan_softmax_bwd",
+                 "buctd_pos_softmax_bwd", "buctd_rowdot", "buctd_stem_wgrad", "buctd_repack_weights"]
+
 OP_STRUCT = {OP_TAPGEMM: TapGemmArgs, OP_STEM: StemArgs, OP_FUSE: FuseArgs, OP_RESIZE: ResizeArgs,
              OP_CHAN_ATT: ChanAttArgs, OP_POS_ATT: PosAttArgs, OP_DA_COMBINE: DaCombineArgs, OP_PRENET: PrenetArgs,
              OP_DECODE: DecodeArgs, OP_RASTER: RasterArgs, OP_CHAIN: TapGemmChainArgs}
@@ -153,7 +242,7 @@ EXPORTS = ["buctd_abi_version", "buctd_last_error", "buctd_create", "buctd_destr
            "buctd_rasterize_condition", "buctd_flip_channels", "buctd_flip_merge", "buctd_joints_mse", "buctd_adam_step",
            "buctd_crop_warp", "buctd_generate_target", "buctd_pck_accuracy", "buctd_act16_to_nchw32", "buctd_nchw32_to_act16", "buctd_plan_create",
            "buctd_plan_destroy", "buctd_plan_add", "buctd_plan_add_lane", "buctd_plan_num_lanes", "buctd_plan_instantiate",
-           "buctd_plan_size", "buctd_plan_run", "buctd_plan_run_range"]
+           "buctd_plan_size", "buctd_plan_run", "buctd_plan_run_range"] + TRAIN_EXPORTS
 
 _IMMEDIATE = {OP_TAPGEMM: "buctd_tapgemm", OP_STEM: "buctd_stem_conv", OP_FUSE: "buctd_hr_fuse",
               OP_RESIZE: "buctd_cond_resize", OP_CHAN_ATT: "buctd_coam_channel_att",
@@ -185,7 +274,7 @@ def load():
         lib.buctd_create.argtypes = [C.c_int, C.POINTER(vp)]
         lib.buctd_destroy.argtypes = [vp]
         for name in list(_IMMEDIATE.values()) + ["buctd_cond_resize3", "buctd_cond_from_kpts", "buctd_flip_channels", "buctd_flip_merge", "buctd_joints_mse", "buctd_adam_step",
-                                                     "buctd_crop_warp", "buctd_generate_target", "buctd_pck_accuracy"]:
+                                                     "buctd_crop_warp", "buctd_generate_target", "buctd_pck_accuracy"] + TRAIN_EXPORTS:
             getattr(lib, name).argtypes = [vp, vp, vp]
         lib.buctd_act16_to_nchw32.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
         lib.buctd_nchw32_to_act16.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -291,6 +291,7 @@ BUCTD_API int buctd_create(int device, buctd_ctx** out) {
   int rc = tapgemm_init_device();
   if (!rc) rc = tapgemm_chain_init_device();
   if (!rc) rc = pos_att_tc_init_device();
+  if (!rc) rc = gemm16_init_device();
   if (!rc && get_encode_tiled() == nullptr) {
     set_error("buctd_create: cuTensorMapEncodeTiled driver entry point not found");
     rc = BUCTD_ERR_NO_DEVICE;
@@ -394,6 +395,54 @@ BUCTD_API int buctd_generate_target(buctd_ctx* c, const buctd_gen_target_args* a
 }
 BUCTD_API int buctd_pck_accuracy(buctd_ctx* c, const buctd_pck_args* a, buctd_stream s) {
   return simple_call(c, a, 1, [&](const buctd_pck_args& x) { return launch_pck(x, static_cast<cudaStream_t>(s)); });
+}
+BUCTD_API int buctd_gemm16(buctd_ctx* c, const buctd_gemm16_args* a, buctd_stream s) {
+  return simple_call(c, a, 1, [&](const buctd_gemm16_args& x) { return launch_gemm16(x, static_cast<cudaStream_t>(s)); });
+}
+BUCTD_API int buctd_wgrad_reduce(buctd_ctx* c, const buctd_wgrad_reduce_args* a, buctd_stream s) {
+  return simple_call(c, a, 1, [&](const buctd_wgrad_reduce_args& x) { return launch_wgrad_reduce(x, static_cast<cudaStream_t>(s)); });
+}
+BUCTD_API int buctd_bn_stats(buctd_ctx* c, const buctd_bn_stats_args* a, buctd_stream s) {
+  return simple_call(c, a, 2, [&](const buctd_bn_stats_args& x) { return launch_bn_stats(x, static_cast<cudaStream_t>(s)); });
+}
+BUCTD_API int buctd_bn_apply(buctd_ctx* c, const buctd_bn_apply_args* a, buctd_stream s) {
+  return simple_call(c, a, 1, [&](const buctd_bn_apply_args& x) { return launch_bn_apply(x, static_cast<cudaStream_t>(s)); });
+}
+BUCTD_API int buctd_bn_bwd(buctd_ctx* c, const buctd_bn_bwd_args* a, buctd_stream s) {
+  return simple_call(c, a, 3, [&](const buctd_bn_bwd_args& x) { return launch_bn_bwd(x, static_cast<cudaStream_t>(s)); });
+}
+BUCTD_API int buctd_colsum(buctd_ctx* c, const buctd_colsum_args* a, buctd_stream s) {
+  return simple_call(c, a, 2, [&](const buctd_colsum_args& x) { return launch_colsum(x, static_cast<cudaStream_t>(s)); });
+}
+BUCTD_API int buctd_zero_stuff(buctd_ctx* c, const buctd_zero_stuff_args* a, buctd_stream s) {
+  return simple_call(c, a, 1, [&](const buctd_zero_stuff_args& x) { return launch_zero_stuff(x, static_cast<cudaStream_t>(s)); });
+}
+BUCTD_API int buctd_hr_fuse_bwd(buctd_ctx* c, const buctd_fuse_bwd_args* a, buctd_stream s) {
+  return simple_call(c, a, 2, [&](const buctd_fuse_bwd_args& x) { return launch_fuse_bwd(x, static_cast<cudaStream_t>(s)); });
+}
+BUCTD_API int buctd_add16(buctd_ctx* c, const buctd_add16_args* a, buctd_stream s) {
+  return simple_call(c, a, 1, [&](const buctd_add16_args& x) { return launch_add16(x, static_cast<cudaStream_t>(s)); });
+}
+BUCTD_API int buctd_planar_to_act16(buctd_ctx* c, const buctd_relayout_args* a, buctd_stream s) {
+  return simple_call(c, a, 1, [&](const buctd_relayout_args& x) { return launch_planar_to_act16(x, static_cast<cudaStream_t>(s)); });
+}
+BUCTD_API int buctd_act16_to_planar(buctd_ctx* c, const buctd_relayout_args* a, buctd_stream s) {
+  return simple_call(c, a, 1, [&](const buctd_relayout_args& x) { return launch_act16_to_planar(x, static_cast<cudaStream_t>(s)); });
+}
+BUCTD_API int buctd_chan_softmax_bwd(buctd_ctx* c, const buctd_chan_softmax_bwd_args* a, buctd_stream s) {
+  return simple_call(c, a, 1, [&](const buctd_chan_softmax_bwd_args& x) { return launch_chan_softmax_bwd(x, static_cast<cudaStream_t>(s)); });
+}
+BUCTD_API int buctd_pos_softmax_bwd(buctd_ctx* c, const buctd_pos_softmax_bwd_args* a, buctd_stream s) {
+  return simple_call(c, a, 1, [&](const buctd_pos_softmax_bwd_args& x) { return launch_pos_softmax_bwd(x, static_cast<cudaStream_t>(s)); });
+}
+BUCTD_API int buctd_rowdot(buctd_ctx* c, const buctd_rowdot_args* a, buctd_stream s) {
+  return simple_call(c, a, 1, [&](const buctd_rowdot_args& x) { return launch_rowdot(x, static_cast<cudaStream_t>(s)); });
+}
+BUCTD_API int buctd_stem_wgrad(buctd_ctx* c, const buctd_stem_wgrad_args* a, buctd_stream s) {
+  return simple_call(c, a, 1, [&](const buctd_stem_wgrad_args& x) { return launch_stem_wgrad(x, static_cast<cudaStream_t>(s)); });
+}
+BUCTD_API int buctd_repack_weights(buctd_ctx* c, const buctd_repack_args* a, buctd_stream s) {
+  return simple_call(c, a, 1, [&](const buctd_repack_args& x) { return launch_repack(x, static_cast<cudaStream_t>(s)); });
 }
 BUCTD_API int buctd_act16_to_nchw32(buctd_ctx* c, int dtype, const void* act, int batch, int h, int w, int ch, int cs,
                                     float* out, buctd_stream s) {

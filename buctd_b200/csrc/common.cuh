@@ -213,6 +213,17 @@ __host__ __device__ inline uint32_t umma_idesc_f16(int fmt, int M, int N) {
 }
 #endif  // __CUDACC__
 
+// ---- attention dropout: counter-based hash of (seed, crop, row, column), see include/buctd_b200.h "Dropout" -----
+__host__ __device__ inline uint32_t drop_hash(uint32_t seed, uint32_t crop, uint32_t row, uint32_t col) {
+  uint32_t x = seed ^ (row * 0x9E3779B1u + col * 0x85EBCA77u + crop * 0xC2B2AE3Du);
+  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+  return x;
+}
+__host__ __device__ inline uint32_t drop_threshold(float p) {     // keep iff hash >= threshold
+  const double t = (double)p * 4294967296.0;
+  return t <= 0.0 ? 0u : (t >= 4294967295.0 ? 4294967295u : (uint32_t)t);
+}
+
 // ---- driver entry point for tensor-map encoding (no link-time libcuda dependency) ------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

@@ -100,6 +100,23 @@ int launch_adam(const buctd_adam_args& a, int sm_count, cudaStream_t st);
 int launch_gen_target(const buctd_gen_target_args& a, cudaStream_t st);
 int launch_pck(const buctd_pck_args& a, cudaStream_t st);
 int launch_crop_warp(const buctd_crop_warp_args& a, cudaStream_t st);
+int gemm16_init_device();
+int launch_gemm16(const buctd_gemm16_args& a, cudaStream_t st);
+int launch_wgrad_reduce(const buctd_wgrad_reduce_args& a, cudaStream_t st);
+int launch_bn_stats(const buctd_bn_stats_args& a, cudaStream_t st);
+int launch_bn_apply(const buctd_bn_apply_args& a, cudaStream_t st);
+int launch_bn_bwd(const buctd_bn_bwd_args& a, cudaStream_t st);
+int launch_colsum(const buctd_colsum_args& a, cudaStream_t st);
+int launch_zero_stuff(const buctd_zero_stuff_args& a, cudaStream_t st);
+int launch_fuse_bwd(const buctd_fuse_bwd_args& a, cudaStream_t st);
+int launch_add16(const buctd_add16_args& a, cudaStream_t st);
+int launch_planar_to_act16(const buctd_relayout_args& a, cudaStream_t st);
+int launch_act16_to_planar(const buctd_relayout_args& a, cudaStream_t st);
+int launch_chan_softmax_bwd(const buctd_chan_softmax_bwd_args& a, cudaStream_t st);
+int launch_pos_softmax_bwd(const buctd_pos_softmax_bwd_args& a, cudaStream_t st);
+int launch_rowdot(const buctd_rowdot_args& a, cudaStream_t st);
+int launch_stem_wgrad(const buctd_stem_wgrad_args& a, cudaStream_t st);
+int launch_repack(const buctd_repack_args& a, cudaStream_t st);
 struct ChainLaunch;
 int tapgemm_chain_init_device();
 int tapgemm_chain_prepare(const buctd_tapgemm_chain_args& a, ChainLaunch* C, int sm_count, unsigned int* counter);

@@ -65,11 +65,12 @@ __global__ void __launch_bounds__(256) stem_kernel(buctd_stem_args a) {
       acc[4] = fmaf(in[t], w1.x, acc[4]); acc[5] = fmaf(in[t], w1.y, acc[5]);
       acc[6] = fmaf(in[t], w1.z, acc[6]); acc[7] = fmaf(in[t], w1.w, acc[7]);
     }
+    const float lo = a.no_relu ? -INFINITY : 0.f;
     uint4 u;
-    u.x = T16<T>::pack2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f));
-    u.y = T16<T>::pack2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
-    u.z = T16<T>::pack2(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f));
-    u.w = T16<T>::pack2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
+    u.x = T16<T>::pack2(fmaxf(acc[0], lo), fmaxf(acc[1], lo));
+    u.y = T16<T>::pack2(fmaxf(acc[2], lo), fmaxf(acc[3], lo));
+    u.z = T16<T>::pack2(fmaxf(acc[4], lo), fmaxf(acc[5], lo));
+    u.w = T16<T>::pack2(fmaxf(acc[6], lo), fmaxf(acc[7], lo));
     *reinterpret_cast<uint4*>(o + c0) = u;
   }
 }
@@ -599,7 +600,17 @@ __global__ void __launch_bounds__(128) chan_apply_kernel(buctd_chan_att_args a) 
   const int cs1 = a.c + 1;
   const int nchunks = (int)(((long long)(a.h + 1) * (a.w + 1) + BUCTD_CHAN_ATT_ROWS_PER_CHUNK - 1) / BUCTD_CHAN_ATT_ROWS_PER_CHUNK);
   const float* att = a.scratch + ((long long)b * nchunks * a.c + t1 * kCaTile) * a.c;     // probabilities live in chunk 0
-  for (int i = threadIdx.x; i < kCaTile * a.c; i += 128) s_att[i] = att[i];
+  if (a.drop_p > 0.f) {
+    // training: nn.Dropout on the probabilities (hash mask keyed by (seed, crop, c1, c2), kept values / (1 - p))
+    const uint32_t thr = drop_threshold(a.drop_p);
+    const float ks = 1.f / (1.f - a.drop_p);
+    for (int i = threadIdx.x; i < kCaTile * a.c; i += 128) {
+      const int c1 = t1 * kCaTile + i / a.c, c2 = i % a.c;
+      s_att[i] = drop_hash(a.drop_seed, (uint32_t)b, (uint32_t)c1, (uint32_t)c2) >= thr ? att[i] * ks : 0.f;
+    }
+  } else {
+    for (int i = threadIdx.x; i < kCaTile * a.c; i += 128) s_att[i] = att[i];
+  }
   const T* y = reinterpret_cast<const T*>(a.y) + (long long)b * (a.h + 1) * (a.w + 1) * a.y_cs;
   for (int i = threadIdx.x; i < kCaPix * (a.c / 8); i += 128) {
     const int pp = i / (a.c / 8), c8 = (i % (a.c / 8)) * 8;

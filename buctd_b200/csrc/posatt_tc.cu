@@ -38,6 +38,9 @@ struct PosAttTcParams {
   int n_last;                          // MMA N of the last V block (its channels, + the ones column, rounded up to 16)
   int ones;                            // row sums come from a column of ones planted in the last V block
   int tmem_cols;
+  float drop_p;                        // training: dropout of the probabilities (hash mask), 0: none
+  uint32_t drop_seed;
+  float* lse2;                         // optional: log2-sum-exp per query row
   int o_cs;
   float sc;                            // 1/sqrt(C) * log2(e)
   void* o;
@@ -216,6 +219,7 @@ pos_att_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const int Wp = p.W + 1;
     const bool ones = p.ones != 0;               // a free channel slot exists for the ones column
+    const uint32_t drop_thr = p.drop_p > 0.f ? drop_threshold(p.drop_p) : 0u;
     float m_run = -INFINITY, l_run = 0.f;
     uint8_t* prow = s_p + row * 128;
     const int sw = row & 7;
@@ -299,6 +303,15 @@ pos_att_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             if (!ones) {
               const float2 f0 = T16<T>::unpack2(pk[i]), f1 = T16<T>::unpack2(pk[i + 1]);
               ls += (f0.x + f0.y) + (f1.x + f1.y);
+            }
+            if (drop_thr != 0u) {           // the row sum above is over the UNDROPPED probabilities; 1 / (1 - p) goes into `inv`
+              const uint32_t kb = (uint32_t)(j * kTcTile + c0 + 2 * i);
+              const uint32_t k0 = drop_hash(p.drop_seed, (uint32_t)b, (uint32_t)(m0 + row), kb) >= drop_thr ? 0x0000FFFFu : 0u;
+              const uint32_t k1 = drop_hash(p.drop_seed, (uint32_t)b, (uint32_t)(m0 + row), kb + 1) >= drop_thr ? 0xFFFF0000u : 0u;
+              const uint32_t k2 = drop_hash(p.drop_seed, (uint32_t)b, (uint32_t)(m0 + row), kb + 2) >= drop_thr ? 0x0000FFFFu : 0u;
+              const uint32_t k3 = drop_hash(p.drop_seed, (uint32_t)b, (uint32_t)(m0 + row), kb + 3) >= drop_thr ? 0xFFFF0000u : 0u;
+              pk[i] &= (k0 | k1);
+              pk[i + 1] &= (k2 | k3);
             }
           }
           uint8_t* blk = prow + (c0 >> 6) * kTcBlk;
@@ -397,7 +410,8 @@ pos_att_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       tmem_ld_wait();
       l_run = __uint_as_float(lv);
     }
-    const float inv = (ok && !pad) ? 1.f / l_run : 0.f;
+    const float inv = (ok && !pad) ? 1.f / (l_run * (1.f - p.drop_p)) : 0.f;
+    if (p.lse2 != nullptr && ok) p.lse2[(long long)row_base + r] = pad ? 0.f : m_run + log2f(l_run);
     T* go = reinterpret_cast<T*>(p.o) + ((long long)row_base + r) * p.o_cs;
 #pragma unroll 1
     for (int c0 = 0; c0 < p.c; c0 += 16) {
@@ -476,7 +490,9 @@ int launch_pos_att_tc(const buctd_pos_att_args& a, cudaStream_t st) {
   p.ns = p.nkc == 1 ? 3 : 4;
   // the ones column needs a free channel slot in the last 64-channel block, and the last V block of a tile must be able
   // to land while the soft-max warps still hold P back (ring >= nkc + 2 slots): C = 16 .. 48, 80 .. 112
-  p.ones = (a.c % 64 != 0 && p.nkc + 2 <= p.ns) ? 1 : 0;
+  p.ones = (a.c % 64 != 0 && p.nkc + 2 <= p.ns && !(a.drop_p > 0.f)) ? 1 : 0;     // (dropout: the ones column would sum the dropped P)
+  BUCTD_CHECK(a.drop_p >= 0.f && a.drop_p < 1.f, BUCTD_ERR_INVALID, "pos_att: drop_p %f out of [0, 1)", a.drop_p);
+  p.drop_p = a.drop_p; p.drop_seed = a.drop_seed; p.lse2 = a.lse2;
   const int c_last = a.c - 64 * (p.nkc - 1);
   p.n_last = p.ones ? (c_last + 1 + 15) / 16 * 16 : c_last;
   p.n2 = 64 * (p.nkc - 1) + p.n_last;

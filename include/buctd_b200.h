@@ -115,7 +115,7 @@ int buctd_tapgemm_chain(buctd_ctx* ctx, const buctd_tapgemm_chain_args* args, bu
 typedef struct {
   int32_t dtype, batch, x_channels, h, w, out_cs;
   int32_t x_half;       /* 0: x is float32 (the reference's tensor); 1: x is IEEE half [B][x_channels][H][W] (halves the H2D copy) */
-  int32_t reserved;
+  int32_t no_relu;      /* training: raw convolution output (BatchNorm + ReLU follow as separate passes) */
   const void* x; const float* weight; const float* bias; void* out;
 } buctd_stem_args;
 int buctd_stem_conv(buctd_ctx* ctx, const buctd_stem_args* args, buctd_stream stream);
@@ -179,6 +179,7 @@ int buctd_cond_from_kpts(buctd_ctx* ctx, const buctd_cond_kpts_args* args, buctd
 typedef struct {
   int32_t dtype, batch, h, w, c, y_cs, yc_cs;
   int32_t out_stride;   /* planar row stride of out in elements (0 = H*W); a multiple of 8 lets the HW x HW fc_o read it by TMA */
+  float drop_p; uint32_t drop_seed;   /* training: dropout of the probabilities (see "Dropout" below); 0: none */
   const void* y; const void* yc; float* scratch; void* out;
 } buctd_chan_att_args;
 int buctd_coam_channel_att(buctd_ctx* ctx, const buctd_chan_att_args* args, buctd_stream stream);
@@ -191,7 +192,9 @@ int buctd_coam_channel_att(buctd_ctx* ctx, const buctd_chan_att_args* args, buct
  * lib/models/self_attention.py:78-86 (eval mode: dropout is the identity). */
 typedef struct {
   int32_t dtype, batch, h, w, c, q_cs, k_cs, v_cs, o_cs, reserved;
+  float drop_p; uint32_t drop_seed;   /* training: dropout of the probabilities; 0: none */
   const void* q; const void* k; const void* v; void* o;
+  float* lse2;          /* optional out [B][(H+1)(W+1)]: log2-sum-exp of every query row's scaled scores (for the backward) */
 } buctd_pos_att_args;
 int buctd_coam_position_att(buctd_ctx* ctx, const buctd_pos_att_args* args, buctd_stream stream);
 
@@ -346,6 +349,141 @@ typedef struct {
   double* acc; int32_t* cnt;
 } buctd_pck_args;
 int buctd_pck_accuracy(buctd_ctx* ctx, const buctd_pck_args* args, buctd_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The training step (SURVEY.md section 8 row a-T): lib/core/function.py:113-138 -- model.train() forward with batch
+ * statistics and attention dropout, JointsMSELoss, backward, Adam.  The data gradients of every convolution / linear
+ * layer are tap-GEMMs with transposed (and tap-flipped) packed weights (buctd_tapgemm; a stride-2 convolution through the
+ * zero-stuffed output gradient); everything else the autograd of the reference does is below.  All 16-bit gradient
+ * tensors are act16 with zero pads, like the activations.  `inv_scale` = 1 / (static loss scale): parameter gradients
+ * are written unscaled in float32 (torch layouts), straight into the optimizer's flat gradient buffer.
+ * ------------------------------------------------------------------------------------------ */
+
+/* D[M][N] = alpha * sum_k A[m][k] B[n][k] on tcgen05; each operand K-major ([MN rows][K contiguous], row stride ld) or
+ * MN-major ([K rows][MN contiguous]).  z = (tap t, split s, batch b): batch b offsets both operands by *_batch_stride
+ * elements (K ranges never cross a batch: 3-D tensor maps), split s contracts k in [s Kc, (s+1) Kc), tap t adds
+ * tap_off[t] to the K-row index of an MN-major B (rows outside [0, b_rows) read as zero).  D element offset
+ * = t d_t_stride + s d_s_stride + b d_b_stride + m ldd + n; float32 or 16-bit; accumulate != 0 adds to what is there.
+ * Uses: weight gradients dW_t[n][k] = sum_r dY[r][n] X[r + off_t][k] (A, B MN-major act16 tensors, split partials),
+ * nn.Linear weight gradients, and the products of the attention backward (torch.matmul autograd). */
+typedef struct {
+  int32_t dtype, a_mn_major, b_mn_major, m, n, k;
+  int32_t nbatch, nsplit, ntaps, b_rows;       /* b_rows: K rows of one batch of an MN-major B (0: k) */
+  int32_t lda, ldb, ldd, out_f32, accumulate, reserved;
+  int64_t a_batch_stride, b_batch_stride, d_t_stride, d_s_stride, d_b_stride;
+  int32_t tap_off[9]; float alpha;
+  const void* a; const void* b; void* d;
+} buctd_gemm16_args;
+int buctd_gemm16(buctd_ctx* ctx, const buctd_gemm16_args* args, buctd_stream stream);
+
+/* Split partials [nsplit][ntaps][n][k] float32 (buctd_gemm16) -> grad[n][k][ntaps] float32 (nn.Conv2d weight layout
+ * [cout][cin][kh][kw]; nn.Linear [out][in] with ntaps = 1), summed over the splits in index order, times inv_scale. */
+typedef struct {
+  int32_t n, k, ntaps, nsplit, accumulate, reserved; float inv_scale, pad_;
+  const float* partial; float* grad;
+} buctd_wgrad_reduce_args;
+int buctd_wgrad_reduce(buctd_ctx* ctx, const buctd_wgrad_reduce_args* args, buctd_stream stream);
+
+/* nn.BatchNorm2d(training=True) statistics of an act16 tensor z (C channels, the B*H*W valid pixels): mean_rstd[0][c] =
+ * mean, [1][c] = 1 / sqrt(biased var + eps) (float64 accumulation, fixed order); running_mean / running_var updated in
+ * place with `momentum` and the UNBIASED variance (lib/models/pose_hrnet_coam.py:20 BN_MOMENTUM = 0.1) when not NULL.
+ * scratch: 2 * C * BUCTD_BN_BLOCKS doubles. */
+#define BUCTD_BN_BLOCKS 296
+typedef struct {
+  int32_t dtype, batch, h, w, c, z_cs; float eps, momentum;
+  const void* z; float* mean_rstd; float* running_mean; float* running_var; double* scratch;
+} buctd_bn_stats_args;
+int buctd_bn_stats(buctd_ctx* ctx, const buctd_bn_stats_args* args, buctd_stream stream);
+
+/* y = [ReLU]( gamma (z - mean) rstd + beta [+ residual] ), act16 in / out (pads written as zero). */
+typedef struct {
+  int32_t dtype, batch, h, w, c, z_cs, res_cs, out_cs, relu, reserved;
+  const void* z; const float* mean_rstd; const float* gamma; const float* beta; const void* residual; void* out;
+} buctd_bn_apply_args;
+int buctd_bn_apply(buctd_ctx* ctx, const buctd_bn_apply_args* args, buctd_stream stream);
+
+/* Backward of the above: g = dy * [y > 0] (relu != 0); dbeta = sum g, dgamma = sum g zhat (zhat = (z - mean) rstd), both
+ * times inv_scale; dz = gamma rstd (g - mean(g) - zhat mean(g zhat)); dres (optional) = g (res_accumulate: += g), the
+ * gradient of the residual input.  y is only read when relu != 0.  scratch: 2 * C * (BUCTD_BN_BLOCKS + 1) doubles. */
+typedef struct {
+  int32_t dtype, batch, h, w, c, dy_cs, y_cs, z_cs, dz_cs, dres_cs, relu, res_accumulate;
+  float inv_scale, pad_;
+  const void* dy; const void* y; const void* z; const float* mean_rstd; const float* gamma;
+  float* dgamma; float* dbeta; double* scratch; void* dz; void* dres;
+} buctd_bn_bwd_args;
+int buctd_bn_bwd(buctd_ctx* ctx, const buctd_bn_bwd_args* args, buctd_stream stream);
+
+/* dbias[c] (+)= inv_scale * sum over rows of dy[r][c]  (16-bit [rows][cs] matrix; pads are zero).  scratch: C * BUCTD_BN_BLOCKS doubles */
+typedef struct {
+  int32_t dtype, c, cs, accumulate; int64_t rows; float inv_scale, pad_;
+  const void* dy; float* dbias; double* scratch;
+} buctd_colsum_args;
+int buctd_colsum(buctd_ctx* ctx, const buctd_colsum_args* args, buctd_stream stream);
+
+/* Zero-stuffing: out [B][2h+1][2w+1][cs] with out[b][2y][2x] = in[b][y][x] (in: act16 [B][h+1][w+1][cs]) and zeros elsewhere:
+ * a stride-2 3x3 convolution's data gradient is the stride-1 transposed convolution of this, and its weight gradient the
+ * stride-1 weight gradient against it. */
+typedef struct { int32_t dtype, batch, h, w, cs, reserved; const void* in; void* out; } buctd_zero_stuff_args;
+int buctd_zero_stuff(buctd_ctx* ctx, const buctd_zero_stuff_args* args, buctd_stream stream);
+
+/* Backward of buctd_hr_fuse: g = dout * [out > 0]; term j at the output resolution gets g, a term 2^shift coarser the
+ * sum of g over its 2^shift x 2^shift block (nearest up-sampling); term_accumulate[j] adds to dterm[j]. */
+typedef struct {
+  int32_t dtype, batch, h, w, c, cs, nterms, relu;
+  const void* dout; const void* out;
+  void* dterm[4]; int32_t term_cs[4]; int32_t term_shift[4]; int32_t term_accumulate[4];
+} buctd_fuse_bwd_args;
+int buctd_hr_fuse_bwd(buctd_ctx* ctx, const buctd_fuse_bwd_args* args, buctd_stream stream);
+
+/* out (+)= a for act16 tensors of one geometry (gradient accumulation where no kernel epilogue can do it). */
+typedef struct { int32_t dtype, cs_out, cs_a, c; int64_t rows; int32_t accumulate, reserved; const void* a; void* out; } buctd_add16_args;
+int buctd_add16(buctd_ctx* ctx, const buctd_add16_args* args, buctd_stream stream);
+
+/* planar [B][C][p_stride] <-> act16 [B][H+1][W+1][cs] (valid pixels; act16 pads / spare channels written as zero). */
+typedef struct { int32_t dtype, batch, h, w, c, cs, p_stride, accumulate; const void* in; void* out; } buctd_relayout_args;
+int buctd_planar_to_act16(buctd_ctx* ctx, const buctd_relayout_args* args, buctd_stream stream);
+int buctd_act16_to_planar(buctd_ctx* ctx, const buctd_relayout_args* args, buctd_stream stream);
+
+/* Dropout of the attention probabilities (nn.Dropout(0.1), lib/models/self_attention.py:38,84,115,156) is a counter-based
+ * hash of (seed, crop, row, column) so that the test oracle reproduces the mask:
+ *   x = seed ^ (row * 0x9E3779B1 + col * 0x85EBCA77 + crop * 0xC2B2AE3D);  x ^= x >> 16; x *= 0x7FEB352D; x ^= x >> 15;
+ *   x *= 0x846CA68B; x ^= x >> 16;   keep iff x >= floor(p * 2^32)   (all uint32 arithmetic), kept values are scaled by 1 / (1 - p). */
+
+/* Softmax backward on the [C x C] channel-attention matrices: probs [B][C][C] (buctd_coam_channel_att leaves them in
+ * scratch chunk 0, stride prob_stride floats per crop), da_d = gradient w.r.t. the DROPPED probabilities;
+ * ds = probs (da - rowsum(da probs)) * scale with da = mask da_d / (1 - p); writes ds and the dropped probabilities as
+ * 16-bit [B][C][ld] matrices (GEMM operands). */
+typedef struct {
+  int32_t dtype, batch, c, ld; int64_t prob_stride; float scale, drop_p; uint32_t seed; int32_t reserved;
+  const float* probs; const float* da_d; void* ds; void* probs_d;
+} buctd_chan_softmax_bwd_args;
+int buctd_chan_softmax_bwd(buctd_ctx* ctx, const buctd_chan_softmax_bwd_args* args, buctd_stream stream);
+
+/* Position-attention backward, element-wise part over the [rows x rows] matrices of every crop (rows = (H+1)(W+1), row
+ * stride ld): s = log2-domain scores q.k * log2(e)/sqrt(C) and dpd = dO V^T (float32, buctd_gemm16), lse2[b][r] = the
+ * forward's log2-sum-exp, delta[b][r] = sum_c dO O.  p = exp2(s - lse2) on valid (query, key) pixels, else 0;
+ * pd = mask p / (1 - drop_p); ds = p (mask dpd / (1 - drop_p) - delta) / sqrt(C).  Writes pd and ds as 16-bit. */
+typedef struct {
+  int32_t dtype, batch, h, w, ld, reserved; float inv_sqrt_c, drop_p; uint32_t seed; int32_t reserved2;
+  const float* s; const float* dpd; const float* lse2; const float* delta; void* pd; void* ds;
+} buctd_pos_softmax_bwd_args;
+int buctd_pos_softmax_bwd(buctd_ctx* ctx, const buctd_pos_softmax_bwd_args* args, buctd_stream stream);
+
+/* delta[r] = sum_c a[r][c] b[r][c] (float32) over 16-bit [rows][cs] matrices */
+typedef struct { int32_t dtype, c, a_cs, b_cs; int64_t rows; const void* a; const void* b; float* out; } buctd_rowdot_args;
+int buctd_rowdot(buctd_ctx* ctx, const buctd_rowdot_args* args, buctd_stream stream);
+
+/* Weight gradient of the stem conv1 (3x3 stride 2, 3 -> 64, float32 nchw input): partial[blk][64][27] float32 with
+ * blk < BUCTD_BN_BLOCKS (reduce with buctd_wgrad_reduce: n 64, k 27, ntaps 1, nsplit BUCTD_BN_BLOCKS). */
+typedef struct { int32_t dtype, batch, x_channels, h, w, dz_cs, x_half, reserved; const void* x; const void* dz; float* partial; } buctd_stem_wgrad_args;
+int buctd_stem_wgrad(buctd_ctx* ctx, const buctd_stem_wgrad_args* args, buctd_stream stream);
+
+/* Re-pack float32 master weights into the 16-bit tap-GEMM layouts after an optimizer step, table driven (one launch):
+ * entry e: src [cout][cin][taps] float32 at param + src_off -> dst at w16 + dst_off, forward layout [tap][n_alloc][k_cs]
+ * (transposed = 0) or data-gradient layout [taps-1-tap][cin_alloc][cout_cs] holding W[co][ci][tap] at [..][ci][co]
+ * (transposed = 1).  table: int64 [n_entries][8] = {src_off, dst_off, cout, cin, taps, rows_alloc, cs, transposed}. */
+typedef struct { int32_t dtype, n_entries; const float* param; void* w16; const int64_t* table; } buctd_repack_args;
+int buctd_repack_weights(buctd_ctx* ctx, const buctd_repack_args* args, buctd_stream stream);
 
 /* Utility kernels used by the host mirror: zero-fill, and act16 -> nchw32 export for tests. */
 int buctd_act16_to_nchw32(buctd_ctx* ctx, int dtype, const void* act, int batch, int h, int w, int c, int cs,

@@ -37,7 +37,15 @@ def test_struct_fields_match_header():
              "buctd_da_combine_args": L.DaCombineArgs, "buctd_prenet_args": L.PrenetArgs, "buctd_decode_args": L.DecodeArgs,
              "buctd_raster_args": L.RasterArgs, "buctd_flip_args": L.FlipArgs, "buctd_flip_merge_args": L.FlipMergeArgs,
              "buctd_joints_mse_args": L.JointsMseArgs, "buctd_adam_args": L.AdamArgs, "buctd_crop_warp_args": L.CropWarpArgs,
-             "buctd_gen_target_args": L.GenTargetArgs, "buctd_pck_args": L.PckArgs}
+             "buctd_gen_target_args": L.GenTargetArgs, "buctd_pck_args": L.PckArgs, "buctd_cond_kpts_args": L.CondKptsArgs,
+             "buctd_resize3_args": L.Resize3Args,
+             # the training step
+             "buctd_gemm16_args": L.Gemm16Args, "buctd_wgrad_reduce_args": L.WgradReduceArgs, "buctd_bn_stats_args": L.BnStatsArgs,
+             "buctd_bn_apply_args": L.BnApplyArgs, "buctd_bn_bwd_args": L.BnBwdArgs, "buctd_colsum_args": L.ColsumArgs,
+             "buctd_zero_stuff_args": L.ZeroStuffArgs, "buctd_fuse_bwd_args": L.FuseBwdArgs, "buctd_add16_args": L.Add16Args,
+             "buctd_relayout_args": L.RelayoutArgs, "buctd_chan_softmax_bwd_args": L.ChanSoftmaxBwdArgs,
+             "buctd_pos_softmax_bwd_args": L.PosSoftmaxBwdArgs, "buctd_rowdot_args": L.RowdotArgs,
+             "buctd_stem_wgrad_args": L.StemWgradArgs, "buctd_repack_args": L.RepackArgs}
     for cname, st in pairs.items():
         body = re.search(r"typedef struct \{([^}]*)\}\s*%s;" % cname, h).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
@@ -47,10 +55,11 @@ def test_struct_fields_match_header():
             if not decl:
                 continue
             # "int32_t a, b, c" / "const void* term[4]" / "const float* x"
-            decl = re.sub(r"^(const\s+)?(int32_t|int64_t|uint8_t|float|void|double)\s*\**(\s*const\s*\*)?", "", decl)
+            decl = re.sub(r"^(const\s+)?(int32_t|int64_t|uint32_t|uint8_t|float|void|double)\s*\**(\s*const\s*\*)?", "", decl)
             for part in decl.split(","):
                 names.append(re.sub(r"\[.*\]", "", part).replace("*", "").strip())
-        assert names == [f[0] for f in st._fields_], (cname, names, [f[0] for f in st._fields_])
+        mine = [f[0] if f[0] != "in_" else "in" for f in st._fields_]       # `in` is a Python keyword
+        assert names == mine, (cname, names, mine)
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
