@@ -118,7 +118,7 @@ class FlipMergeArgs(C.Structure):
 
 
 class JointsMseArgs(C.Structure):
-    _fields_ = [("batch", i32), ("k", i32), ("hw", i32), ("use_target_weight", i32),
+    _fields_ = [("batch", i32), ("k", i32), ("hw", i32), ("use_target_weight", i32), ("grad_scale", C.c_float), ("reserved", i32),
                 ("output", fp), ("target", fp), ("target_weight", fp), ("loss", fp), ("grad", fp), ("scratch", vp)]
 
 

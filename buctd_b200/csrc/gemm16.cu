@@ -27,7 +27,7 @@ struct Gemm16Params {
   int k_per_split;
   int tap_off[9];
   long long d_t_stride, d_s_stride, d_b_stride;
-  int ldd, out_f32;
+  int ldd, out_f32, accumulate;
   float alpha;
   void* d;
   int bn, bn_pad, stages;
@@ -164,17 +164,31 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
       }
       if (m >= p.M) continue;
       const int nc = min(32, ncols - c0);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * p.alpha);
+      if (p.accumulate) {                          // D += ...: the same thread owns the element, no hazard
+        if (p.out_f32) {
+          const float* src = reinterpret_cast<const float*>(p.d) + off + c0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < nc) v[i] = __float_as_uint(__uint_as_float(v[i]) + src[i]);
+        } else {
+          const T* src = reinterpret_cast<const T*>(p.d) + off + c0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < nc) v[i] = __float_as_uint(__uint_as_float(v[i]) + T16<T>::to_f(src[i]));
+        }
+      }
       if (p.out_f32) {
         float* dst = reinterpret_cast<float*>(p.d) + off + c0;
         if (nc == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<float4*>(dst + i) = make_float4(__uint_as_float(v[i]) * p.alpha, __uint_as_float(v[i + 1]) * p.alpha,
-                                                              __uint_as_float(v[i + 2]) * p.alpha, __uint_as_float(v[i + 3]) * p.alpha);
+            *reinterpret_cast<float4*>(dst + i) = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (i < nc) dst[i] = __uint_as_float(v[i]) * p.alpha;
+            if (i < nc) dst[i] = __uint_as_float(v[i]);
         }
       } else {
         T* dst = reinterpret_cast<T*>(p.d) + off + c0;
@@ -182,16 +196,16 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
             uint4 u;
-            u.x = T16<T>::pack2(__uint_as_float(v[i]) * p.alpha, __uint_as_float(v[i + 1]) * p.alpha);
-            u.y = T16<T>::pack2(__uint_as_float(v[i + 2]) * p.alpha, __uint_as_float(v[i + 3]) * p.alpha);
-            u.z = T16<T>::pack2(__uint_as_float(v[i + 4]) * p.alpha, __uint_as_float(v[i + 5]) * p.alpha);
-            u.w = T16<T>::pack2(__uint_as_float(v[i + 6]) * p.alpha, __uint_as_float(v[i + 7]) * p.alpha);
+            u.x = T16<T>::pack2(__uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+            u.y = T16<T>::pack2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+            u.z = T16<T>::pack2(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+            u.w = T16<T>::pack2(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
             *reinterpret_cast<uint4*>(dst + i) = u;
           }
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (i < nc) dst[i] = T16<T>::from_f(__uint_as_float(v[i]) * p.alpha);
+            if (i < nc) dst[i] = T16<T>::from_f(__uint_as_float(v[i]));
         }
       }
     }
@@ -240,7 +254,7 @@ int launch_gemm16(const buctd_gemm16_args& a, cudaStream_t st) {
   if (p.k_per_split == 0) p.k_per_split = kGmStageK;
   for (int i = 0; i < 9; ++i) p.tap_off[i] = a.tap_off[i];
   p.d_t_stride = a.d_t_stride; p.d_s_stride = a.d_s_stride; p.d_b_stride = a.d_b_stride;
-  p.ldd = a.ldd; p.out_f32 = a.out_f32; p.alpha = a.alpha; p.d = a.d;
+  p.ldd = a.ldd; p.out_f32 = a.out_f32; p.accumulate = a.accumulate; p.alpha = a.alpha; p.d = a.d;
   // N tile: the whole N when it fits one instruction (multiple of 16, <= 256), else 256 / 128
   int bn = a.n <= 256 ? (a.n + 15) / 16 * 16 : 256;
   if (a.n > 256 && a.n % 256 != 0 && a.n % 128 == 0) bn = 128;

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) joints_mse_rows_kernel(buctd_joints_mse_a
   const float* o = a.output + (long long)row * a.hw;
   const float* t = a.target + (long long)row * a.hw;
   float* g = a.grad ? a.grad + (long long)row * a.hw : nullptr;
-  const float gscale = w * w / ((float)a.k * (float)a.batch * (float)a.hw);
+  const float gscale = w * w / ((float)a.k * (float)a.batch * (float)a.hw) * (a.grad_scale != 0.f ? a.grad_scale : 1.f);
   double acc = 0.0;
   for (int i = threadIdx.x; i < a.hw; i += 256) {
     const float d = o[i] - t[i];

@@ -287,6 +287,8 @@ int buctd_flip_merge(buctd_ctx* ctx, const buctd_flip_merge_args* args, buctd_st
  * (bit-reproducible).  Replaces JointsMSELoss.forward (+ its autograd backward), lib/core/loss.py:17-41. */
 typedef struct {
   int32_t batch, k, hw, use_target_weight;
+  float grad_scale;     /* static loss scale applied to `grad` only (0 is read as 1): 16-bit gradient tensors downstream */
+  int32_t reserved;
   const float* output; const float* target; const float* target_weight;
   float* loss; float* grad; double* scratch;
 } buctd_joints_mse_args;

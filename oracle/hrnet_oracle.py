@@ -26,6 +26,11 @@ _ID = lambda t: t  # noqa: E731
 
 _AQ = [_ID]   # design-experiment hook: quantiser applied to conv / linear INPUTS (identity for the oracle)
 
+# Training-mode switches (oracle/train_oracle.py sets them around a forward): nn.BatchNorm2d with batch statistics
+# (momentum BN_MOMENTUM = 0.1, pose_hrnet_coam.py:20) and nn.Dropout(0.1) on both attention maps
+# (lib/models/self_attention.py:38,84,115,156) with an externally supplied keep-mask so that the CUDA path can be checked.
+_CTX = {"train": False, "running": None, "drop": None, "drop_p": 0.0}
+
 
 def _conv(sd: SD, p: str, x, stride=1, wq=_ID):
     x = _AQ[0](x)
@@ -36,6 +41,12 @@ def _conv(sd: SD, p: str, x, stride=1, wq=_ID):
 
 
 def _bn(sd: SD, p: str, x, eps=1e-5):
+    if _CTX["train"]:
+        rm, rv = sd[p + ".running_mean"].detach().clone(), sd[p + ".running_var"].detach().clone()
+        y = F.batch_norm(x, rm, rv, sd[p + ".weight"], sd[p + ".bias"], training=True, momentum=0.1, eps=eps)
+        if _CTX["running"] is not None:
+            _CTX["running"][p] = (rm, rv)
+        return y
     # eval-mode nn.BatchNorm2d: (x - running_mean) / sqrt(running_var + eps) * weight + bias
     return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"],
                         sd[p + ".bias"], training=False, eps=eps)
@@ -137,6 +148,14 @@ def _lin(sd, p, x, wq=_ID):
     return F.linear(x, wq(sd[p + ".weight"]), sd[p + ".bias"])
 
 
+def _dropout(att, tag):
+    """nn.Dropout on an attention map in training mode: keep-mask from the hook, kept values / (1 - p)"""
+    if not _CTX["train"] or _CTX["drop_p"] <= 0.0 or _CTX["drop"] is None:
+        return att
+    keep = _CTX["drop"](tag, att)
+    return att * keep / (1.0 - _CTX["drop_p"])
+
+
 def _da_module(sd, p, x, cond, channel_only: bool, act, wq, rec=None):
     # DAModule.forward :705-724
     bs, c, h, w = x.shape
@@ -145,7 +164,7 @@ def _da_module(sd, p, x, cond, channel_only: bool, act, wq, rec=None):
     y = act(_conv(sd, cp + ".cnn", x, wq=wq)).view(bs, c, -1)                   # [B,C,HW] keys = values
     yc = act(_conv(sd, cp + ".cnn_cond", cond, wq=wq)).view(bs, c, -1)          # [B,C,HW] queries
     att = torch.softmax(torch.matmul(yc, y.transpose(1, 2)) / math.sqrt(h * w), -1)  # [B,C,C]
-    c_out = act(_lin(sd, cp + ".pa.fc_o", act(torch.matmul(att, y)), wq)).view(bs, c, h, w)
+    c_out = act(_lin(sd, cp + ".pa.fc_o", act(torch.matmul(_dropout(att, p + ":chan"), y)), wq)).view(bs, c, h, w)
     if rec is not None:
         rec(p + ":chan_att", att)
         rec(p + ":c_out", c_out)
@@ -160,7 +179,7 @@ def _da_module(sd, p, x, cond, channel_only: bool, act, wq, rec=None):
     k = act(_lin(sd, pp + ".pa.fc_k", yp, wq))
     v = act(_lin(sd, pp + ".pa.fc_v", yp, wq))
     att = torch.softmax(torch.matmul(q, k.transpose(1, 2)) / math.sqrt(c), -1)            # [B,HW,HW]
-    o = act(_lin(sd, pp + ".pa.fc_o", act(torch.matmul(act(att), v)), wq))                # [B,HW,C]
+    o = act(_lin(sd, pp + ".pa.fc_o", act(torch.matmul(act(_dropout(att, p + ":pos")), v)), wq))                # [B,HW,C]
     p_out = o.permute(0, 2, 1).reshape(bs, c, h, w)
     if rec is not None:
         rec(p + ":pos_att_rows", att[:, ::61])

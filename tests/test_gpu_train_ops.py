@@ -160,7 +160,7 @@ def test_bn_train_forward_backward(dt, C, h, w):
     assert_close(mr[1], 1.0 / torch.sqrt(z.var((0, 2, 3), unbiased=False) + 1e-5), 1e-4, "rstd")
     assert_close(rm_d, rm_r, 1e-5, "running_mean")
     assert_close(rv_d, rv_r, 1e-5, "running_var")
-    assert pads_are_zero(y) and y[..., C:].float().abs().max() == 0
+    assert pads_are_zero(y) and (C == cs or y[..., C:].float().abs().max() == 0)
     assert_close(from_act16(y, C), yr.detach(), TOL[dt], "bn forward")
     # backward
     dy = q16(_rand(B, C, h, w, seed=16), dt)
@@ -313,7 +313,7 @@ def test_relayout_add_rowdot(dt):
 def test_chan_softmax_backward(dt, p):
     B, C, ld = 3, 48, 48
     S = _rand(B, C, C, seed=30)
-    probs = torch.softmax(S, -1).contiguous()
+    probs = torch.softmax(S * 0.2, -1).contiguous()
     da_d = _rand(B, C, C, seed=31)
     ds = torch.zeros(B, C, ld, dtype=TDT[dt], device="cuda")
     pd = torch.zeros(B, C, ld, dtype=TDT[dt], device="cuda")
