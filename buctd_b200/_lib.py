@@ -73,13 +73,13 @@ class CondKptsArgs(C.Structure):
 class ChanAttArgs(C.Structure):
     _fields_ = [("dtype", i32), ("batch", i32), ("h", i32), ("w", i32), ("c", i32), ("y_cs", i32), ("yc_cs", i32),
                 ("out_stride", i32), ("drop_p", C.c_float), ("drop_seed", C.c_uint32),
-                ("y", vp), ("yc", vp), ("scratch", fp), ("out", vp)]
+                ("y", vp), ("yc", vp), ("scratch", fp), ("out", vp), ("seed_xor", vp)]
 
 
 class PosAttArgs(C.Structure):
     _fields_ = [("dtype", i32), ("batch", i32), ("h", i32), ("w", i32), ("c", i32), ("q_cs", i32), ("k_cs", i32),
                 ("v_cs", i32), ("o_cs", i32), ("reserved", i32), ("drop_p", C.c_float), ("drop_seed", C.c_uint32),
-                ("q", vp), ("k", vp), ("v", vp), ("o", vp), ("lse2", fp)]
+                ("q", vp), ("k", vp), ("v", vp), ("o", vp), ("lse2", fp), ("seed_xor", vp)]
 
 
 class DaCombineArgs(C.Structure):
@@ -206,12 +206,12 @@ class RelayoutArgs(C.Structure):
 
 class ChanSoftmaxBwdArgs(C.Structure):
     _fields_ = [("dtype", i32), ("batch", i32), ("c", i32), ("ld", i32), ("prob_stride", i64), ("scale", f32c), ("drop_p", f32c),
-                ("seed", u32), ("reserved", i32), ("probs", fp), ("da_d", fp), ("ds", vp), ("probs_d", vp)]
+                ("seed", u32), ("reserved", i32), ("probs", fp), ("da_d", fp), ("ds", vp), ("probs_d", vp), ("seed_xor", vp)]
 
 
 class PosSoftmaxBwdArgs(C.Structure):
     _fields_ = [("dtype", i32), ("batch", i32), ("h", i32), ("w", i32), ("ld", i32), ("reserved", i32), ("inv_sqrt_c", f32c),
-                ("drop_p", f32c), ("seed", u32), ("reserved2", i32), ("s", fp), ("dpd", fp), ("lse2", fp), ("delta", fp), ("pd", vp), ("ds", vp)]
+                ("drop_p", f32c), ("seed", u32), ("reserved2", i32), ("s", fp), ("dpd", fp), ("lse2", fp), ("delta", fp), ("pd", vp), ("ds", vp), ("seed_xor", vp)]
 
 
 class RowdotArgs(C.Structure):

@@ -604,9 +604,10 @@ __global__ void __launch_bounds__(128) chan_apply_kernel(buctd_chan_att_args a) 
     // training: nn.Dropout on the probabilities (hash mask keyed by (seed, crop, c1, c2), kept values / (1 - p))
     const uint32_t thr = drop_threshold(a.drop_p);
     const float ks = 1.f / (1.f - a.drop_p);
+    const uint32_t seed = a.drop_seed ^ (a.seed_xor ? *a.seed_xor : 0u);
     for (int i = threadIdx.x; i < kCaTile * a.c; i += 128) {
       const int c1 = t1 * kCaTile + i / a.c, c2 = i % a.c;
-      s_att[i] = drop_hash(a.drop_seed, (uint32_t)b, (uint32_t)c1, (uint32_t)c2) >= thr ? att[i] * ks : 0.f;
+      s_att[i] = drop_hash(seed, (uint32_t)b, (uint32_t)c1, (uint32_t)c2) >= thr ? att[i] * ks : 0.f;
     }
   } else {
     for (int i = threadIdx.x; i < kCaTile * a.c; i += 128) s_att[i] = att[i];

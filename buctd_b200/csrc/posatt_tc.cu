@@ -41,6 +41,7 @@ struct PosAttTcParams {
   float drop_p;                        // training: dropout of the probabilities (hash mask), 0: none
   uint32_t drop_seed;
   float* lse2;                         // optional: log2-sum-exp per query row
+  const uint32_t* seed_xor;            // optional device word XOR-ed into drop_seed
   int o_cs;
   float sc;                            // 1/sqrt(C) * log2(e)
   void* o;
@@ -220,6 +221,7 @@ pos_att_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const int Wp = p.W + 1;
     const bool ones = p.ones != 0;               // a free channel slot exists for the ones column
     const uint32_t drop_thr = p.drop_p > 0.f ? drop_threshold(p.drop_p) : 0u;
+    const uint32_t drop_seed = p.drop_seed ^ ((p.drop_p > 0.f && p.seed_xor) ? *p.seed_xor : 0u);
     float m_run = -INFINITY, l_run = 0.f;
     uint8_t* prow = s_p + row * 128;
     const int sw = row & 7;
@@ -306,10 +308,10 @@ pos_att_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             }
             if (drop_thr != 0u) {           // the row sum above is over the UNDROPPED probabilities; 1 / (1 - p) goes into `inv`
               const uint32_t kb = (uint32_t)(j * kTcTile + c0 + 2 * i);
-              const uint32_t k0 = drop_hash(p.drop_seed, (uint32_t)b, (uint32_t)(m0 + row), kb) >= drop_thr ? 0x0000FFFFu : 0u;
-              const uint32_t k1 = drop_hash(p.drop_seed, (uint32_t)b, (uint32_t)(m0 + row), kb + 1) >= drop_thr ? 0xFFFF0000u : 0u;
-              const uint32_t k2 = drop_hash(p.drop_seed, (uint32_t)b, (uint32_t)(m0 + row), kb + 2) >= drop_thr ? 0x0000FFFFu : 0u;
-              const uint32_t k3 = drop_hash(p.drop_seed, (uint32_t)b, (uint32_t)(m0 + row), kb + 3) >= drop_thr ? 0xFFFF0000u : 0u;
+              const uint32_t k0 = drop_hash(drop_seed, (uint32_t)b, (uint32_t)(m0 + row), kb) >= drop_thr ? 0x0000FFFFu : 0u;
+              const uint32_t k1 = drop_hash(drop_seed, (uint32_t)b, (uint32_t)(m0 + row), kb + 1) >= drop_thr ? 0xFFFF0000u : 0u;
+              const uint32_t k2 = drop_hash(drop_seed, (uint32_t)b, (uint32_t)(m0 + row), kb + 2) >= drop_thr ? 0x0000FFFFu : 0u;
+              const uint32_t k3 = drop_hash(drop_seed, (uint32_t)b, (uint32_t)(m0 + row), kb + 3) >= drop_thr ? 0xFFFF0000u : 0u;
               pk[i] &= (k0 | k1);
               pk[i + 1] &= (k2 | k3);
             }
@@ -492,7 +494,7 @@ int launch_pos_att_tc(const buctd_pos_att_args& a, cudaStream_t st) {
   // to land while the soft-max warps still hold P back (ring >= nkc + 2 slots): C = 16 .. 48, 80 .. 112
   p.ones = (a.c % 64 != 0 && p.nkc + 2 <= p.ns && !(a.drop_p > 0.f)) ? 1 : 0;     // (dropout: the ones column would sum the dropped P)
   BUCTD_CHECK(a.drop_p >= 0.f && a.drop_p < 1.f, BUCTD_ERR_INVALID, "pos_att: drop_p %f out of [0, 1)", a.drop_p);
-  p.drop_p = a.drop_p; p.drop_seed = a.drop_seed; p.lse2 = a.lse2;
+  p.drop_p = a.drop_p; p.drop_seed = a.drop_seed; p.lse2 = a.lse2; p.seed_xor = a.seed_xor;
   const int c_last = a.c - 64 * (p.nkc - 1);
   p.n_last = p.ones ? (c_last + 1 + 15) / 16 * 16 : c_last;
   p.n2 = 64 * (p.nkc - 1) + p.n_last;

@@ -539,9 +539,10 @@ __global__ void __launch_bounds__(256) chan_softmax_bwd_kernel(buctd_chan_softma
   const float* da = a.da_d + ((long long)b * a.c + c1) * a.c;
   const uint32_t thr = drop_threshold(a.drop_p);
   const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+  const uint32_t seed = a.seed ^ (a.seed_xor ? *a.seed_xor : 0u);
   float dot = 0.f;
   for (int c2 = lane; c2 < a.c; c2 += 32) {
-    const bool keep = a.drop_p <= 0.f || drop_hash(a.seed, (uint32_t)b, (uint32_t)c1, (uint32_t)c2) >= thr;
+    const bool keep = a.drop_p <= 0.f || drop_hash(seed, (uint32_t)b, (uint32_t)c1, (uint32_t)c2) >= thr;
     dot += (keep ? da[c2] * keep_scale : 0.f) * pr[c2];
   }
   for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffff, dot, o);
@@ -550,7 +551,7 @@ __global__ void __launch_bounds__(256) chan_softmax_bwd_kernel(buctd_chan_softma
   for (int c2 = lane; c2 < a.ld; c2 += 32) {
     float dsv = 0.f, pdv = 0.f;
     if (c2 < a.c) {
-      const bool keep = a.drop_p <= 0.f || drop_hash(a.seed, (uint32_t)b, (uint32_t)c1, (uint32_t)c2) >= thr;
+      const bool keep = a.drop_p <= 0.f || drop_hash(seed, (uint32_t)b, (uint32_t)c1, (uint32_t)c2) >= thr;
       const float p = pr[c2];
       dsv = p * ((keep ? da[c2] * keep_scale : 0.f) - dot) * a.scale;
       pdv = keep ? p * keep_scale : 0.f;
@@ -579,6 +580,7 @@ __global__ void __launch_bounds__(256) pos_softmax_bwd_kernel(buctd_pos_softmax_
   const long long total = (long long)a.batch * rows * groups;
   const uint32_t thr = drop_threshold(a.drop_p);
   const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+  const uint32_t seed = a.seed ^ (a.seed_xor ? *a.seed_xor : 0u);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long qr = i / groups;                 // global query row
     const int k0 = (int)(i - qr * groups) * 8;
@@ -599,7 +601,7 @@ __global__ void __launch_bounds__(256) pos_softmax_bwd_kernel(buctd_pos_softmax_
         const int k = k0 + j;
         if (k < rows && (k % (a.w + 1)) != a.w && (k / (a.w + 1)) != a.h) {
           const float p = exp2f(sv[j] - lse);
-          const bool keep = a.drop_p <= 0.f || drop_hash(a.seed, (uint32_t)b, (uint32_t)q, (uint32_t)k) >= thr;
+          const bool keep = a.drop_p <= 0.f || drop_hash(seed, (uint32_t)b, (uint32_t)q, (uint32_t)k) >= thr;
           pd[j] = keep ? p * keep_scale : 0.f;
           ds[j] = p * ((keep ? dv[j] * keep_scale : 0.f) - dl) * a.inv_sqrt_c;
         }

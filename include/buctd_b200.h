@@ -181,6 +181,7 @@ typedef struct {
   int32_t out_stride;   /* planar row stride of out in elements (0 = H*W); a multiple of 8 lets the HW x HW fc_o read it by TMA */
   float drop_p; uint32_t drop_seed;   /* training: dropout of the probabilities (see "Dropout" below); 0: none */
   const void* y; const void* yc; float* scratch; void* out;
+  const uint32_t* seed_xor;           /* optional device word XOR-ed into drop_seed (the step counter of a replayed CUDA graph) */
 } buctd_chan_att_args;
 int buctd_coam_channel_att(buctd_ctx* ctx, const buctd_chan_att_args* args, buctd_stream stream);
 
@@ -195,6 +196,7 @@ typedef struct {
   float drop_p; uint32_t drop_seed;   /* training: dropout of the probabilities; 0: none */
   const void* q; const void* k; const void* v; void* o;
   float* lse2;          /* optional out [B][(H+1)(W+1)]: log2-sum-exp of every query row's scaled scores (for the backward) */
+  const uint32_t* seed_xor;           /* optional device word XOR-ed into drop_seed */
 } buctd_pos_att_args;
 int buctd_coam_position_att(buctd_ctx* ctx, const buctd_pos_att_args* args, buctd_stream stream);
 
@@ -457,7 +459,7 @@ int buctd_act16_to_planar(buctd_ctx* ctx, const buctd_relayout_args* args, buctd
  * 16-bit [B][C][ld] matrices (GEMM operands). */
 typedef struct {
   int32_t dtype, batch, c, ld; int64_t prob_stride; float scale, drop_p; uint32_t seed; int32_t reserved;
-  const float* probs; const float* da_d; void* ds; void* probs_d;
+  const float* probs; const float* da_d; void* ds; void* probs_d; const uint32_t* seed_xor;
 } buctd_chan_softmax_bwd_args;
 int buctd_chan_softmax_bwd(buctd_ctx* ctx, const buctd_chan_softmax_bwd_args* args, buctd_stream stream);
 
@@ -467,7 +469,7 @@ int buctd_chan_softmax_bwd(buctd_ctx* ctx, const buctd_chan_softmax_bwd_args* ar
  * pd = mask p / (1 - drop_p); ds = p (mask dpd / (1 - drop_p) - delta) / sqrt(C).  Writes pd and ds as 16-bit. */
 typedef struct {
   int32_t dtype, batch, h, w, ld, reserved; float inv_sqrt_c, drop_p; uint32_t seed; int32_t reserved2;
-  const float* s; const float* dpd; const float* lse2; const float* delta; void* pd; void* ds;
+  const float* s; const float* dpd; const float* lse2; const float* delta; void* pd; void* ds; const uint32_t* seed_xor;
 } buctd_pos_softmax_bwd_args;
 int buctd_pos_softmax_bwd(buctd_ctx* ctx, const buctd_pos_softmax_bwd_args* args, buctd_stream stream);
 

@@ -1,0 +1,154 @@
+"""-m gpu: the recorded training step (buctd_b200.train.TrainStep, row a-T) against
+(1) tests/golden/train_step_*.npz -- loss, heat-maps, gradient norms / heads and running statistics of the UNMODIFIED
+    reference in train() mode (oracle/make_golden_trainstep.py), and
+(2) oracle/train_oracle.py (pinned to (1) by tests/test_train_oracle.py) for every gradient entry and for the dropout path
+    with the shared hash mask.
+
+Tolerances: the step stores activations, activation gradients and packed weights in 16 bit (float32 accumulation, float32
+parameter gradients).  Relative L2 error per gradient tensor, over ~110 layers of train-mode BatchNorm at batch 4:
+fp16 (+ loss scale 1024) <= 5e-2, bf16 <= 1.5e-1; over the whole gradient vector fp16 <= 2e-2, bf16 <= 6e-2."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from buctd_b200 import pose_hrnet, pose_hrnet_coam
+from buctd_b200.train import TrainStep
+from oracle import make_golden_trainstep as G
+from oracle import train_oracle as T
+
+pytestmark = pytest.mark.gpu
+TENSOR_TOL = {"fp16": 5e-2, "bf16": 1.5e-1}
+GLOBAL_TOL = {"fp16": 2e-2, "bf16": 6e-2}
+LOSS_TOL = {"fp16": 5e-3, "bf16": 2e-2}
+HM_TOL = {"fp16": 1e-2, "bf16": 6e-2}
+
+
+def _setup(name, dtype, drop_p=0.0, graph=None, loss_scale=None):
+    cfg, batch = G.case_cfg(name)
+    mod = pose_hrnet_coam if cfg.MODEL.NAME == "pose_hrnet_coam" else pose_hrnet
+    net = mod.get_pose_net(cfg, is_train=True, dtype=dtype)
+    sd = G.case_state_dict(name)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().train()
+    ls = loss_scale if loss_scale is not None else (1024.0 if dtype == "fp16" else 1.0)
+    ts = TrainStep(net, batch, lr=1e-3, dtype=dtype, loss_scale=ls, drop_p=drop_p, seed=5, graph=graph)
+    x, tgt, tw = [torch.from_numpy(a).cuda() for a in G.case_data(name)]
+    return cfg, net, sd, ts, x, tgt, tw
+
+
+def _grads(net):
+    return {k: p.grad.detach().float().cpu() for k, p in net.named_parameters()}
+
+
+def _compare(grads, ref, dtype, what):
+    num = den = 0.0
+    worst = (0.0, "")
+    for k, g in ref.items():
+        mine = grads[k]
+        d = float((mine - g).double().norm())
+        n = float(g.double().norm())
+        num += d * d
+        den += n * n
+        if n > 1e-6 * np.sqrt(g.numel()):
+            worst = max(worst, (d / n, k))
+    glob = np.sqrt(num / den)
+    print("\n%s %s: global rel L2 gradient error %.4f, worst tensor %.4f (%s)" % (what, dtype, glob, worst[0], worst[1]))
+    assert glob <= GLOBAL_TOL[dtype], (what, glob)
+    assert worst[0] <= TENSOR_TOL[dtype], (what, worst)
+
+
+@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
+@pytest.mark.parametrize("name", list(G.CASES))
+def test_forward_backward_matches_reference(golden_dir, name, dtype):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    cfg, net, sd, ts, x, tgt, tw = _setup(name, dtype)
+    loss = float(ts.forward_backward(x, tgt, tw).item())
+    assert abs(loss - float(g["loss"])) <= LOSS_TOL[dtype] * float(g["loss"]), (loss, float(g["loss"]))
+    assert np.abs(ts.heatmaps.cpu().numpy() - g["heatmaps"]).max() <= HM_TOL[dtype]
+    grads = _grads(net)
+    # (1) the reference's own numbers: every gradient norm, and the leading entries
+    names = [str(n) for n in g["grad_names"]]
+    assert sorted(names) == sorted(grads)
+    tot = np.sqrt((g["grad_norms"] ** 2).sum())
+    for i, k in enumerate(names):
+        n = float(grads[k].double().norm())
+        assert abs(n - g["grad_norms"][i]) <= TENSOR_TOL[dtype] * g["grad_norms"][i] + 1e-4 * tot, (k, n, g["grad_norms"][i])
+    # (2) every entry, against the oracle (pinned to the reference by tests/test_train_oracle.py)
+    _, _, ref, running = T.train_forward_backward(sd, cfg, x.cpu(), tgt.cpu(), tw.cpu(), drop_p=0.0)
+    _compare(grads, ref, dtype, name)
+    # BatchNorm running statistics after one step, num_batches_tracked
+    bsd = net.state_dict()
+    for key in g.files:
+        if key.startswith("rm:"):
+            assert np.abs(bsd[key[3:] + ".running_mean"].cpu().numpy() - g[key]).max() <= 2e-2
+        if key.startswith("rv:"):
+            assert np.abs(bsd[key[3:] + ".running_var"].cpu().numpy() - g[key]).max() <= 2e-2 * max(1.0, np.abs(g[key]).max())
+    assert int(bsd["bn1.num_batches_tracked"]) == 1
+    assert sorted(bsd) == sorted(sd)
+
+
+@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
+def test_dropout_path_matches_oracle_with_shared_mask(dtype):
+    name = "train_step_coam_w32_128x96"
+    cfg, net, sd, ts, x, tgt, tw = _setup(name, dtype, drop_p=0.1)
+    loss = float(ts.forward_backward(x, tgt, tw).item())
+    ref_loss, hm, ref, _ = T.train_forward_backward(sd, cfg, x.cpu(), tgt.cpu(), tw.cpu(), drop_p=0.1, seeds=ts.effective_seeds(0))
+    assert abs(loss - ref_loss) <= LOSS_TOL[dtype] * ref_loss
+    assert np.abs(ts.heatmaps.cpu().numpy() - hm.numpy()).max() <= HM_TOL[dtype]
+    _compare(_grads(net), ref, dtype, name + " dropout 0.1")
+    # and the mask matters: without it the oracle's gradients differ by more than the tolerance
+    _, _, nodrop, _ = T.train_forward_backward(sd, cfg, x.cpu(), tgt.cpu(), tw.cpu(), drop_p=0.0)
+    k = "stage2_att.att_layers.0.position_attention_module.pa.fc_v.weight"
+    assert float((nodrop[k] - ref[k]).norm() / ref[k].norm()) > 2 * TENSOR_TOL[dtype]
+
+
+def test_graph_replay_equals_eager_and_steps_train():
+    name = "train_step_coam_w32_128x96"
+    outs = {}
+    for graph in (False, True):
+        cfg, net, sd, ts, x, tgt, tw = _setup(name, "bf16", drop_p=0.1, graph=graph)
+        ts.forward_backward(x, tgt, tw)
+        ts.forward_backward(x, tgt, tw)                       # graph: second call replays
+        torch.cuda.synchronize()
+        outs[graph] = ts.opt.flat_grad.clone()
+    assert torch.equal(outs[False], outs[True])
+    # a few optimizer steps on one batch: the loss goes down, parameters move, the dropout mask changes per step
+    cfg, net, sd, ts, x, tgt, tw = _setup(name, "bf16", drop_p=0.1)
+    w0 = net.final_layer.weight.detach().clone()
+    losses = [float(ts.step(x, tgt, tw).item()) for _ in range(6)]
+    assert losses[-1] < losses[0], losses
+    assert not torch.equal(w0, net.final_layer.weight.detach())
+    assert int(net.state_dict()["bn1.num_batches_tracked"]) == 6
+    assert ts.effective_seeds(0) != ts.effective_seeds(1)
+    # the inference path picks the updated parameters up
+    net.eval()
+    with torch.no_grad():
+        hm = net(x)
+    assert torch.isfinite(hm).all()
+
+
+def test_adam_is_a_torch_optimizer():
+    from buctd_b200.optim import Adam
+    ps = [torch.nn.Parameter(torch.randn(7, 5, device="cuda")), torch.nn.Parameter(torch.randn(11, device="cuda"))]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    opt, ropt = Adam(ps, lr=1e-2), torch.optim.Adam(ref, lr=1e-2)
+    sched = torch.optim.lr_scheduler.MultiStepLR(opt, [2], 0.1)
+    rsched = torch.optim.lr_scheduler.MultiStepLR(ropt, [2], 0.1)
+    for it in range(4):
+        for p, r in zip(ps, ref):
+            g = torch.randn_like(p)
+            p.grad.copy_(g)
+            r.grad = g.clone()
+        opt.step(); ropt.step(); sched.step(); rsched.step()
+        opt.zero_grad()
+    for p, r in zip(ps, ref):
+        assert (p - r).abs().max().item() < 1e-6
+    sd = opt.state_dict()
+    ropt2 = torch.optim.Adam(ref, lr=1e-2)
+    ropt2.load_state_dict(sd)                                  # torch's own optimizer accepts the checkpoint
+    opt2 = Adam([torch.nn.Parameter(p.detach().clone()) for p in ps], lr=1e-2)
+    opt2.load_state_dict(ropt.state_dict())                    # and the other way round
+    assert opt2.step_count == 4 and abs(opt2.lr - ropt.param_groups[0]["lr"]) < 1e-12
+    assert torch.allclose(opt2.exp_avg[:35], opt.exp_avg[:35], atol=1e-7)
