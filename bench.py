@@ -559,6 +559,7 @@ def main():
     ap.add_argument("--ref-crops", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    args.dtype_given = any(a.startswith("--dtype") for a in sys.argv[1:])
     # Exactly ONE line on stdout: libraries that write to file descriptor 1 themselves (NCCL prints its version banner
     # there when a communicator is created) are sent to stderr; the JSON line goes to the original stdout.
     sys.stdout.flush()

@@ -1,0 +1,142 @@
+"""bench.py --config train: BASELINE.json configs[4] -- BUCTD-CoAM-W48 384x288 bf16 training step (JointsMSELoss +
+backward + Adam), 32 crops per GPU, data parallel with ONE NCCL all-reduce (mean) of the flat gradient buffer per step
+(the reference: torch.nn.DataParallel + torch.optim.Adam, tools/train.py:147, lib/core/function.py:113-138).
+
+One step = TrainStep.step(): H2D-free (inputs resident), training-mode forward, loss, backward, all-reduce, Adam, weight
+re-pack.  `value` = crops/s over all ranks (max-over-ranks CUDA-event time); `e2e` = the same with the batch (crop planes,
+targets, weights) coming from pinned host memory every step and the loss read back."""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+
+TRAIN_GFLOP = 3 * 88.75          # ~3x the forward's 88.75 GFLOP per crop
+
+
+def run(args, ClockSampler, load_peaks):
+    import torch
+    import torch.distributed as dist
+    from buctd_b200 import condition, pose_hrnet_coam, synth
+    from buctd_b200.config import make_cfg
+    from buctd_b200.train import TrainStep
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    B = args.batch or 32
+    dtype = args.dtype if args.dtype_given else "bf16"
+    cfg = make_cfg("coam", 48, (288, 384), cond="stacked")
+    net = pose_hrnet_coam.get_pose_net(cfg, is_train=True, dtype=dtype)
+    net.load_state_dict(synth.synth_state_dict(net.arch, 0), strict=True)
+    net = net.cuda().train()
+    ts = TrainStep(net, B, lr=1e-3, dtype=dtype, loss_scale=1024.0 if dtype == "fp16" else 1.0, drop_p=0.1, seed=1 + rank)
+    H, W, K = 384, 288, 17
+    g = torch.Generator(device=device).manual_seed(777 + rank)
+    sets = []
+    for j in range(2):
+        x = torch.empty(B, 3 + K, H, W, device=device)
+        x[:, :3] = torch.randn(B, 3, H, W, generator=g, device=device)
+        kp = torch.rand(B, K, 2, generator=g, device=device) * torch.tensor([W - 16.0, H - 16.0], device=device) + 8.0
+        condition.rasterize_condition(kp, H, W, "stacked", out=x, c_off=3)
+        # targets: the reference's sigma-3 Gaussian stamps around (jittered) keypoints, 20 % of the joints unlabelled
+        yy, xx = torch.meshgrid(torch.arange(H // 4, device=device), torch.arange(W // 4, device=device), indexing="ij")
+        c = (kp / 4.0 + torch.randn(B, K, 2, generator=g, device=device)).view(B, K, 2, 1, 1)
+        tgt = torch.exp(-((xx - c[:, :, 0]) ** 2 + (yy - c[:, :, 1]) ** 2) / (2 * 3.0 ** 2)).contiguous()
+        tw = (torch.rand(B, K, 1, generator=g, device=device) < 0.8).float()
+        sets.append((x, tgt, tw))
+
+    ar_ms = [0.0]
+    if world > 1:
+        ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+
+        def allreduce():
+            ev[0].record()
+            dist.all_reduce(ts.opt.flat_grad, op=dist.ReduceOp.AVG)
+            ev[1].record()
+        ts.on_grads_ready = allreduce
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        fn(n)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1)
+
+    losses = []
+
+    def loop(n):
+        for i in range(n):
+            losses.append(ts.step(*sets[i & 1]))
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    loop(max(args.warmup, 3))
+    barrier()
+    l0 = ts.ctx.launch_count()
+    sampler.mark_begin()
+    ms = timed(loop, args.steps)
+    sampler.mark_end()
+    launches = ts.ctx.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        torch.cuda.synchronize()
+        ar_ms[0] = ev[0].elapsed_time(ev[1])
+    first, last = float(losses[0].item()), float(losses[-1].item())
+
+    host = [tuple(t.cpu().pin_memory() for t in s) for s in sets]
+    sink = [0.0]
+
+    def e2e_loop(n):
+        for i in range(n):
+            sink[0] += float(ts.step(*host[i & 1]).item())          # H2D of the batch + D2H of the loss every step
+
+    e2e_loop(2)
+    ms_e2e = timed(e2e_loop, args.steps)
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+    if rank == 0:
+        peaks = load_peaks()
+        crops = B * world * args.steps
+        value = crops / (ms / 1e3)
+        per_gpu = value / world
+        out = {
+            "metric": "crops/sec, training step at 384x288 CoAM-W48 (forward + JointsMSELoss + backward + Adam)",
+            "value": round(value, 2), "unit": "crops/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype,
+            "data": "synthetic",
+            "config": {"workload": "BUCTD-CoAM-W48 384x288 training step, batch=%d/GPU, JointsMSELoss(use_target_weight) + backward + Adam lr 1e-3, "
+                                   "attention dropout 0.1, train-mode BatchNorm (per-GPU statistics)" % B,
+                       "name": "train", "global_batch": B * world, "parallelism": "data parallel dp%d, one NCCL all-reduce (AVG) of the flat "
+                       "%.1f M-element float32 gradient buffer per step" % (world, ts.opt.flat_grad.numel() / 1e6),
+                       "weights": "random-init (buctd_b200.synth, seed 0)", "l2": "two resident batches alternate (2 x %d MB)" % (B * 20 * H * W * 4 >> 20),
+                       "loss_first_last": [round(first, 6), round(last, 6)], "workspace_gb": round(ts.ws.numel() / 2 ** 30, 2)},
+            "roofline": {"bound": "tensor", "unit": "TFLOP/s", "peak": peaks["tflops_sustained"],
+                         "achieved": round(per_gpu * TRAIN_GFLOP / 1e3, 2), "frac": round(per_gpu * TRAIN_GFLOP / 1e3 / peaks["tflops_sustained"], 4),
+                         "traffic": None, "what": "whole step: crops/s/GPU x 3 x 88.75 GFLOP (SURVEY.md 8a-T) over the sustained measured peak"},
+            "e2e": {"value": round(crops / (ms_e2e / 1e3), 2), "unit": "crops/s",
+                    "h2d_bytes_per_step": int(sum(t.numel() * 4 for t in host[0])), "d2h_bytes_per_step": 4,
+                    "ms_per_step": round(ms_e2e / args.steps, 3), "api": "TrainStep.step(input_host, target_host, target_weight_host).item()"},
+            "allreduce_ms": round(ar_ms[0], 3) if world > 1 else None,
+            "gpu_launches": int(args.steps * ts.launches_per_step()), "launches_per_step": ts.launches_per_step(),
+            "launch_note": "C-ABI launches recorded per step (replayed as one CUDA graph + Adam + re-pack); %d immediate launches counted by the handle" % launches,
+            "clocks": clocks,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
