@@ -16,19 +16,47 @@ from . import condition, crop, inference, results, transforms
 COCO_FLIP_PAIRS = [[1, 2], [3, 4], [5, 6], [7, 8], [9, 10], [11, 12], [13, 14], [15, 16]]   # lib/dataset/coco.py:66-67
 
 
+def fliplr_joints(joints, joints_vis, width, matched_parts):
+    """``utils.transforms.fliplr_joints`` (lib/utils/transforms.py:60-74) for a batch [B, K, 3] (numpy, new arrays)"""
+    j, v = np.array(joints, dtype=np.float64, copy=True), np.array(joints_vis, dtype=np.float64, copy=True)
+    j[..., 0] = width - j[..., 0] - 1
+    for p0, p1 in matched_parts:
+        j[..., [p0, p1], :] = j[..., [p1, p0], :]
+        v[..., [p0, p1], :] = v[..., [p1, p0], :]
+    return j * v, v
+
+
 @torch.no_grad()
-def forward_flip_test(config, model, input: torch.Tensor, flip_pairs: Sequence[Sequence[int]] = COCO_FLIP_PAIRS) -> torch.Tensor:
-    """``output`` of validate() after the FLIP_TEST block (function.py:207-236); reads TEST.FLIP_TEST,
-    TEST.SHIFT_HEATMAP, MODEL.CONDITIONAL_TOPDOWN, DATASET.STACKED_CONDITION."""
-    x = input.cuda()
+def forward_flip_test(config, model, input: torch.Tensor, flip_pairs: Sequence[Sequence[int]] = COCO_FLIP_PAIRS,
+                      cond_joints=None, cond_joints_vis=None, colors=None) -> torch.Tensor:
+    """``output`` of validate() after the FLIP_TEST block (function.py:202-236); reads TEST.FLIP_TEST,
+    TEST.SHIFT_HEATMAP, MODEL.CONDITIONAL_TOPDOWN.  The flipped condition follows ``flip_hm`` (transforms.py:33-57), which
+    dispatches on the CHANNEL COUNT of the condition: > 3 channels = stacked (mirror + swap the planes of the flip
+    pairs); exactly 3 = coloured / plain image, re-rasterised from the mirrored proposals ``meta['cond_joints']``
+    (``cond_joints`` [B, K, 3], ``cond_joints_vis``) -- on the device here; fewer = mirrored only."""
+    x = input
+    if not config.MODEL.CONDITIONAL_TOPDOWN:
+        x = x[:, :3]                                           # function.py:202-203
+    x = x.cuda()
     output = model(x)
     if not config.TEST.FLIP_TEST:
         return output
-    if config.MODEL.CONDITIONAL_TOPDOWN:
-        if x.shape[1] == 6 and not config.DATASET.STACKED_CONDITION:
-            raise NotImplementedError("a 3-channel (coloured) condition is re-rasterised from mirrored proposals in the "
-                                      "reference (transforms.py:38-47): build it with condition.rasterize_condition")
-        x_f = transforms.flip_input_device(x, flip_pairs, stacked=bool(config.DATASET.STACKED_CONDITION))
+    if config.MODEL.CONDITIONAL_TOPDOWN and x.shape[1] > 3:
+        nc = x.shape[1] - 3
+        if nc == 3:
+            if cond_joints is None or cond_joints_vis is None:
+                raise ValueError("a 3-channel condition is re-rasterised from the mirrored proposals: pass meta['cond_joints'] and "
+                                 "meta['cond_joints_vis'] (lib/utils/transforms.py:38-47)")
+            cj = cond_joints.cpu().numpy() if torch.is_tensor(cond_joints) else np.asarray(cond_joints)
+            cv = cond_joints_vis.cpu().numpy() if torch.is_tensor(cond_joints_vis) else np.asarray(cond_joints_vis)
+            W = int(config.MODEL.IMAGE_SIZE[0])
+            fj, _ = fliplr_joints(cj, cv, W, flip_pairs)
+            x_f = transforms.flip_channels_device(x, list(range(x.shape[1])))          # RGB planes mirrored (condition overwritten next)
+            # the reference always calls get_condition_image_colored here, whatever DATASET.COLORED says
+            condition.rasterize_condition(torch.from_numpy(np.trunc(fj).astype(np.float32)).to(x.device), x.shape[2], x.shape[3], "colored",
+                                          colors=colors, out=x_f, c_off=3)
+        else:
+            x_f = transforms.flip_input_device(x, flip_pairs, stacked=nc > 3)
     else:
         x_f = transforms.flip_channels_device(x, list(range(x.shape[1])))
     output_flipped = model(x_f)

