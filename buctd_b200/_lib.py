@@ -150,7 +150,7 @@ f32c, u32, f64c = C.c_float, C.c_uint32, C.c_double
 class Gemm16Args(C.Structure):
     _fields_ = [("dtype", i32), ("a_mn_major", i32), ("b_mn_major", i32), ("m", i32), ("n", i32), ("k", i32),
                 ("nbatch", i32), ("nsplit", i32), ("ntaps", i32), ("b_rows", i32),
-                ("lda", i32), ("ldb", i32), ("ldd", i32), ("out_f32", i32), ("accumulate", i32), ("reserved", i32),
+                ("lda", i32), ("ldb", i32), ("ldd", i32), ("out_f32", i32), ("accumulate", i32), ("tap_group", i32),
                 ("a_batch_stride", i64), ("b_batch_stride", i64), ("d_t_stride", i64), ("d_s_stride", i64), ("d_b_stride", i64),
                 ("tap_off", i32 * 9), ("alpha", f32c), ("a", vp), ("b", vp), ("d", vp)]
 
@@ -224,7 +224,7 @@ class StemWgradArgs(C.Structure):
 
 
 class RepackArgs(C.Structure):
-    _fields_ = [("dtype", i32), ("n_entries", i32), ("param", fp), ("w16", vp), ("table", vp)]
+    _fields_ = [("dtype", i32), ("n_entries", i32), ("n_units", i32), ("reserved", i32), ("param", fp), ("w16", vp), ("table", vp), ("units", vp)]
 
 
 TRAIN_EXPORTS = ["buctd_gemm16", "buctd_wgrad_reduce", "buctd_bn_stats", "buctd_bn_apply", "buctd_bn_bwd", "buctd_colsum", "buctd_zero_stuff",

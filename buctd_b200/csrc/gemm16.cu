@@ -28,6 +28,7 @@ struct Gemm16Params {
   int tap_off[9];
   long long d_t_stride, d_s_stride, d_b_stride;
   int ldd, out_f32, accumulate;
+  int group;             // 3: one CTA computes the three dx taps of a kernel row from ONE A tile and a 72-row B stage
   float alpha;
   void* d;
   int bn, bn_pad, stages;
@@ -44,6 +45,10 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uin
 // (SBO), consecutive 64-element MN blocks 8192 B apart (LBO)
 __device__ __forceinline__ uint64_t gm_desc_mn(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint64_t gm_desc_mn_lbo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 __device__ __forceinline__ void gm_tmem_ld32(uint32_t taddr, uint32_t* r) {
@@ -63,7 +68,8 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int a_bytes = 128 * 128;
-  const int b_bytes = p.bn_pad * 128;
+  const int b_blk = p.group == 3 ? 72 * 128 : 64 * 128;          // one 64-channel block of an MN-major B stage (+ 8 halo rows)
+  const int b_bytes = p.group == 3 ? (p.bn_pad / 64) * b_blk : p.bn_pad * 128;
   const int stage_bytes = a_bytes + b_bytes;
   const int S = p.stages;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
@@ -76,11 +82,21 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
   int z = blockIdx.z;
   const int b = z % p.nbatch; z /= p.nbatch;
   const int s = z % p.nsplit;
-  const int t = z / p.nsplit;
+  const int t = (z / p.nsplit) * (p.group == 3 ? 3 : 1);         // first tap of this CTA
   const int k_begin = s * p.k_per_split;
   const int k_end = min(p.K, k_begin + p.k_per_split);
   const int nstage = k_end > k_begin ? (k_end - k_begin + kGmStageK - 1) / kGmStageK : 0;
-  const uint32_t tmem_cols = p.bn <= 32 ? 32 : p.bn <= 64 ? 64 : p.bn <= 128 ? 128 : 256;
+  const int nacc = p.group == 3 ? 3 : 1;
+  const int acc_stride = (p.bn + 31) / 32 * 32;
+  const int need_cols = nacc * acc_stride;
+  const uint32_t tmem_cols = need_cols <= 32 ? 32 : need_cols <= 64 ? 64 : need_cols <= 128 ? 128 : need_cols <= 256 ? 256 : 512;
+  // an MN-major A whose M fits one 64-element block: the second block of every stage is zeroed once and never loaded
+  const bool a_half = p.a_mn && (p.M - m0) <= 64;
+  if (a_half) {
+    for (int i = threadIdx.x; i < S * 512; i += blockDim.x)
+      *reinterpret_cast<uint4*>(smem + (size_t)(i / 512) * stage_bytes + 8192 + (i % 512) * 16) = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -97,7 +113,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 
   if (warp == 0) {
     if (elect_one()) {
-      const uint32_t tx = (uint32_t)(a_bytes + (p.b_mn ? b_bytes : p.bn * 128));
+      const uint32_t tx = (uint32_t)((a_half ? a_bytes / 2 : a_bytes) + (p.b_mn ? b_bytes : p.bn * 128));
       uint32_t slot = 0, ph = 1;
       for (int i = 0; i < nstage; ++i) {
         const int k0 = k_begin + i * kGmStageK;
@@ -107,11 +123,14 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         mbar_expect_tx(&full_bar[slot], tx);
         if (p.a_mn) {
           tma_load_3d(sa, &map_a, &full_bar[slot], m0, k0, b);
-          tma_load_3d(sa + 8192, &map_a, &full_bar[slot], m0 + 64, k0, b);
+          if (!a_half) tma_load_3d(sa + 8192, &map_a, &full_bar[slot], m0 + 64, k0, b);
         } else {
           tma_load_3d(sa, &map_a, &full_bar[slot], k0, m0, b);
         }
-        if (p.b_mn) {
+        if (p.group == 3) {
+          // rows k0 + off(dx = -1) .. + 72 of the input: the three dx taps are this stage shifted by 0 / 1 / 2 rows
+          for (int j = 0; j * 64 < p.bn_pad; ++j) tma_load_3d(sb + j * b_blk, &map_b, &full_bar[slot], n0 + 64 * j, k0 + p.tap_off[t], b);
+        } else if (p.b_mn) {
           for (int j = 0; j * 64 < p.bn_pad; ++j) tma_load_3d(sb + j * 8192, &map_b, &full_bar[slot], n0 + 64 * j, k0 + p.tap_off[t], b);
         } else {
           tma_load_3d(sb, &map_b, &full_bar[slot], k0, n0, b);
@@ -129,11 +148,21 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)slot * stage_bytes);
         const uint32_t sb = sa + a_bytes;
+        if (p.group == 3) {
 #pragma unroll
-        for (int ks = 0; ks < kGmStageK / 16; ++ks) {
-          const uint64_t ad = p.a_mn ? gm_desc_mn(sa + ks * 2048) : umma_desc_sw128(sa + ks * 32);
-          const uint64_t bd = p.b_mn ? gm_desc_mn(sb + ks * 2048) : umma_desc_sw128(sb + ks * 32);
-          tc_mma_f16(tmem_base, ad, bd, idesc, (i | ks) != 0);
+          for (int ks = 0; ks < kGmStageK / 16; ++ks) {
+            const uint64_t ad = gm_desc_mn(sa + ks * 2048);
+#pragma unroll
+            for (int j = 0; j < 3; ++j)        // a row-shifted view of a SWIZZLE_128B tile is still a valid operand (address-based swizzle)
+              tc_mma_f16(tmem_base + j * acc_stride, ad, gm_desc_mn_lbo(sb + ks * 2048 + j * 128, 72 * 128), idesc, (i | ks) != 0);
+          }
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < kGmStageK / 16; ++ks) {
+            const uint64_t ad = p.a_mn ? gm_desc_mn(sa + ks * 2048) : umma_desc_sw128(sa + ks * 32);
+            const uint64_t bd = p.b_mn ? gm_desc_mn(sb + ks * 2048) : umma_desc_sw128(sb + ks * 32);
+            tc_mma_f16(tmem_base, ad, bd, idesc, (i | ks) != 0);
+          }
         }
         tc_commit(&empty_bar[slot]);
         if (++slot == (uint32_t)S) { slot = 0; ph ^= 1; }
@@ -146,13 +175,14 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int m = m0 + row;
-    const long long off = (long long)t * p.d_t_stride + (long long)s * p.d_s_stride + (long long)b * p.d_b_stride + (long long)m * p.ldd + n0;
     if (nstage > 0) {
       mbar_wait(acc_bar, 0);
       tc_fence_after();
     }
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int ncols = min(p.bn, p.N - n0);
+    for (int ja = 0; ja < nacc; ++ja) {
+    const long long off = (long long)(t + ja) * p.d_t_stride + (long long)s * p.d_s_stride + (long long)b * p.d_b_stride + (long long)m * p.ldd + n0;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ja * acc_stride);
     for (int c0 = 0; c0 < ncols; c0 += 32) {
       uint32_t v[32];
       if (nstage > 0) {
@@ -209,6 +239,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         }
       }
     }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -244,6 +275,13 @@ int launch_gemm16(const buctd_gemm16_args& a, cudaStream_t st) {
   BUCTD_CHECK(a.lda % 8 == 0 && a.ldb % 8 == 0 && (((uintptr_t)a.a | (uintptr_t)a.b) & 15) == 0, BUCTD_ERR_INVALID,
               "gemm16: operands need 16-byte aligned rows (lda %d ldb %d)", a.lda, a.ldb);
   BUCTD_CHECK(a.ntaps == 1 || a.b_mn_major, BUCTD_ERR_INVALID, "gemm16: taps shift the K rows of an MN-major B");
+  const bool group3 = a.tap_group == 3;
+  if (group3) {
+    BUCTD_CHECK(a.ntaps % 3 == 0 && a.a_mn_major && a.b_mn_major && a.nbatch == 1, BUCTD_ERR_INVALID, "gemm16: tap_group 3 needs 3k taps, MN-major operands, one batch");
+    for (int g = 0; g < a.ntaps; g += 3)
+      BUCTD_CHECK(a.tap_off[g + 1] == a.tap_off[g] + 1 && a.tap_off[g + 2] == a.tap_off[g] + 2, BUCTD_ERR_INVALID,
+                  "gemm16: tap_group 3 needs consecutive row offsets within a group");
+  }
   Gemm16Params p;
   memset(&p, 0, sizeof(p));
   p.M = a.m; p.N = a.n; p.K = a.k;
@@ -258,9 +296,11 @@ int launch_gemm16(const buctd_gemm16_args& a, cudaStream_t st) {
   // N tile: the whole N when it fits one instruction (multiple of 16, <= 256), else 256 / 128
   int bn = a.n <= 256 ? (a.n + 15) / 16 * 16 : 256;
   if (a.n > 256 && a.n % 256 != 0 && a.n % 128 == 0) bn = 128;
+  if (group3 && bn > 128) bn = a.n % 128 == 0 ? 128 : (a.n % 96 == 0 ? 96 : 128);     // three accumulators in 512 TMEM columns
+  p.group = group3 ? 3 : 1;
   p.bn = bn;
   p.bn_pad = (bn + 63) / 64 * 64;
-  const int stage_bytes = 128 * 128 + p.bn_pad * 128;
+  const int stage_bytes = 128 * 128 + (group3 ? (p.bn_pad / 64) * 72 * 128 : p.bn_pad * 128);
   int stages = (227 * 1024 - 2048) / stage_bytes;
   p.stages = stages > 8 ? 8 : stages;
   // K-major: inner = K, rows = MN; MN-major: inner = MN, rows = K (+ tap offsets: signed coordinates, zero fill outside)
@@ -269,10 +309,10 @@ int launch_gemm16(const buctd_gemm16_args& a, cudaStream_t st) {
   if (p.a_mn) rc = gm_encode(&ma, a.dtype, a.a, a.m, a.k, a.nbatch, a.lda, a.a_batch_stride, 64, 64, "A");
   else rc = gm_encode(&ma, a.dtype, a.a, a.k, a.m, a.nbatch, a.lda, a.a_batch_stride, 64, 128, "A");
   if (rc) return rc;
-  if (p.b_mn) rc = gm_encode(&mb, a.dtype, a.b, a.n, a.b_rows > 0 ? a.b_rows : a.k, a.nbatch, a.ldb, a.b_batch_stride, 64, 64, "B");
+  if (p.b_mn) rc = gm_encode(&mb, a.dtype, a.b, a.n, a.b_rows > 0 ? a.b_rows : a.k, a.nbatch, a.ldb, a.b_batch_stride, 64, group3 ? 72 : 64, "B");
   else rc = gm_encode(&mb, a.dtype, a.b, a.k, a.n, a.nbatch, a.ldb, a.b_batch_stride, 64, bn, "B");
   if (rc) return rc;
-  dim3 grid((a.m + 127) / 128, (a.n + bn - 1) / bn, a.ntaps * a.nsplit * a.nbatch);
+  dim3 grid((a.m + 127) / 128, (a.n + bn - 1) / bn, (group3 ? a.ntaps / 3 : a.ntaps) * a.nsplit * a.nbatch);
   const size_t smem = 1024 + (size_t)p.stages * stage_bytes + 256;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = dim3(kGmThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;

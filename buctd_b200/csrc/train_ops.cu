@@ -109,14 +109,26 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(buctd_bn_stats_args a) {
     for (int j = 0; j < 8; ++j) { acc[0][j] += f[j]; acc[1][j] = fmaf(f[j], f[j], acc[1][j]); }
   });
 }
-__global__ void bn_stats_finalize_kernel(buctd_bn_stats_args a, int nblocks) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= a.c) return;
+// one warp per channel: lane l adds the partials of blocks l, l + 32, ... in order, then a fixed shuffle tree (bit-reproducible)
+__device__ __forceinline__ void warp_sum2(const double* partial, int nblocks, int nv, int v0, int v1, int c, int cstride, double* o0, double* o1) {
+  const int lane = threadIdx.x & 31;
   double s = 0.0, ss = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
-    s += a.scratch[((size_t)b * 2 + 0) * a.c + c];
-    ss += a.scratch[((size_t)b * 2 + 1) * a.c + c];
+  for (int b = lane; b < nblocks; b += 32) {
+    s += partial[((size_t)b * nv + v0) * cstride + c];
+    if (v1 >= 0) ss += partial[((size_t)b * nv + v1) * cstride + c];
   }
+  for (int o = 16; o; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffff, s, o);
+    ss += __shfl_xor_sync(0xffffffff, ss, o);
+  }
+  *o0 = s; *o1 = ss;
+}
+__global__ void __launch_bounds__(256) bn_stats_finalize_kernel(buctd_bn_stats_args a, int nblocks) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= a.c) return;
+  double s, ss;
+  warp_sum2(a.scratch, nblocks, 2, 0, 1, c, a.c, &s, &ss);
+  if ((threadIdx.x & 31) != 0) return;
   const double n = (double)a.batch * a.h * a.w;
   const double mean = s / n;
   double var = ss / n - mean * mean;
@@ -141,7 +153,7 @@ int launch_bn_stats(const buctd_bn_stats_args& a, cudaStream_t st) {
     BUCTD_CUDA(cudaFuncSetAttribute(bn_stats_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     bn_stats_kernel<__nv_bfloat16><<<kRedBlocks, 256, smem, st>>>(a);
   }
-  bn_stats_finalize_kernel<<<ceil_div(a.c, 128), 128, 0, st>>>(a, kRedBlocks);
+  bn_stats_finalize_kernel<<<ceil_div(a.c, 8), 256, 0, st>>>(a, kRedBlocks);
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;
 }
@@ -213,14 +225,12 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(buctd_bn_bwd_args a)
     }
   });
 }
-__global__ void bn_bwd_finalize_kernel(buctd_bn_bwd_args a, int nblocks) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(buctd_bn_bwd_args a, int nblocks) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (c >= a.c) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
-    s1 += a.scratch[((size_t)b * 2 + 0) * a.c + c];
-    s2 += a.scratch[((size_t)b * 2 + 1) * a.c + c];
-  }
+  double s1, s2;
+  warp_sum2(a.scratch, nblocks, 2, 0, 1, c, a.c, &s1, &s2);
+  if ((threadIdx.x & 31) != 0) return;
   // note: pad rows have z = 0 -> zhat != 0, but dy = 0 there (gradient tensors keep zero pads), so they add nothing
   if (a.dbeta) a.dbeta[c] = (float)(s1 * (double)a.inv_scale);
   if (a.dgamma) a.dgamma[c] = (float)(s2 * (double)a.inv_scale);
@@ -282,12 +292,12 @@ int launch_bn_bwd(const buctd_bn_bwd_args& a, cudaStream_t st) {
   if (a.dtype == BUCTD_F16) {
     BUCTD_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     bn_bwd_reduce_kernel<__half><<<kRedBlocks, 256, smem, st>>>(a);
-    bn_bwd_finalize_kernel<<<ceil_div(a.c, 128), 128, 0, st>>>(a, kRedBlocks);
+    bn_bwd_finalize_kernel<<<ceil_div(a.c, 8), 256, 0, st>>>(a, kRedBlocks);
     bn_bwd_apply_kernel<__half><<<blocks, 256, 0, st>>>(a, kRedBlocks);
   } else {
     BUCTD_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     bn_bwd_reduce_kernel<__nv_bfloat16><<<kRedBlocks, 256, smem, st>>>(a);
-    bn_bwd_finalize_kernel<<<ceil_div(a.c, 128), 128, 0, st>>>(a, kRedBlocks);
+    bn_bwd_finalize_kernel<<<ceil_div(a.c, 8), 256, 0, st>>>(a, kRedBlocks);
     bn_bwd_apply_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(a, kRedBlocks);
   }
   BUCTD_CUDA(cudaGetLastError());
@@ -306,11 +316,12 @@ __global__ void __launch_bounds__(256) colsum_kernel(buctd_colsum_args a) {
     for (int j = 0; j < 8; ++j) acc[0][j] += f[j];
   });
 }
-__global__ void colsum_finalize_kernel(buctd_colsum_args a, int nblocks) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) colsum_finalize_kernel(buctd_colsum_args a, int nblocks) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (c >= a.c) return;
-  double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += a.scratch[(size_t)b * a.c + c];
+  double s, unused;
+  warp_sum2(a.scratch, nblocks, 1, 0, -1, c, a.c, &s, &unused);
+  if ((threadIdx.x & 31) != 0) return;
   const float v = (float)(s * (double)a.inv_scale);
   a.dbias[c] = a.accumulate ? a.dbias[c] + v : v;
 }
@@ -332,7 +343,7 @@ int launch_colsum(const buctd_colsum_args& a, cudaStream_t st) {
       BUCTD_CUDA(cudaFuncSetAttribute(colsum_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       colsum_kernel<__nv_bfloat16><<<kRedBlocks, 256, smem, st>>>(b);
     }
-    colsum_finalize_kernel<<<ceil_div(b.c, 128), 128, 0, st>>>(b, kRedBlocks);
+    colsum_finalize_kernel<<<ceil_div(b.c, 8), 256, 0, st>>>(b, kRedBlocks);
   }
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;
@@ -660,45 +671,58 @@ int launch_rowdot(const buctd_rowdot_args& a, cudaStream_t st) {
 // =================================================================================================
 template <typename T>
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(buctd_stem_wgrad_args a) {
-  __shared__ float s_p[4][64][27];
+  // one output row (b, oy) at a time: its three input rows of the three colour planes go through shared memory (coalesced
+  // loads, broadcast reads), thread (co, lane) walks every fourth output column
+  extern __shared__ float s_dyn[];
+  float* s_x = s_dyn;                                   // [3 ci][3 ky][w + 2]  (column -1 and w are zero)
+  float* s_p = s_dyn + 9 * (a.w + 2);                   // [4][64][27]
   const int oh = a.h / 2, ow = a.w / 2;
-  const long long npix = (long long)a.batch * oh * ow;
+  const int nrows = a.batch * oh;
   const int co = threadIdx.x & 63, pl = threadIdx.x >> 6;
+  const int wp = a.w + 2;
   float acc[27];
 #pragma unroll
   for (int t = 0; t < 27; ++t) acc[t] = 0.f;
-  for (long long p = (long long)blockIdx.x * 4 + pl; p < npix; p += (long long)gridDim.x * 4) {
-    const int ox = (int)(p % ow);
-    const long long t1 = p / ow;
-    const int oy = (int)(t1 % oh), b = (int)(t1 / oh);
-    const float g = T16<T>::to_f(reinterpret_cast<const T*>(a.dz)[(((long long)b * (oh + 1) + oy) * (ow + 1) + ox) * a.dz_cs + co]);
+  for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int b = row / oh, oy = row - b * oh;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * wp; i += 256) {
+      const int plane = i / wp, xx = i - plane * wp - 1;
+      const int ci = plane / 3, ky = plane - ci * 3;
+      const int iy = 2 * oy + ky - 1;
+      float v = 0.f;
+      if (iy >= 0 && iy < a.h && xx >= 0 && xx < a.w) {
+        const long long o = (((long long)b * a.x_channels + ci) * a.h + iy) * a.w + xx;
+        v = a.x_half ? __half2float(reinterpret_cast<const __half*>(a.x)[o]) : reinterpret_cast<const float*>(a.x)[o];
+      }
+      s_x[i] = v;
+    }
+    __syncthreads();
+    const T* dz = reinterpret_cast<const T*>(a.dz) + (((long long)b * (oh + 1) + oy) * (ow + 1)) * a.dz_cs + co;
+    for (int ox = pl; ox < ow; ox += 4) {
+      const float g = T16<T>::to_f(dz[(long long)ox * a.dz_cs]);
 #pragma unroll
-    for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int iy = 2 * oy + ky - 1, ix = 2 * ox + kx - 1;
-          float xv = 0.f;
-          if (iy >= 0 && iy < a.h && ix >= 0 && ix < a.w) {
-            const long long o = (((long long)b * a.x_channels + ci) * a.h + iy) * a.w + ix;
-            xv = a.x_half ? __half2float(reinterpret_cast<const __half*>(a.x)[o]) : reinterpret_cast<const float*>(a.x)[o];
-          }
-          acc[ci * 9 + ky * 3 + kx] = fmaf(g, xv, acc[ci * 9 + ky * 3 + kx]);
-        }
+      for (int p9 = 0; p9 < 9; ++p9) {                  // (ci, ky)
+        const float* xr = s_x + p9 * wp + 2 * ox;        // columns 2 ox - 1 .. 2 ox + 1 (+1 for the zero column)
+        acc[p9 * 3 + 0] = fmaf(g, xr[0], acc[p9 * 3 + 0]);
+        acc[p9 * 3 + 1] = fmaf(g, xr[1], acc[p9 * 3 + 1]);
+        acc[p9 * 3 + 2] = fmaf(g, xr[2], acc[p9 * 3 + 2]);
+      }
+    }
   }
-#pragma unroll
-  for (int t = 0; t < 27; ++t) s_p[pl][co][t] = acc[t];
   __syncthreads();
-  for (int i = threadIdx.x; i < 64 * 27; i += 256) {
-    const int c = i / 27, t = i - c * 27;
-    a.partial[(long long)blockIdx.x * 64 * 27 + i] = (s_p[0][c][t] + s_p[1][c][t]) + (s_p[2][c][t] + s_p[3][c][t]);
-  }
+#pragma unroll
+  for (int t = 0; t < 27; ++t) s_p[(pl * 64 + co) * 27 + t] = acc[t];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * 27; i += 256)
+    a.partial[(long long)blockIdx.x * 64 * 27 + i] = (s_p[i] + s_p[64 * 27 + i]) + (s_p[2 * 64 * 27 + i] + s_p[3 * 64 * 27 + i]);
 }
 int launch_stem_wgrad(const buctd_stem_wgrad_args& a, cudaStream_t st) {
   BUCTD_CHECK(a.x && a.dz && a.partial && a.h % 2 == 0 && a.w % 2 == 0 && a.dz_cs >= 64, BUCTD_ERR_INVALID, "stem_wgrad: bad arguments");
-  if (a.dtype == BUCTD_F16) stem_wgrad_kernel<__half><<<kRedBlocks, 256, 0, st>>>(a);
-  else stem_wgrad_kernel<__nv_bfloat16><<<kRedBlocks, 256, 0, st>>>(a);
+  const size_t smem = sizeof(float) * (9 * (size_t)(a.w + 2) + 4 * 64 * 27);
+  BUCTD_CHECK(smem <= 48 * 1024, BUCTD_ERR_INVALID, "stem_wgrad: width %d too large", a.w);
+  if (a.dtype == BUCTD_F16) stem_wgrad_kernel<__half><<<kRedBlocks, 256, smem, st>>>(a);
+  else stem_wgrad_kernel<__nv_bfloat16><<<kRedBlocks, 256, smem, st>>>(a);
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;
 }
@@ -731,35 +755,49 @@ int launch_wgrad_reduce(const buctd_wgrad_reduce_args& a, cudaStream_t st) {
 }
 
 // =================================================================================================
-// Weight re-pack (float32 masters -> 16-bit tap-GEMM layouts), table driven
+// Weight re-pack (float32 masters -> 16-bit tap-GEMM layouts), table driven.  One block = one 32 (cout) x 32 (cin) tile of one
+// entry, all taps: the float32 rows are read in contiguous 32*taps-float segments and written as 64-byte runs along the
+// destination's contiguous dimension in both layouts (shared-memory transpose).  Padding rows / columns of the packed
+// buffers are never touched (they are zero from allocation).  units: int32 [n_units][4] = {entry, cout tile, cin tile, 0}.
 // =================================================================================================
 template <typename T>
 __global__ void __launch_bounds__(256) repack_kernel(buctd_repack_args a) {
-  const int64_t* e = a.table + (long long)blockIdx.x * 8;
+  __shared__ float s_w[32][32 * 9 + 1];
+  const int* u = a.units + (long long)blockIdx.x * 4;
+  const int64_t* e = a.table + (long long)u[0] * 8;
   const long long src_off = e[0], dst_off = e[1];
   const int cout = (int)e[2], cin = (int)e[3], taps = (int)e[4], rows_alloc = (int)e[5], cs = (int)e[6], tr = (int)e[7];
+  const int co0 = u[1] * 32, ci0 = u[2] * 32;
+  const int nco = min(32, cout - co0), nci = min(32, cin - ci0);
   const float* src = a.param + src_off;
   T* dst = reinterpret_cast<T*>(a.w16) + dst_off;
-  const long long total = (long long)taps * rows_alloc * cs;
-  for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.y * blockDim.x) {
-    const int col = (int)(i % cs);
-    const long long t1 = i / cs;
-    const int row = (int)(t1 % rows_alloc), tap = (int)(t1 / rows_alloc);
-    float v = 0.f;
-    if (!tr) {                      // [tap][co][ci]
-      if (row < cout && col < cin) v = src[((long long)row * cin + col) * taps + tap];
-    } else {                        // [taps-1-tap][ci][co]
-      if (row < cin && col < cout) v = src[((long long)col * cin + row) * taps + (taps - 1 - tap)];
+  const int seg = nci * taps;                                      // contiguous floats per cout row
+  for (int i = threadIdx.x; i < nco * seg; i += 256) {
+    const int r = i / seg, j = i - r * seg;
+    s_w[r][j] = src[((long long)(co0 + r) * cin + ci0) * taps + j];
+  }
+  __syncthreads();
+  if (!tr) {                      // dst[tap][co][ci]: ci contiguous
+    for (int i = threadIdx.x; i < taps * nco * nci; i += 256) {
+      const int ci = i % nci;
+      const int t1 = i / nci;
+      const int co = t1 % nco, tap = t1 / nco;
+      dst[((long long)tap * rows_alloc + co0 + co) * cs + ci0 + ci] = T16<T>::from_f(s_w[co][ci * taps + tap]);
     }
-    dst[i] = T16<T>::from_f(v);
+  } else {                        // dst[taps-1-tap][ci][co]: co contiguous
+    for (int i = threadIdx.x; i < taps * nco * nci; i += 256) {
+      const int co = i % nco;
+      const int t1 = i / nco;
+      const int ci = t1 % nci, tap = t1 / nci;
+      dst[((long long)(taps - 1 - tap) * rows_alloc + ci0 + ci) * cs + co0 + co] = T16<T>::from_f(s_w[co][ci * taps + tap]);
+    }
   }
 }
 int launch_repack(const buctd_repack_args& a, cudaStream_t st) {
-  BUCTD_CHECK(a.param && a.w16 && a.table && a.n_entries >= 0, BUCTD_ERR_INVALID, "repack: bad arguments");
-  if (a.n_entries == 0) return BUCTD_OK;
-  dim3 grid(a.n_entries, 16);
-  if (a.dtype == BUCTD_F16) repack_kernel<__half><<<grid, 256, 0, st>>>(a);
-  else repack_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a);
+  BUCTD_CHECK(a.param && a.w16 && a.table && a.units && a.n_entries >= 0 && a.n_units >= 0, BUCTD_ERR_INVALID, "repack: bad arguments");
+  if (a.n_units == 0) return BUCTD_OK;
+  if (a.dtype == BUCTD_F16) repack_kernel<__half><<<a.n_units, 256, 0, st>>>(a);
+  else repack_kernel<__nv_bfloat16><<<a.n_units, 256, 0, st>>>(a);
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;
 }

@@ -105,6 +105,12 @@ class TrainStep:
         self.w16 = torch.zeros(self._w16_elems + 64, dtype=self.tdt, device=self.device)
         self._build(dry=False)
         self.table = torch.tensor(self._table, dtype=torch.int64, device=self.device)
+        units = []
+        for e, (_, _, cout, cin, taps, _, _, _) in enumerate(self._table):
+            assert taps <= 9
+            for i in range((cout + 31) // 32):
+                units.extend([e, i, j, 0] for j in range((cin + 31) // 32))
+        self.units = torch.tensor(units, dtype=torch.int32, device=self.device)
         self.seed_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.seed_dev.zero_()
         self._repack()
@@ -183,10 +189,11 @@ class TrainStep:
         rows = dz.rows
         g = L.Gemm16Args()
         g.dtype, g.a_mn_major, g.b_mn_major, g.m, g.n, g.k = self.dt, 1, 1, cout, cin, rows
-        bn = _rup(cin, 16) if cin <= 256 else 256
-        tiles = ((cout + 127) // 128) * ((cin + bn - 1) // bn) * taps
-        nsplit = max(1, min((2 * 148 + tiles - 1) // tiles, (rows + 511) // 512, 64))
-        g.nbatch, g.nsplit, g.ntaps, g.b_rows = 1, nsplit, taps, rows
+        group = 3 if taps == 9 else 0         # the three dx taps of a kernel row share one A tile and one widened B stage
+        bn = _rup(cin, 16) if cin <= (128 if group else 256) else (128 if group else 256)
+        tiles = ((cout + 127) // 128) * ((cin + bn - 1) // bn) * (taps // 3 if group else taps)
+        nsplit = max(1, min(148 // tiles if tiles <= 148 else 1, (rows + 255) // 256, 64))      # one wave of CTAs
+        g.nbatch, g.nsplit, g.ntaps, g.b_rows, g.tap_group = 1, nsplit, taps, rows, group
         g.lda, g.ldb, g.ldd, g.out_f32, g.accumulate = dz.cs, x.cs, cin, 1, 0
         g.d_t_stride, g.d_s_stride, g.d_b_stride = cout * cin, taps * cout * cin, 0
         if taps == 9:
@@ -636,8 +643,8 @@ class TrainStep:
 
     def _repack(self):
         a = L.RepackArgs()
-        a.dtype, a.n_entries = self.dt, self.table.shape[0]
-        a.param, a.w16, a.table = self.opt.flat.data_ptr(), self._w16_base, self.table.data_ptr()
+        a.dtype, a.n_entries, a.n_units = self.dt, self.table.shape[0], self.units.shape[0]
+        a.param, a.w16, a.table, a.units = self.opt.flat.data_ptr(), self._w16_base, self.table.data_ptr(), self.units.data_ptr()
         with torch.cuda.device(self.device):
             self.ctx.call("buctd_repack_weights", a, torch.cuda.current_stream(self.device).cuda_stream)
 

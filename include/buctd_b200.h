@@ -373,7 +373,9 @@ int buctd_pck_accuracy(buctd_ctx* ctx, const buctd_pck_args* args, buctd_stream 
 typedef struct {
   int32_t dtype, a_mn_major, b_mn_major, m, n, k;
   int32_t nbatch, nsplit, ntaps, b_rows;       /* b_rows: K rows of one batch of an MN-major B (0: k) */
-  int32_t lda, ldb, ldd, out_f32, accumulate, reserved;
+  int32_t lda, ldb, ldd, out_f32, accumulate;
+  int32_t tap_group;    /* 3: the taps come in groups of three with row offsets o, o+1, o+2 (the dx taps of a kernel row): one CTA computes
+                           a group from one A tile and one widened B stage (a third of the operand traffic); 0 / 1: one tap per CTA */
   int64_t a_batch_stride, b_batch_stride, d_t_stride, d_s_stride, d_b_stride;
   int32_t tap_off[9]; float alpha;
   const void* a; const void* b; void* d;
@@ -485,8 +487,10 @@ int buctd_stem_wgrad(buctd_ctx* ctx, const buctd_stem_wgrad_args* args, buctd_st
 /* Re-pack float32 master weights into the 16-bit tap-GEMM layouts after an optimizer step, table driven (one launch):
  * entry e: src [cout][cin][taps] float32 at param + src_off -> dst at w16 + dst_off, forward layout [tap][n_alloc][k_cs]
  * (transposed = 0) or data-gradient layout [taps-1-tap][cin_alloc][cout_cs] holding W[co][ci][tap] at [..][ci][co]
- * (transposed = 1).  table: int64 [n_entries][8] = {src_off, dst_off, cout, cin, taps, rows_alloc, cs, transposed}. */
-typedef struct { int32_t dtype, n_entries; const float* param; void* w16; const int64_t* table; } buctd_repack_args;
+ * (transposed = 1).  table: int64 [n_entries][8] = {src_off, dst_off, cout, cin, taps (<= 9), rows_alloc, cs, transposed};
+ * units: int32 [n_units][4] = {entry, cout tile, cin tile, 0}, one per 32 x 32 tile of every entry.  Padding rows / columns of
+ * w16 are not written: allocate it zeroed. */
+typedef struct { int32_t dtype, n_entries, n_units, reserved; const float* param; void* w16; const int64_t* table; const int32_t* units; } buctd_repack_args;
 int buctd_repack_weights(buctd_ctx* ctx, const buctd_repack_args* args, buctd_stream stream);
 
 /* Utility kernels used by the host mirror: zero-fill, and act16 -> nchw32 export for tests. */

@@ -35,13 +35,13 @@ def drop_mask(seed, crop, rows, cols, p):
 
 
 def gemm16(dt, a, b, m, n, k, *, a_mn, b_mn, nbatch=1, nsplit=1, ntaps=1, tap_off=None, out_f32=True, alpha=1.0, accumulate=False,
-           d=None, lda=None, ldb=None, a_bs=0, b_bs=0, b_rows=0, ldd=None, d_strides=(0, 0, 0)):
+           d=None, lda=None, ldb=None, a_bs=0, b_bs=0, b_rows=0, ldd=None, d_strides=(0, 0, 0), tap_group=0):
     g = L.Gemm16Args()
     g.dtype, g.a_mn_major, g.b_mn_major, g.m, g.n, g.k = dt, int(a_mn), int(b_mn), m, n, k
     g.nbatch, g.nsplit, g.ntaps, g.b_rows = nbatch, nsplit, ntaps, b_rows
     g.lda, g.ldb = lda or a.shape[-1], ldb or b.shape[-1]
     g.ldd = ldd or n
-    g.out_f32, g.accumulate = int(out_f32), int(accumulate)
+    g.out_f32, g.accumulate, g.tap_group = int(out_f32), int(accumulate), tap_group
     g.a_batch_stride, g.b_batch_stride = a_bs, b_bs
     g.d_t_stride, g.d_s_stride, g.d_b_stride = d_strides
     for i, o in enumerate(tap_off or [0] * 9):
@@ -80,8 +80,10 @@ def test_gemm16_majors(dt, a_mn, b_mn, m, n, k):
 
 
 @pytest.mark.parametrize("dt", DTS)
-@pytest.mark.parametrize("cin,cout,B,h,w,nsplit", [(48, 48, 3, 12, 9, 4), (96, 64, 2, 7, 5, 3), (32, 200, 2, 6, 4, 1), (17, 48, 2, 8, 6, 2)])
-def test_gemm16_conv_weight_gradient(dt, cin, cout, B, h, w, nsplit):
+@pytest.mark.parametrize("group", [0, 3])
+@pytest.mark.parametrize("cin,cout,B,h,w,nsplit", [(48, 48, 3, 12, 9, 4), (96, 64, 2, 7, 5, 3), (32, 200, 2, 6, 4, 1), (17, 48, 2, 8, 6, 2),
+                                                   (192, 192, 2, 6, 5, 2), (384, 384, 2, 3, 2, 1), (256, 48, 1, 9, 7, 3)])
+def test_gemm16_conv_weight_gradient(dt, cin, cout, B, h, w, nsplit, group):
     """dW[co][ci][ky][kx] of a 3x3 stride-1 convolution: gemm16 (taps = row offsets of the padded act16 matrices, split
     partials) + wgrad_reduce against torch's conv2d weight gradient."""
     x = q16(_rand(B, cin, h, w, seed=3), dt)
@@ -91,7 +93,7 @@ def test_gemm16_conv_weight_gradient(dt, cin, cout, B, h, w, nsplit):
     part = torch.full((nsplit, 9, cout, cin), 3.0, device="cuda")
     offs = [(ky - 1) * (w + 1) + (kx - 1) for ky in range(3) for kx in range(3)]
     gemm16(dt, dya, xa, cout, cin, rows, a_mn=1, b_mn=1, nsplit=nsplit, ntaps=9, tap_off=offs, d=part, ldd=cin,
-           d_strides=(cout * cin, 9 * cout * cin, 0), b_rows=rows)
+           d_strides=(cout * cin, 9 * cout * cin, 0), b_rows=rows, tap_group=group)
     grad = torch.zeros(cout, cin, 3, 3, device="cuda")
     r = L.WgradReduceArgs()
     r.n, r.k, r.ntaps, r.nsplit, r.accumulate, r.inv_scale = cout, cin, 9, nsplit, 0, 0.25
@@ -488,8 +490,11 @@ def test_repack_weights(dt):
     flat = torch.cat(params)
     w16 = torch.full((dst_off,), 3.0, dtype=TDT[dt], device="cuda")
     tab = torch.tensor(table, dtype=torch.int64, device="cuda")
+    units = [[e, i, j, 0] for e, t in enumerate(table) for i in range((t[2] + 31) // 32) for j in range((t[3] + 31) // 32)]
+    un = torch.tensor(units, dtype=torch.int32, device="cuda")
+    w16.zero_()                                      # padding rows / columns are not written by the kernel
     a = L.RepackArgs()
-    a.dtype, a.n_entries, a.param, a.w16, a.table = dt, len(table), flat.data_ptr(), w16.data_ptr(), tab.data_ptr()
+    a.dtype, a.n_entries, a.n_units, a.param, a.w16, a.table, a.units = dt, len(table), len(units), flat.data_ptr(), w16.data_ptr(), tab.data_ptr(), un.data_ptr()
     ctx().call("buctd_repack_weights", a, stream())
     torch.cuda.synchronize()
     for off, e in exp:
