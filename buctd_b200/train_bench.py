@@ -110,6 +110,9 @@ def run(args, ClockSampler, load_peaks):
         t = torch.tensor([ms, ms_e2e], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = t.tolist()
+    lib = None
+    if world == 1 and not args.no_gpu_baseline and not args.quick:
+        lib = library_baseline(torch, cfg, net, sets[0], args.lib_batch or B)
     if rank == 0:
         peaks = load_peaks()
         crops = B * world * args.steps
@@ -137,6 +140,64 @@ def run(args, ClockSampler, load_peaks):
             "launch_note": "C-ABI launches recorded per step (replayed as one CUDA graph + Adam + re-pack); %d immediate launches counted by the handle" % launches,
             "clocks": clocks,
         }
+        if lib is not None:
+            out["gpu_library_baseline"] = lib
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def library_baseline(torch, cfg, net, batch, B):
+    """The same training step through PyTorch eager on this GPU (cuDNN / cuBLAS / ATen autograd + torch.optim.Adam): the
+    reference's own training loop (lib/core/function.py:113-138) with its network restated functionally
+    (oracle/train_oracle.py, pinned to the reference by tests/test_train_oracle.py; /root/reference does not exist on the GPU
+    box).  (tf32) PyTorch's default for the reference's fp32 model, (bf16) autocast(bfloat16).  Reported baseline only."""
+    import contextlib
+    import torch.nn.functional as F
+    from oracle import hrnet_oracle as O
+    from oracle import train_oracle as T
+    x, tgt, tw = [t[:B] for t in batch]
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    params = {k: v.float().requires_grad_(v.dtype.is_floating_point and "running_" not in k) for k, v in sd.items() if not k.endswith("num_batches_tracked")}
+    opt = torch.optim.Adam([p for p in params.values() if p.requires_grad], lr=1e-3)
+    out = {}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+    try:
+        for name in ("tf32", "bf16"):
+            torch.backends.cudnn.allow_tf32 = True
+            amp = torch.autocast("cuda", dtype=torch.bfloat16) if name == "bf16" else contextlib.nullcontext()
+
+            def step():
+                O._CTX.update({"train": True, "running": None, "drop": None, "drop_p": 0.0})
+                try:
+                    with amp:
+                        hm = O.forward(params, cfg, x)
+                        hm = F.dropout(hm, 0.0)
+                    loss = T.joints_mse(hm.float(), tgt, tw, True)
+                finally:
+                    O._CTX.update({"train": False})
+                opt.zero_grad(set_to_none=True)
+                loss.backward()
+                opt.step()
+                return loss
+            try:
+                step()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n = 2
+                e0.record()
+                for _ in range(n):
+                    step()
+                e1.record()
+                torch.cuda.synchronize()
+                out[name] = {"value": round(B * n / (e0.elapsed_time(e1) / 1e3), 2), "unit": "crops/s", "batch": B, "steps": n,
+                             "ms_per_step": round(e0.elapsed_time(e1) / n, 2)}
+            except torch.cuda.OutOfMemoryError:
+                out[name] = {"value": None, "note": "out of memory at batch %d" % B}
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark = old
+    out["what"] = ("the reference's training step through PyTorch eager on this GPU (functional restatement of the network + "
+                   "torch.autograd + torch.optim.Adam; attention dropout omitted), batch %d" % B)
+    return out
