@@ -214,6 +214,12 @@ class PosSoftmaxBwdArgs(C.Structure):
                 ("drop_p", f32c), ("seed", u32), ("reserved2", i32), ("s", fp), ("dpd", fp), ("lse2", fp), ("delta", fp), ("pd", vp), ("ds", vp), ("seed_xor", vp)]
 
 
+class PosBwdScoresArgs(C.Structure):
+    _fields_ = [("dtype", i32), ("batch", i32), ("h", i32), ("w", i32), ("c", i32), ("q_cs", i32), ("k_cs", i32), ("v_cs", i32),
+                ("do_cs", i32), ("ld", i32), ("drop_p", f32c), ("seed", u32), ("q", vp), ("k", vp), ("v", vp), ("d_o", vp),
+                ("lse2", fp), ("delta", fp), ("pd", vp), ("ds", vp), ("seed_xor", vp)]
+
+
 class RowdotArgs(C.Structure):
     _fields_ = [("dtype", i32), ("c", i32), ("a_cs", i32), ("b_cs", i32), ("rows", i64), ("a", vp), ("b", vp), ("out", fp)]
 
@@ -229,7 +235,7 @@ class RepackArgs(C.Structure):
 
 TRAIN_EXPORTS = ["buctd_gemm16", "buctd_wgrad_reduce", "buctd_bn_stats", "buctd_bn_apply", "buctd_bn_bwd", "buctd_colsum", "buctd_zero_stuff",
                  "buctd_hr_fuse_bwd", "buctd_add16", "buctd_planar_to_act16", "buctd_act16_to_planar", "buctd_chan_softmax_bwd",
-                 "buctd_pos_softmax_bwd", "buctd_rowdot", "buctd_stem_wgrad", "buctd_repack_weights"]
+                 "buctd_pos_softmax_bwd", "buctd_pos_att_bwd_scores", "buctd_rowdot", "buctd_stem_wgrad", "buctd_repack_weights"]
 
 OP_STRUCT = {OP_TAPGEMM: TapGemmArgs, OP_STEM: StemArgs, OP_FUSE: FuseArgs, OP_RESIZE: ResizeArgs,
              OP_CHAN_ATT: ChanAttArgs, OP_POS_ATT: PosAttArgs, OP_DA_COMBINE: DaCombineArgs, OP_PRENET: PrenetArgs,

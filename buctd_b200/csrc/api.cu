@@ -292,6 +292,7 @@ BUCTD_API int buctd_create(int device, buctd_ctx** out) {
   if (!rc) rc = tapgemm_chain_init_device();
   if (!rc) rc = pos_att_tc_init_device();
   if (!rc) rc = gemm16_init_device();
+  if (!rc) rc = pos_att_bwd_init_device();
   if (!rc && get_encode_tiled() == nullptr) {
     set_error("buctd_create: cuTensorMapEncodeTiled driver entry point not found");
     rc = BUCTD_ERR_NO_DEVICE;
@@ -434,6 +435,9 @@ BUCTD_API int buctd_chan_softmax_bwd(buctd_ctx* c, const buctd_chan_softmax_bwd_
 }
 BUCTD_API int buctd_pos_softmax_bwd(buctd_ctx* c, const buctd_pos_softmax_bwd_args* a, buctd_stream s) {
   return simple_call(c, a, 1, [&](const buctd_pos_softmax_bwd_args& x) { return launch_pos_softmax_bwd(x, static_cast<cudaStream_t>(s)); });
+}
+BUCTD_API int buctd_pos_att_bwd_scores(buctd_ctx* c, const buctd_pos_bwd_scores_args* a, buctd_stream s) {
+  return simple_call(c, a, 1, [&](const buctd_pos_bwd_scores_args& x) { return launch_pos_bwd_scores(x, static_cast<cudaStream_t>(s)); });
 }
 BUCTD_API int buctd_rowdot(buctd_ctx* c, const buctd_rowdot_args* a, buctd_stream s) {
   return simple_call(c, a, 1, [&](const buctd_rowdot_args& x) { return launch_rowdot(x, static_cast<cudaStream_t>(s)); });

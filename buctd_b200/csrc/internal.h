@@ -114,6 +114,8 @@ int launch_planar_to_act16(const buctd_relayout_args& a, cudaStream_t st);
 int launch_act16_to_planar(const buctd_relayout_args& a, cudaStream_t st);
 int launch_chan_softmax_bwd(const buctd_chan_softmax_bwd_args& a, cudaStream_t st);
 int launch_pos_softmax_bwd(const buctd_pos_softmax_bwd_args& a, cudaStream_t st);
+int pos_att_bwd_init_device();
+int launch_pos_bwd_scores(const buctd_pos_bwd_scores_args& a, cudaStream_t st);
 int launch_rowdot(const buctd_rowdot_args& a, cudaStream_t st);
 int launch_stem_wgrad(const buctd_stem_wgrad_args& a, cudaStream_t st);
 int launch_repack(const buctd_repack_args& a, cudaStream_t st);

@@ -102,6 +102,13 @@ template <> __device__ __forceinline__ uint32_t ex2_pack<__nv_bfloat16>(float a,
   return r;
 }
 
+#ifndef BUCTD_PA_F32_EXP
+template <typename T> constexpr bool kPackedExp = false;
+template <> constexpr bool kPackedExp<__half> = true;
+#else
+template <typename T> constexpr bool kPackedExp = false;
+#endif
+
 template <typename T>
 __global__ void __launch_bounds__(kTcThreads, 2)
 pos_att_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
@@ -332,7 +339,11 @@ pos_att_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           for (int i = 0; i < 16; ++i) {
             const float s0 = __uint_as_float(v[2 * i]), s1 = __uint_as_float(v[2 * i + 1]);
             rawmax = fmaxf(rawmax, fmaxf(s0, s1));
-            pk[i] = pack_ns<T>(ex2f(fmaf(s0, p.sc, neg_m)), ex2f(fmaf(s1, p.sc, neg_m)));
+            // fp16: ONE packed MUFU op (ex2.approx.f16x2) per two scores, result already packed -- the exponent argument
+            // is in (-inf, 8] where half precision keeps exp2 within 0.3 % (P is rounded to 16 bit anyway); bf16 keeps
+            // the float32 exponentials (an 8-bit argument would cost 2 %)
+            if (kPackedExp<T>) pk[i] = ex2_pack<T>(fmaf(s0, p.sc, neg_m), fmaf(s1, p.sc, neg_m));
+            else pk[i] = pack_ns<T>(ex2f(fmaf(s0, p.sc, neg_m)), ex2f(fmaf(s1, p.sc, neg_m)));
           }
           uint8_t* blk = prow + (c0 >> 6) * kTcBlk;
           const int ci = (c0 & 63) >> 3;

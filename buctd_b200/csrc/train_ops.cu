@@ -88,10 +88,12 @@ size_t col_reduce_smem(int c, int nv) {
   return sizeof(double) * (size_t)nrl * nv * groups * 8;
 }
 
-__device__ __forceinline__ bool is_pad_row(long long r, int H, int W) {
-  const int x = (int)(r % (W + 1));
-  const int y = (int)((r / (W + 1)) % (H + 1));
-  return x == W || y == H;
+// row indices of one tensor fit 32 bits (<= 7.2 M rows at batch 256): 32-bit divisions, not 64-bit ones
+__device__ __forceinline__ bool is_pad_row(unsigned r, int H, int W) {
+  const unsigned ry = r / (unsigned)(W + 1);
+  const unsigned x = r - ry * (unsigned)(W + 1);
+  const unsigned y = ry % (unsigned)(H + 1);
+  return x == (unsigned)W || y == (unsigned)H;
 }
 
 }  // namespace
@@ -163,11 +165,11 @@ int launch_bn_stats(const buctd_bn_stats_args& a, cudaStream_t st) {
 // =================================================================================================
 template <typename T>
 __global__ void __launch_bounds__(256) bn_apply_kernel(buctd_bn_apply_args a) {
-  const long long rows = (long long)a.batch * (a.h + 1) * (a.w + 1);
-  const int groups = a.out_cs / 8;
-  const long long total = rows * groups;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / groups;
+  const unsigned rows = (unsigned)a.batch * (a.h + 1) * (a.w + 1);
+  const unsigned groups = a.out_cs / 8;
+  const unsigned total = rows * groups;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned r = i / groups;
     const int c0 = (int)(i - r * groups) * 8;
     float o[8];
 #pragma unroll
@@ -241,12 +243,12 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(buctd_bn_bwd_args 
 }
 template <typename T>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(buctd_bn_bwd_args a, int nblocks) {
-  const long long rows = (long long)a.batch * (a.h + 1) * (a.w + 1);
-  const int groups = a.dz_cs / 8;
-  const long long total = rows * groups;
+  const unsigned rows = (unsigned)a.batch * (a.h + 1) * (a.w + 1);
+  const unsigned groups = a.dz_cs / 8;
+  const unsigned total = rows * groups;
   const double* m = a.scratch + (size_t)nblocks * 2 * a.c;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / groups;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned r = i / groups;
     const int c0 = (int)(i - r * groups) * 8;
     float o[8], gr[8];
 #pragma unroll
@@ -355,15 +357,15 @@ int launch_colsum(const buctd_colsum_args& a, cudaStream_t st) {
 template <typename T>
 __global__ void __launch_bounds__(256) zero_stuff_kernel(buctd_zero_stuff_args a) {
   const int OH = 2 * a.h, OW = 2 * a.w;
-  const int groups = a.cs / 8;
-  const long long total = (long long)a.batch * (OH + 1) * (OW + 1) * groups;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / groups;
+  const unsigned groups = a.cs / 8;
+  const unsigned total = (unsigned)a.batch * (OH + 1) * (OW + 1) * groups;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned r = i / groups;
     const int c0 = (int)(i - r * groups) * 8;
-    const int X = (int)(r % (OW + 1));
-    const long long ry = r / (OW + 1);
-    const int Y = (int)(ry % (OH + 1));
-    const int b = (int)(ry / (OH + 1));
+    const unsigned ry = r / (unsigned)(OW + 1);
+    const int X = (int)(r - ry * (unsigned)(OW + 1));
+    const int b = (int)(ry / (unsigned)(OH + 1));
+    const int Y = (int)(ry - (unsigned)b * (unsigned)(OH + 1));
     uint4 u = make_uint4(0, 0, 0, 0);
     if (!(X & 1) && !(Y & 1) && X < OW && Y < OH) u = ld8<T>(a.in, ((long long)b * (a.h + 1) + (Y >> 1)) * (a.w + 1) + (X >> 1), a.cs, c0);
     st8<T>(a.out, r, a.cs, c0, u);
@@ -388,16 +390,16 @@ __global__ void __launch_bounds__(256) fuse_bwd_kernel(buctd_fuse_bwd_args a, in
   const int sh = a.term_shift[j];
   const int th = a.h >> sh, tw = a.w >> sh;
   const int tcs = a.term_cs[j];
-  const int groups = tcs / 8;
-  const long long total = (long long)a.batch * (th + 1) * (tw + 1) * groups;
+  const unsigned groups = tcs / 8;
+  const unsigned total = (unsigned)a.batch * (th + 1) * (tw + 1) * groups;
   const int n = 1 << sh;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / groups;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned r = i / groups;
     const int c0 = (int)(i - r * groups) * 8;
-    const int X = (int)(r % (tw + 1));
-    const long long ry = r / (tw + 1);
-    const int Y = (int)(ry % (th + 1));
-    const int b = (int)(ry / (th + 1));
+    const unsigned ry = r / (unsigned)(tw + 1);
+    const int X = (int)(r - ry * (unsigned)(tw + 1));
+    const int b = (int)(ry / (unsigned)(th + 1));
+    const int Y = (int)(ry - (unsigned)b * (unsigned)(th + 1));
     float acc[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc[q] = 0.f;
@@ -587,30 +589,31 @@ int launch_chan_softmax_bwd(const buctd_chan_softmax_bwd_args& a, cudaStream_t s
 template <typename T>
 __global__ void __launch_bounds__(256) pos_softmax_bwd_kernel(buctd_pos_softmax_bwd_args a) {
   const int rows = (a.h + 1) * (a.w + 1);
-  const int groups = a.ld / 8;
-  const long long total = (long long)a.batch * rows * groups;
+  const unsigned groups = a.ld / 8;
+  const unsigned total = (unsigned)a.batch * rows * groups;            // < 2^32 (checked by the launcher)
   const uint32_t thr = drop_threshold(a.drop_p);
   const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
   const uint32_t seed = a.seed ^ (a.seed_xor ? *a.seed_xor : 0u);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long qr = i / groups;                 // global query row
+  const unsigned wp = a.w + 1;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned qr = i / groups;                  // global query row
     const int k0 = (int)(i - qr * groups) * 8;
-    const int b = (int)(qr / rows), q = (int)(qr - (long long)b * rows);
-    const bool qv = (q % (a.w + 1)) != a.w && (q / (a.w + 1)) != a.h;
+    const int b = (int)(qr / (unsigned)rows), q = (int)(qr - (unsigned)b * (unsigned)rows);
+    const bool qv = ((unsigned)q % wp) != (unsigned)a.w && ((unsigned)q / wp) != (unsigned)a.h;
     float pd[8], ds[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { pd[j] = 0.f; ds[j] = 0.f; }
     if (qv) {
       const float lse = a.lse2[qr], dl = a.delta[qr];
-      const float4* sp = reinterpret_cast<const float4*>(a.s + qr * a.ld + k0);
-      const float4* dp = reinterpret_cast<const float4*>(a.dpd + qr * a.ld + k0);
+      const float4* sp = reinterpret_cast<const float4*>(a.s + (long long)qr * a.ld + k0);
+      const float4* dp = reinterpret_cast<const float4*>(a.dpd + (long long)qr * a.ld + k0);
       const float4 s0 = sp[0], s1 = sp[1], d0 = dp[0], d1 = dp[1];
       const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
       const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int k = k0 + j;
-        if (k < rows && (k % (a.w + 1)) != a.w && (k / (a.w + 1)) != a.h) {
+        const unsigned k = (unsigned)(k0 + j);
+        if (k < (unsigned)rows && (k % wp) != (unsigned)a.w && (k / wp) != (unsigned)a.h) {
           const float p = exp2f(sv[j] - lse);
           const bool keep = a.drop_p <= 0.f || drop_hash(seed, (uint32_t)b, (uint32_t)q, (uint32_t)k) >= thr;
           pd[j] = keep ? p * keep_scale : 0.f;
@@ -626,6 +629,7 @@ int launch_pos_softmax_bwd(const buctd_pos_softmax_bwd_args& a, cudaStream_t st)
   BUCTD_CHECK(a.s && a.dpd && a.lse2 && a.delta && a.pd && a.ds, BUCTD_ERR_INVALID, "pos_softmax_bwd: null pointer");
   BUCTD_CHECK(a.ld % 8 == 0 && a.ld >= (a.h + 1) * (a.w + 1), BUCTD_ERR_INVALID, "pos_softmax_bwd: bad row stride %d", a.ld);
   const long long total = (long long)a.batch * (a.h + 1) * (a.w + 1) * (a.ld / 8);
+  BUCTD_CHECK(total < (1ll << 32), BUCTD_ERR_INVALID, "pos_softmax_bwd: %lld element groups exceed 32-bit indexing (split the batch)", total);
   const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
   if (blocks == 0) return BUCTD_OK;
   if (a.dtype == BUCTD_F16) pos_softmax_bwd_kernel<__half><<<blocks, 256, 0, st>>>(a);

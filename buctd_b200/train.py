@@ -390,19 +390,27 @@ class TrainStep:
             r.dtype, r.c, r.a_cs, r.b_cs, r.rows = self.dt, C_, do.cs, o.cs, B * rows1
             r.a, r.b, r.out = do.ptr, o.ptr, delta
             self._call(ops, "buctd_rowdot", r)
-            s32 = self._take(B * rows1 * ld * 4)
-            dpd = self._take(B * rows1 * ld * 4)
-            sc = math.log2(math.e) / math.sqrt(C_)
-            self._gemm(ops, q.ptr, k.ptr, s32, rows1, rows1, C_, a_mn=0, b_mn=0, lda=q.cs, ldb=k.cs, ldd=ld, nbatch=B, a_bs=rows1 * q.cs,
-                       b_bs=rows1 * k.cs, d_bs=rows1 * ld, out_f32=1, alpha=sc)
-            self._gemm(ops, do.ptr, v.ptr, dpd, rows1, rows1, C_, a_mn=0, b_mn=0, lda=do.cs, ldb=v.cs, ldd=ld, nbatch=B, a_bs=rows1 * do.cs,
-                       b_bs=rows1 * v.cs, d_bs=rows1 * ld, out_f32=1)
             pd = self._take(B * rows1 * ld * 2)
             ds = self._take(B * rows1 * ld * 2)
-            e = L.PosSoftmaxBwdArgs()
-            e.dtype, e.batch, e.h, e.w, e.ld, e.inv_sqrt_c, e.drop_p, e.seed = self.dt, B, h, w, ld, 1.0 / math.sqrt(C_), self.drop_p, seed_p
-            e.s, e.dpd, e.lse2, e.delta, e.pd, e.ds, e.seed_xor = s32, dpd, lse, delta, pd, ds, self.seed_dev_ptr
-            self._call(ops, "buctd_pos_softmax_bwd", e)
+            if os.environ.get("BUCTD_POS_BWD_FUSED", "1") != "0":
+                # S = Q K^T and dP = dO V^T in TMEM, soft-max backward in the epilogue: the float32 score matrices never exist
+                f = L.PosBwdScoresArgs()
+                f.dtype, f.batch, f.h, f.w, f.c, f.q_cs, f.k_cs, f.v_cs, f.do_cs, f.ld = self.dt, B, h, w, C_, q.cs, k.cs, v.cs, do.cs, ld
+                f.drop_p, f.seed, f.seed_xor = self.drop_p, seed_p, self.seed_dev_ptr
+                f.q, f.k, f.v, f.d_o, f.lse2, f.delta, f.pd, f.ds = q.ptr, k.ptr, v.ptr, do.ptr, lse, delta, pd, ds
+                self._call(ops, "buctd_pos_att_bwd_scores", f)
+            else:
+                s32 = self._take(B * rows1 * ld * 4)
+                dpd = self._take(B * rows1 * ld * 4)
+                sc = math.log2(math.e) / math.sqrt(C_)
+                self._gemm(ops, q.ptr, k.ptr, s32, rows1, rows1, C_, a_mn=0, b_mn=0, lda=q.cs, ldb=k.cs, ldd=ld, nbatch=B, a_bs=rows1 * q.cs,
+                           b_bs=rows1 * k.cs, d_bs=rows1 * ld, out_f32=1, alpha=sc)
+                self._gemm(ops, do.ptr, v.ptr, dpd, rows1, rows1, C_, a_mn=0, b_mn=0, lda=do.cs, ldb=v.cs, ldd=ld, nbatch=B, a_bs=rows1 * do.cs,
+                           b_bs=rows1 * v.cs, d_bs=rows1 * ld, out_f32=1)
+                e = L.PosSoftmaxBwdArgs()
+                e.dtype, e.batch, e.h, e.w, e.ld, e.inv_sqrt_c, e.drop_p, e.seed = self.dt, B, h, w, ld, 1.0 / math.sqrt(C_), self.drop_p, seed_p
+                e.s, e.dpd, e.lse2, e.delta, e.pd, e.ds, e.seed_xor = s32, dpd, lse, delta, pd, ds, self.seed_dev_ptr
+                self._call(ops, "buctd_pos_softmax_bwd", e)
             dv, accv = self._grad(v)
             dk, acck = self._grad(k)
             dq, accq = self._grad(q)

@@ -475,6 +475,16 @@ typedef struct {
 } buctd_pos_softmax_bwd_args;
 int buctd_pos_softmax_bwd(buctd_ctx* ctx, const buctd_pos_softmax_bwd_args* args, buctd_stream stream);
 
+/* The same result without the float32 score matrices: per (query tile, key tile) both products S = Q K^T and dP = dO V^T are
+ * accumulated in TMEM and the soft-max backward runs in the epilogue (2 x 6.4 GB of float32 less at batch 32, 96x72).
+ * q, k, v, d_o: act16 [B][(H+1)(W+1)][cs]; pd, ds: 16-bit [B][rows][ld] as above. */
+typedef struct {
+  int32_t dtype, batch, h, w, c, q_cs, k_cs, v_cs, do_cs, ld; float drop_p; uint32_t seed;
+  const void* q; const void* k; const void* v; const void* d_o; const float* lse2; const float* delta; void* pd; void* ds;
+  const uint32_t* seed_xor;
+} buctd_pos_bwd_scores_args;
+int buctd_pos_att_bwd_scores(buctd_ctx* ctx, const buctd_pos_bwd_scores_args* args, buctd_stream stream);
+
 /* delta[r] = sum_c a[r][c] b[r][c] (float32) over 16-bit [rows][cs] matrices */
 typedef struct { int32_t dtype, c, a_cs, b_cs; int64_t rows; const void* a; const void* b; float* out; } buctd_rowdot_args;
 int buctd_rowdot(buctd_ctx* ctx, const buctd_rowdot_args* args, buctd_stream stream);

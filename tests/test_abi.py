@@ -44,7 +44,7 @@ def test_struct_fields_match_header():
              "buctd_bn_apply_args": L.BnApplyArgs, "buctd_bn_bwd_args": L.BnBwdArgs, "buctd_colsum_args": L.ColsumArgs,
              "buctd_zero_stuff_args": L.ZeroStuffArgs, "buctd_fuse_bwd_args": L.FuseBwdArgs, "buctd_add16_args": L.Add16Args,
              "buctd_relayout_args": L.RelayoutArgs, "buctd_chan_softmax_bwd_args": L.ChanSoftmaxBwdArgs,
-             "buctd_pos_softmax_bwd_args": L.PosSoftmaxBwdArgs, "buctd_rowdot_args": L.RowdotArgs,
+             "buctd_pos_softmax_bwd_args": L.PosSoftmaxBwdArgs, "buctd_pos_bwd_scores_args": L.PosBwdScoresArgs, "buctd_rowdot_args": L.RowdotArgs,
              "buctd_stem_wgrad_args": L.StemWgradArgs, "buctd_repack_args": L.RepackArgs}
     for cname, st in pairs.items():
         body = re.search(r"typedef struct \{([^}]*)\}\s*%s;" % cname, h).group(1)

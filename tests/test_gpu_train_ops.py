@@ -394,6 +394,19 @@ def test_position_attention_train_forward_backward(dt, p, C, h, w):
     e.dtype, e.batch, e.h, e.w, e.ld, e.inv_sqrt_c, e.drop_p, e.seed = dt, B, h, w, ld, 1.0 / math.sqrt(C), p, 1234
     e.s, e.dpd, e.lse2, e.delta, e.pd, e.ds = s.data_ptr(), dpd.data_ptr(), lse.data_ptr(), delta.data_ptr(), pd.data_ptr(), ds.data_ptr()
     ctx().call("buctd_pos_softmax_bwd", e, stream())
+    # the fused score stage (both products in TMEM, soft-max backward in the epilogue) must give the same pd / ds
+    pd2 = torch.full_like(pd, 3.0)
+    ds2 = torch.full_like(ds, 3.0)
+    f = L.PosBwdScoresArgs()
+    f.dtype, f.batch, f.h, f.w, f.c, f.q_cs, f.k_cs, f.v_cs, f.do_cs, f.ld = dt, B, h, w, C, C, 2 * C, 2 * C, C, ld
+    f.drop_p, f.seed = p, 1234
+    f.q, f.k, f.v, f.d_o = qa.data_ptr(), kv.data_ptr(), kv.data_ptr() + 2 * C, doa.data_ptr()
+    f.lse2, f.delta, f.pd, f.ds = lse.data_ptr(), delta.data_ptr(), pd2.data_ptr(), ds2.data_ptr()
+    ctx().call("buctd_pos_att_bwd_scores", f, stream())
+    torch.cuda.synchronize()
+    assert_close(pd2, pd, 2e-3, "fused pd")
+    assert_close(ds2, ds, 2e-3, "fused ds")
+    assert (pd2 == 0)[:, :, rows:].all() and (ds2 == 0)[:, :, rows:].all()
     dkv = torch.zeros(B, h + 1, w + 1, 2 * C, dtype=TDT[dt], device="cuda")
     dq = torch.zeros(B, h + 1, w + 1, C, dtype=TDT[dt], device="cuda")
     dvview = dkv.view(B * rows, 2 * C)[:, C:]
