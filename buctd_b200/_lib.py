@@ -99,6 +99,12 @@ class DecodeArgs(C.Structure):
                 ("idx", vp)]
 
 
+class HeadDecodeArgs(C.Structure):
+    _fields_ = [("dtype", i32), ("batch", i32), ("k", i32), ("h", i32), ("w", i32), ("c", i32), ("a_cs", i32), ("w_cs", i32),
+                ("post_process", i32), ("reserved", i32), ("feat", vp), ("weight", vp), ("bias", fp), ("center", fp), ("scale", fp),
+                ("preds", fp), ("maxvals", fp), ("idx", vp)]
+
+
 class RasterArgs(C.Structure):
     _fields_ = [("batch", i32), ("k", i32), ("kstride", i32), ("h", i32), ("w", i32), ("mode", i32),
                 ("out_channels", i32), ("c_off", i32), ("kpts", fp), ("colors", fp), ("out", fp), ("scratch", vp)]
@@ -244,7 +250,7 @@ OP_STRUCT = {OP_TAPGEMM: TapGemmArgs, OP_STEM: StemArgs, OP_FUSE: FuseArgs, OP_R
 # every symbol include/buctd_b200.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = ["buctd_abi_version", "buctd_last_error", "buctd_create", "buctd_destroy", "buctd_launch_count",
            "buctd_tapgemm", "buctd_tapgemm_chain", "buctd_stem_conv", "buctd_hr_fuse", "buctd_cond_resize", "buctd_cond_resize3", "buctd_cond_from_kpts", "buctd_coam_channel_att",
-           "buctd_coam_position_att", "buctd_da_combine", "buctd_prenet", "buctd_decode_heatmaps",
+           "buctd_coam_position_att", "buctd_da_combine", "buctd_prenet", "buctd_decode_heatmaps", "buctd_head_decode",
            "buctd_rasterize_condition", "buctd_flip_channels", "buctd_flip_merge", "buctd_joints_mse", "buctd_adam_step",
            "buctd_crop_warp", "buctd_generate_target", "buctd_pck_accuracy", "buctd_act16_to_nchw32", "buctd_nchw32_to_act16", "buctd_plan_create",
            "buctd_plan_destroy", "buctd_plan_add", "buctd_plan_add_lane", "buctd_plan_num_lanes", "buctd_plan_instantiate",
@@ -279,7 +285,7 @@ def load():
         lib.buctd_launch_count.argtypes = [vp]
         lib.buctd_create.argtypes = [C.c_int, C.POINTER(vp)]
         lib.buctd_destroy.argtypes = [vp]
-        for name in list(_IMMEDIATE.values()) + ["buctd_cond_resize3", "buctd_cond_from_kpts", "buctd_flip_channels", "buctd_flip_merge", "buctd_joints_mse", "buctd_adam_step",
+        for name in list(_IMMEDIATE.values()) + ["buctd_cond_resize3", "buctd_cond_from_kpts", "buctd_head_decode", "buctd_flip_channels", "buctd_flip_merge", "buctd_joints_mse", "buctd_adam_step",
                                                      "buctd_crop_warp", "buctd_generate_target", "buctd_pck_accuracy"] + TRAIN_EXPORTS:
             getattr(lib, name).argtypes = [vp, vp, vp]
         lib.buctd_act16_to_nchw32.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]

@@ -373,6 +373,9 @@ static int simple_call(buctd_ctx* c, const A* a, int nlaunch, F&& fn) {
 BUCTD_API int buctd_cond_resize3(buctd_ctx* c, const buctd_resize3_args* a, buctd_stream s) {
   return simple_call(c, a, 1, [&](const buctd_resize3_args& x) { return launch_resize3(x, static_cast<cudaStream_t>(s)); });
 }
+BUCTD_API int buctd_head_decode(buctd_ctx* c, const buctd_head_decode_args* a, buctd_stream s) {
+  return simple_call(c, a, 1, [&](const buctd_head_decode_args& x) { return launch_head_decode(x, static_cast<cudaStream_t>(s)); });
+}
 BUCTD_API int buctd_cond_from_kpts(buctd_ctx* c, const buctd_cond_kpts_args* a, buctd_stream s) {
   return simple_call(c, a, 1, [&](const buctd_cond_kpts_args& x) { return launch_cond_from_kpts(x, static_cast<cudaStream_t>(s)); });
 }

@@ -90,6 +90,126 @@ int launch_decode(const buctd_decode_args& a, cudaStream_t st) {
 }
 
 // =================================================================================================
+// Head + decode fused (when the heat-maps themselves are not wanted): final_layer (1x1, C -> K, bias; pose_hrnet_coam.py:565)
+// evaluated on CUDA cores straight from the act16 feature map, running (max, first index) per joint, then the quarter-pixel
+// offset from the four re-evaluated neighbours and the crop transform -- the [B][K][H][W] float32 heat-maps (470 KB per
+// crop written and read back) never exist.  One block per crop; thread = pixel (all K joints), float32 accumulation in
+// channel order.  Same decode arithmetic as decode_kernel.  The tap-GEMM head accumulates the same 16-bit products in the
+// tensor core's own order, so values agree to float32 rounding, not bit for bit (documented at the entry point).
+// =================================================================================================
+constexpr int kHdMaxK = 32, kHdMaxC = 64;
+
+template <typename T>
+__global__ void __launch_bounds__(512) head_decode_kernel(buctd_head_decode_args a) {
+  __shared__ float s_w[kHdMaxK][kHdMaxC + 1];
+  __shared__ float s_b[kHdMaxK];
+  __shared__ float s_v[16][kHdMaxK];
+  __shared__ int s_i[16][kHdMaxK];
+  __shared__ int s_best[kHdMaxK];
+  __shared__ float s_bestv[kHdMaxK];
+  const int b = blockIdx.x;
+  const int K = a.k, Cn = a.c;
+  for (int i = threadIdx.x; i < K * Cn; i += blockDim.x) {
+    const int k = i / Cn, c = i - k * Cn;
+    s_w[k][c] = T16<T>::to_f(reinterpret_cast<const T*>(a.weight)[(long long)k * a.w_cs + c]);
+  }
+  if ((int)threadIdx.x < K) s_b[threadIdx.x] = a.bias ? a.bias[threadIdx.x] : 0.f;
+  __syncthreads();
+  const T* feat = reinterpret_cast<const T*>(a.feat) + (long long)b * (a.h + 1) * (a.w + 1) * a.a_cs;
+  auto eval = [&](int py, int px, float* out) {
+    const T* row = feat + ((long long)py * (a.w + 1) + px) * a.a_cs;
+    float x[kHdMaxC];
+    for (int c0 = 0; c0 < Cn; c0 += 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>(row + c0);
+      float2 t;
+      t = T16<T>::unpack2(u.x); x[c0] = t.x; x[c0 + 1] = t.y;
+      t = T16<T>::unpack2(u.y); x[c0 + 2] = t.x; x[c0 + 3] = t.y;
+      t = T16<T>::unpack2(u.z); x[c0 + 4] = t.x; x[c0 + 5] = t.y;
+      t = T16<T>::unpack2(u.w); x[c0 + 6] = t.x; x[c0 + 7] = t.y;
+    }
+    for (int k = 0; k < K; ++k) {
+      float acc = 0.f;
+      for (int c = 0; c < Cn; ++c) acc = fmaf(x[c], s_w[k][c], acc);
+      out[k] = acc + s_b[k];
+    }
+  };
+  float best[kHdMaxK];
+  int bidx[kHdMaxK];
+  for (int k = 0; k < K; ++k) { best[k] = -INFINITY; bidx[k] = 0x7fffffff; }
+  const int hw = a.h * a.w;
+  for (int p = threadIdx.x; p < hw; p += blockDim.x) {
+    float v[kHdMaxK];
+    eval(p / a.w, p % a.w, v);
+    for (int k = 0; k < K; ++k)
+      if (v[k] > best[k]) { best[k] = v[k]; bidx[k] = p; }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = 0; k < K; ++k) {
+    float bv = best[k];
+    int bi = bidx[k];
+    for (int o = 16; o; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffff, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffff, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { s_v[warp][k] = bv; s_i[warp][k] = bi; }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < K) {
+    const int k = threadIdx.x;
+    float bv = s_v[0][k];
+    int bi = s_i[0][k];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+      if (s_v[w][k] > bv || (s_v[w][k] == bv && s_i[w][k] < bi)) { bv = s_v[w][k]; bi = s_i[w][k]; }
+    if (bi == 0x7fffffff) bi = 0;
+    s_best[k] = bi; s_bestv[k] = bv;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x >= K) return;
+  const int k = threadIdx.x;
+  const int bk = b * K + k;
+  const int bi = s_best[k];
+  const float bv = s_bestv[k];
+  float cx = (float)(bi % a.w);
+  float cy = floorf((float)bi / (float)a.w);
+  if (!(bv > 0.0f)) { cx = 0.f; cy = 0.f; }
+  if (a.idx) a.idx[bk] = bi;
+  a.maxvals[bk] = bv;
+  if (a.post_process) {
+    const int px = (int)floorf(cx + 0.5f), py = (int)floorf(cy + 0.5f);
+    if (1 < px && px < a.w - 1 && 1 < py && py < a.h - 1) {
+      float r[kHdMaxK], l[kHdMaxK], d[kHdMaxK], u[kHdMaxK];
+      eval(py, px + 1, r); eval(py, px - 1, l); eval(py + 1, px, d); eval(py - 1, px, u);
+      const float dx = r[k] - l[k], dy = d[k] - u[k];
+      cx += (dx > 0.f ? 0.25f : (dx < 0.f ? -0.25f : 0.f));
+      cy += (dy > 0.f ? 0.25f : (dy < 0.f ? -0.25f : 0.f));
+    }
+  }
+  if (a.center != nullptr && a.scale != nullptr) {
+    const double f = (double)(a.scale[2 * b] * 200.0f) / (double)a.w;
+    const double tx = (double)a.center[2 * b] - f * (double)a.w * 0.5;
+    const double ty = (double)a.center[2 * b + 1] - f * (double)a.h * 0.5;
+    a.preds[2 * bk] = (float)(f * (double)cx + tx);
+    a.preds[2 * bk + 1] = (float)(f * (double)cy + ty);
+  } else {
+    a.preds[2 * bk] = cx;
+    a.preds[2 * bk + 1] = cy;
+  }
+}
+
+int launch_head_decode(const buctd_head_decode_args& a, cudaStream_t st) {
+  BUCTD_CHECK(a.batch >= 0 && a.k > 0 && a.k <= kHdMaxK && a.c > 0 && a.c <= kHdMaxC && a.c % 8 == 0 && a.h > 0 && a.w > 0, BUCTD_ERR_INVALID,
+              "head_decode: bad shape (K <= %d, C <= %d and a multiple of 8)", kHdMaxK, kHdMaxC);
+  if (a.batch == 0) return BUCTD_OK;
+  BUCTD_CHECK(a.feat && a.weight && a.preds && a.maxvals && a.a_cs % 8 == 0 && a.w_cs >= a.c, BUCTD_ERR_INVALID, "head_decode: bad pointers / strides");
+  BUCTD_CHECK((a.center == nullptr) == (a.scale == nullptr), BUCTD_ERR_INVALID, "head_decode: center and scale go together");
+  if (a.dtype == BUCTD_F16) head_decode_kernel<__half><<<a.batch, 512, 0, st>>>(a);
+  else head_decode_kernel<__nv_bfloat16><<<a.batch, 512, 0, st>>>(a);
+  BUCTD_CUDA(cudaGetLastError());
+  return BUCTD_OK;
+}
+
+// =================================================================================================
 // rasteriser: lib/dataset/JointsDataset.py:457-543.  cv2.GaussianBlur(15x15, sigma 0 -> 2.6,
 // BORDER_REFLECT_101) of an impulse image is separable; with reflection the 1-D response of an
 // impulse at p is  g_p[x] = sum_t k[t] * [reflect101(x + t - 7) == p].  Arithmetic in float64 like

@@ -89,6 +89,7 @@ int launch_pos_att(const buctd_pos_att_args& a, cudaStream_t st);
 int launch_da_combine(const buctd_da_combine_args& a, cudaStream_t st);
 int launch_prenet(const buctd_prenet_args& a, cudaStream_t st);
 int launch_decode(const buctd_decode_args& a, cudaStream_t st);
+int launch_head_decode(const buctd_head_decode_args& a, cudaStream_t st);
 int launch_raster(const buctd_raster_args& a, cudaStream_t st, int* nlaunch);
 int launch_act16_to_nchw32(int dtype, const void* act, int B, int H, int W, int C, int cs, float* out, cudaStream_t st);
 int launch_nchw32_to_act16(int dtype, const float* x, int B, int xc, int c_off, int C, int H, int W, int cs, void* out,

@@ -102,14 +102,18 @@ template <> __device__ __forceinline__ uint32_t ex2_pack<__nv_bfloat16>(float a,
   return r;
 }
 
-#ifndef BUCTD_PA_F32_EXP
+// -DBUCTD_PA_PACKED_EXP: ex2.approx.f16x2 in the fp16 fast path (one MUFU op per two scores).  Measured on B200: 13.44 ms
+// per 64-crop forward against 13.34 ms with two float32 ex2 + a pack -- the soft-max warps are not MUFU-throughput bound
+// (DESIGN.md 3.3); off by default.
+#ifdef BUCTD_PA_PACKED_EXP
 template <typename T> constexpr bool kPackedExp = false;
 template <> constexpr bool kPackedExp<__half> = true;
 #else
 template <typename T> constexpr bool kPackedExp = false;
 #endif
 
-template <typename T>
+// TRAIN: dropout of the probabilities + the log-sum-exp output (the inference instantiation carries neither: registers)
+template <typename T, bool TRAIN>
 __global__ void __launch_bounds__(kTcThreads, 2)
 pos_att_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                   const __grid_constant__ CUtensorMap map_v, const PosAttTcParams p) {
@@ -227,8 +231,8 @@ pos_att_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const int Wp = p.W + 1;
     const bool ones = p.ones != 0;               // a free channel slot exists for the ones column
-    const uint32_t drop_thr = p.drop_p > 0.f ? drop_threshold(p.drop_p) : 0u;
-    const uint32_t drop_seed = p.drop_seed ^ ((p.drop_p > 0.f && p.seed_xor) ? *p.seed_xor : 0u);
+    const uint32_t drop_thr = (TRAIN && p.drop_p > 0.f) ? drop_threshold(p.drop_p) : 0u;
+    const uint32_t drop_seed = TRAIN ? (p.drop_seed ^ ((p.drop_p > 0.f && p.seed_xor) ? *p.seed_xor : 0u)) : 0u;
     float m_run = -INFINITY, l_run = 0.f;
     uint8_t* prow = s_p + row * 128;
     const int sw = row & 7;
@@ -313,7 +317,7 @@ pos_att_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
               const float2 f0 = T16<T>::unpack2(pk[i]), f1 = T16<T>::unpack2(pk[i + 1]);
               ls += (f0.x + f0.y) + (f1.x + f1.y);
             }
-            if (drop_thr != 0u) {           // the row sum above is over the UNDROPPED probabilities; 1 / (1 - p) goes into `inv`
+            if (TRAIN && drop_thr != 0u) {           // the row sum above is over the UNDROPPED probabilities; 1 / (1 - p) goes into `inv`
               const uint32_t kb = (uint32_t)(j * kTcTile + c0 + 2 * i);
               const uint32_t k0 = drop_hash(drop_seed, (uint32_t)b, (uint32_t)(m0 + row), kb) >= drop_thr ? 0x0000FFFFu : 0u;
               const uint32_t k1 = drop_hash(drop_seed, (uint32_t)b, (uint32_t)(m0 + row), kb + 1) >= drop_thr ? 0xFFFF0000u : 0u;
@@ -339,9 +343,6 @@ pos_att_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           for (int i = 0; i < 16; ++i) {
             const float s0 = __uint_as_float(v[2 * i]), s1 = __uint_as_float(v[2 * i + 1]);
             rawmax = fmaxf(rawmax, fmaxf(s0, s1));
-            // fp16: ONE packed MUFU op (ex2.approx.f16x2) per two scores, result already packed -- the exponent argument
-            // is in (-inf, 8] where half precision keeps exp2 within 0.3 % (P is rounded to 16 bit anyway); bf16 keeps
-            // the float32 exponentials (an 8-bit argument would cost 2 %)
             if (kPackedExp<T>) pk[i] = ex2_pack<T>(fmaf(s0, p.sc, neg_m), fmaf(s1, p.sc, neg_m));
             else pk[i] = pack_ns<T>(ex2f(fmaf(s0, p.sc, neg_m)), ex2f(fmaf(s1, p.sc, neg_m)));
           }
@@ -423,8 +424,8 @@ pos_att_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       tmem_ld_wait();
       l_run = __uint_as_float(lv);
     }
-    const float inv = (ok && !pad) ? 1.f / (l_run * (1.f - p.drop_p)) : 0.f;
-    if (p.lse2 != nullptr && ok) p.lse2[(long long)row_base + r] = pad ? 0.f : m_run + log2f(l_run);
+    const float inv = (ok && !pad) ? 1.f / (TRAIN ? l_run * (1.f - p.drop_p) : l_run) : 0.f;
+    if (TRAIN && p.lse2 != nullptr && ok) p.lse2[(long long)row_base + r] = pad ? 0.f : m_run + log2f(l_run);
     T* go = reinterpret_cast<T*>(p.o) + ((long long)row_base + r) * p.o_cs;
 #pragma unroll 1
     for (int c0 = 0; c0 < p.c; c0 += 16) {
@@ -460,8 +461,10 @@ extern "C" __attribute__((visibility("default"))) int buctd_debug_pa_cycles(unsi
 static size_t tc_smem_bytes(int nkc, int ns) { return 1024 + (size_t)(nkc + ns + 2) * kTcBlk + 2 * kTcTile * 4 + 256; }
 
 int pos_att_tc_init_device() {
-  BUCTD_CUDA(cudaFuncSetAttribute(pos_att_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(6, 4)));
-  BUCTD_CUDA(cudaFuncSetAttribute(pos_att_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(6, 4)));
+  BUCTD_CUDA(cudaFuncSetAttribute(pos_att_tc_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(6, 4)));
+  BUCTD_CUDA(cudaFuncSetAttribute(pos_att_tc_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(6, 4)));
+  BUCTD_CUDA(cudaFuncSetAttribute(pos_att_tc_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(6, 4)));
+  BUCTD_CUDA(cudaFuncSetAttribute(pos_att_tc_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(6, 4)));
   return BUCTD_OK;
 }
 
@@ -515,8 +518,11 @@ int launch_pos_att_tc(const buctd_pos_att_args& a, cudaStream_t st) {
   dim3 grid((nrows + kTcTile - 1) / kTcTile, a.batch);
   const size_t smem = tc_smem_bytes(p.nkc, p.ns);
   cudaError_t e;
-  if (a.dtype == BUCTD_F16) e = launch_pdl(pos_att_tc_kernel<__half>, grid, dim3(kTcThreads), smem, st, mq, mk, mv, p);
-  else e = launch_pdl(pos_att_tc_kernel<__nv_bfloat16>, grid, dim3(kTcThreads), smem, st, mq, mk, mv, p);
+  const bool train = a.drop_p > 0.f || a.lse2 != nullptr;
+  if (a.dtype == BUCTD_F16) e = train ? launch_pdl(pos_att_tc_kernel<__half, true>, grid, dim3(kTcThreads), smem, st, mq, mk, mv, p)
+                                      : launch_pdl(pos_att_tc_kernel<__half, false>, grid, dim3(kTcThreads), smem, st, mq, mk, mv, p);
+  else e = train ? launch_pdl(pos_att_tc_kernel<__nv_bfloat16, true>, grid, dim3(kTcThreads), smem, st, mq, mk, mv, p)
+                 : launch_pdl(pos_att_tc_kernel<__nv_bfloat16, false>, grid, dim3(kTcThreads), smem, st, mq, mk, mv, p);
   BUCTD_CHECK(e == cudaSuccess, BUCTD_ERR_CUDA, "pos_att_tc launch failed: %s", cudaGetErrorString(e));
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;

@@ -239,6 +239,19 @@ typedef struct {
 } buctd_decode_args;
 int buctd_decode_heatmaps(buctd_ctx* ctx, const buctd_decode_args* args, buctd_stream stream);
 
+/* final_layer + decode in one kernel, for callers that only want the keypoints: feat act16 [B][H+1][W+1][a_cs] (C channels,
+ * the last stage's branch-0 tensor), weight = the packed 16-bit final_layer weights [K rows][w_cs] (1x1), bias float32 [K];
+ * outputs as buctd_decode_heatmaps.  The heat-map values are the same 16-bit products accumulated in float32 in channel
+ * order instead of the tensor core's order: maxvals agree with the unfused path to float32 rounding (~1e-6 relative), the
+ * arg-max wherever the top-2 margin exceeds that.  Replaces final_layer + get_final_preds,
+ * lib/models/pose_hrnet_coam.py:565 -> lib/core/inference.py:51-87, without the heat-map round trip. */
+typedef struct {
+  int32_t dtype, batch, k, h, w, c, a_cs, w_cs, post_process, reserved;
+  const void* feat; const void* weight; const float* bias; const float* center; const float* scale;
+  float* preds; float* maxvals; int32_t* idx;
+} buctd_head_decode_args;
+int buctd_head_decode(buctd_ctx* ctx, const buctd_head_decode_args* args, buctd_stream stream);
+
 /* Condition rasteriser: keypoint proposals -> blurred impulse maps written into channels
  * [c_off, c_off+Cc) of an nchw32 tensor out[B][out_channels][H][W].
  *  mode 0 stacked: Cc = K, one channel per keypoint, each scaled to peak 255;

@@ -38,7 +38,7 @@ def test_struct_fields_match_header():
              "buctd_raster_args": L.RasterArgs, "buctd_flip_args": L.FlipArgs, "buctd_flip_merge_args": L.FlipMergeArgs,
              "buctd_joints_mse_args": L.JointsMseArgs, "buctd_adam_args": L.AdamArgs, "buctd_crop_warp_args": L.CropWarpArgs,
              "buctd_gen_target_args": L.GenTargetArgs, "buctd_pck_args": L.PckArgs, "buctd_cond_kpts_args": L.CondKptsArgs,
-             "buctd_resize3_args": L.Resize3Args,
+             "buctd_resize3_args": L.Resize3Args, "buctd_head_decode_args": L.HeadDecodeArgs,
              # the training step
              "buctd_gemm16_args": L.Gemm16Args, "buctd_wgrad_reduce_args": L.WgradReduceArgs, "buctd_bn_stats_args": L.BnStatsArgs,
              "buctd_bn_apply_args": L.BnApplyArgs, "buctd_bn_bwd_args": L.BnBwdArgs, "buctd_colsum_args": L.ColsumArgs,
