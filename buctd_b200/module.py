@@ -657,7 +657,28 @@ class PoseHighResolutionNet(nn.Module):
         condition.rasterize_condition(kp, H, W, mode, colors=colors, out=x, c_off=3)
         return self._run(x, x.shape[1], None, None)
 
-    def _run(self, x: torch.Tensor, Cx: int, kp: Optional[torch.Tensor], _stop_after: Optional[str]) -> torch.Tensor:
+    def predict_from_proposals(self, rgb: torch.Tensor, kpts: torch.Tensor, center=None, scale=None, post_process: bool = True):
+        """``forward_from_proposals`` + ``get_final_preds`` with the head fused into the decode (buctd_head_decode): the
+        [B, K, H/4, W/4] heat-maps are never written.  Returns (preds [B, K, 2], maxvals [B, K, 1]) CUDA tensors -- in image
+        coordinates when ``center`` / ``scale`` [B, 2] are given, else heat-map coordinates.  (stacked-condition CoAM, the
+        direct condition pyramid; other modes: forward_from_proposals + inference.decode_device.)"""
+        if self.training:
+            raise NotImplementedError("predict_from_proposals is an inference entry point (model.eval())")
+        arch = self.arch
+        rgb_d = rgb.cuda(non_blocking=True).contiguous()
+        kp = kpts.cuda(non_blocking=True).float().contiguous()
+        H, W = arch.img_h, arch.img_w
+        direct = (arch.use_attention and arch.cond_stacked and self.antialias and H % 16 == 0 and W % 16 == 0 and kp.shape[1] <= 32
+                  and max(len(v) for v in arch.coam.values()) <= 3 and arch.num_joints <= 32 and arch.final.k == 1
+                  and arch.final.cin <= 64 and arch.final.cin % 8 == 0)
+        if not direct or rgb_d.dtype not in (torch.float32, torch.float16) or tuple(rgb_d.shape[1:]) != (3, H, W):
+            from . import inference
+            return inference.decode_device(self.forward_from_proposals(rgb, kpts), center, scale, post_process=post_process)
+        c = torch.as_tensor(center, dtype=torch.float32).to(rgb_d.device).contiguous() if center is not None else None
+        s = torch.as_tensor(scale, dtype=torch.float32).to(rgb_d.device).contiguous() if scale is not None else None
+        return self._run(rgb_d, 3, kp, None, decode=(c, s, bool(post_process)))
+
+    def _run(self, x: torch.Tensor, Cx: int, kp: Optional[torch.Tensor], _stop_after: Optional[str], decode=None) -> torch.Tensor:
         """x: device tensor whose planes [0, 3) are the RGB crop (float32, or float16 with kp given) and, when ``kp`` is
         None, planes [3, 3 + Cc) the condition; kp: proposals for the direct condition pyramid."""
         arch = self.arch
@@ -729,6 +750,20 @@ class PoseHighResolutionNet(nn.Module):
             if _stop_after is not None:
                 return self._export(st, st["marks"][_stop_after][1], stream)
             fs: Act = st["final_src"]
+            if decode is not None:                         # head fused into the decode: no heat-maps
+                center, scale, pp = decode
+                K = arch.num_joints
+                preds = torch.empty(B, K, 2, dtype=torch.float32, device=device)
+                maxvals = torch.empty(B, K, 1, dtype=torch.float32, device=device)
+                wp, bp, e = self._wptr("final_layer")
+                hd = L.HeadDecodeArgs()
+                hd.dtype, hd.batch, hd.k, hd.h, hd.w, hd.c, hd.a_cs, hd.w_cs, hd.post_process = self._dt, B, K, fs.h, fs.w, fs.c, fs.cs, e["w_cs"], int(pp)
+                hd.feat, hd.weight, hd.bias = fs.ptr, wp, bp
+                hd.center, hd.scale = (center.data_ptr() if center is not None else None), (scale.data_ptr() if scale is not None else None)
+                hd.preds, hd.maxvals = preds.data_ptr(), maxvals.data_ptr()
+                ctx.call("buctd_head_decode", hd, stream)
+                self._keepalive = (x, stem_x, center, scale)
+                return preds, maxvals
             out = torch.empty(B, arch.num_joints, fs.h, fs.w, dtype=torch.float32, device=device)
             fa = self._tapgemm("final_layer", fs, out.data_ptr(), 0, fs.h, fs.w, out_mode=L.OUT_NCHW32)
             ctx.run(L.OP_TAPGEMM, fa, stream)

@@ -212,3 +212,32 @@ def test_predict_stream_matches_batch_calls():
             p, m = inference.decode_device(hm, c, s, post_process=True)
         assert torch.equal(torch.cat([p, m], 2).cpu(), r)
     assert list(function.predict_stream(cfg, net, [])) == []
+
+
+@pytest.mark.parametrize("name", ["coam_w32_128x96_stacked", "coam_w48_384x288_stacked"])
+def test_predict_from_proposals_fused_head_decode(name):
+    """buctd_head_decode (final_layer evaluated inside the decode, no heat-maps) against forward_from_proposals +
+    decode_device: same maxvals to float32 rounding, same arg-max wherever the heat-map's top-2 margin exceeds that, and
+    then the same quarter-pixel offsets / image coordinates."""
+    from buctd_b200 import synth
+    cfg, net = _net(name, "fp16")
+    xfull = torch.from_numpy(G.case_inputs(name))
+    B = xfull.shape[0]
+    w, h = cfg.MODEL.IMAGE_SIZE
+    kp = torch.from_numpy(synth.synth_keypoints(B, 17, w, h, 1234).astype(np.float32))
+    c, s = synth.synth_center_scale(B, w, h)
+    c, s = torch.from_numpy(c).cuda(), torch.from_numpy(s).cuda()
+    rgb = xfull[:, :3].contiguous()
+    with torch.no_grad():
+        hm = net.forward_from_proposals(rgb, kp)
+        p0, m0 = inference.decode_device(hm, c, s, post_process=True)
+        p1, m1 = net.predict_from_proposals(rgb, kp, c, s, post_process=True)
+        q0, _ = inference.decode_device(hm, None, None, post_process=False)
+        q1, _ = net.predict_from_proposals(rgb, kp, None, None, post_process=False)
+    assert (m0 - m1).abs().max().item() <= 2e-5 * max(1.0, m0.abs().max().item())
+    flat = hm.flatten(2)
+    top2 = flat.topk(2, -1).values
+    safe = (top2[..., 0] - top2[..., 1]) > 1e-4
+    assert safe.float().mean().item() > 0.9
+    assert torch.equal(q0[safe], q1[safe])
+    assert ((p0 - p1).abs().amax(-1)[safe] < 1e-3).float().mean().item() > 0.98      # (a +-0.25 px offset may flip on a near-tie of neighbours)
