@@ -185,8 +185,7 @@ def run_native(args):
         if passes > 1:
             preds, maxvals = function.iterative_refine_from_proposals(cfg, net, rgb, kp, passes, center, scale)
         else:
-            hm = net.forward_from_proposals(rgb, kp)
-            preds, maxvals = inference.decode_device(hm, center, scale, post_process=True)
+            preds, maxvals = net.predict_from_proposals(rgb, kp, center, scale, post_process=True)   # head fused into the decode
         return post(torch.cat([preds, maxvals], -1))          # [B,K,3] = 204 B per crop
 
     def barrier():
@@ -243,7 +242,7 @@ def run_native(args):
         ms_e2e = timed(e2e_loop, args.steps)
         h2d = sum(int(t.numel() * t.element_size()) for t in host[0])
         d2h = int(B * world * K * 3 * 4)
-        e2e_api = ("function.predict_stream(cfg, model, host batches) -> model.forward_from_proposals + decode_device"
+        e2e_api = ("function.predict_stream(cfg, model, host batches) -> model.predict_from_proposals"
                    if passes == 1 else "function.iterative_refine_from_proposals(cfg, model, rgb_host, kpts_host, 3, center, scale)")
 
         # ---- the reference-shaped call: model(x[B, 3+Cc, H, W] float32) with the rasterised planes ------------
@@ -305,7 +304,7 @@ def run_native(args):
         "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": label % B, "name": args.config, "global_batch": B * world, "parallelism": "crops sharded, dp%d" % world,
                    "weights": "random-init (buctd_b200.synth, seed 0)",
-                   "api": "model.forward_from_proposals(rgb[B,3,H,W], kpts[B,K,2]) + decode_device, inputs resident in HBM",
+                   "api": "model.predict_from_proposals(rgb[B,3,H,W], kpts[B,K,2], center, scale) (forward + fused head/decode), inputs resident in HBM",
                    "l2": "two resident input sets alternate (2 x %d MB > 126 MB L2); each step streams ~GBs of workspace" % (B * 3 * H * W * 4 >> 20),
                    "collective": "one NCCL all_gather of decoded [B,17,3] per step" if world > 1 else "none",
                    "host_binding": numa},

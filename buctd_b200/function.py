@@ -76,7 +76,7 @@ def predict_stream(config, model, batches, post=None):
     (lib/core/function.py:200-270) -- but what crosses PCIe per crop is the normalised RGB crop and 204 B of proposals,
     not 17 rasterised float32 planes: ``batches`` yields (rgb [B,3,H,W] float32/float16 host tensor -- pinned for an
     asynchronous copy --, kpts [B,K,>=2] float32 crop pixels, center [B,2], scale [B,2]); every batch goes through
-    ``model.forward_from_proposals`` + ``get_final_preds`` on the device and comes back as one pinned host tensor
+    ``model.predict_from_proposals`` (forward + ``get_final_preds``, head fused into the decode) and comes back as one pinned host tensor
     [B, K, 3] = (x, y, maxval).  The host -> device copy of batch i+1 runs on a side stream under the forward of batch i
     (two device slots); results are yielded one batch late so that the device -> host read never stalls the queue.
     ``post`` (optional) maps the device result [B, K, 3] before it is read back -- the multi-GPU loop passes the ONE
@@ -121,8 +121,7 @@ def predict_stream(config, model, batches, post=None):
         except StopIteration:
             nxt = None
         rgb_d, kp_d, c_d, s_d = slots[b]
-        hm = model.forward_from_proposals(rgb_d, kp_d)
-        preds, maxvals = inference.decode_device(hm, c_d, s_d, post_process=pp)
+        preds, maxvals = model.predict_from_proposals(rgb_d, kp_d, c_d, s_d, post_process=pp)
         res = torch.cat([preds, maxvals], 2)
         if post is not None:
             res = post(res)

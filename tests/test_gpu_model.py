@@ -208,8 +208,7 @@ def test_predict_stream_matches_batch_calls():
     assert len(got) == 5
     for (rgb, kp, c, s), r in zip(batches, got):
         with torch.no_grad():
-            hm = net.forward_from_proposals(rgb, kp)
-            p, m = inference.decode_device(hm, c, s, post_process=True)
+            p, m = net.predict_from_proposals(rgb, kp, c, s, post_process=True)
         assert torch.equal(torch.cat([p, m], 2).cpu(), r)
     assert list(function.predict_stream(cfg, net, [])) == []
 
