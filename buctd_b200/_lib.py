@@ -102,7 +102,7 @@ class DecodeArgs(C.Structure):
 class HeadDecodeArgs(C.Structure):
     _fields_ = [("dtype", i32), ("batch", i32), ("k", i32), ("h", i32), ("w", i32), ("c", i32), ("a_cs", i32), ("w_cs", i32),
                 ("post_process", i32), ("reserved", i32), ("feat", vp), ("weight", vp), ("bias", fp), ("center", fp), ("scale", fp),
-                ("preds", fp), ("maxvals", fp), ("idx", vp)]
+                ("preds", fp), ("maxvals", fp), ("idx", vp), ("scratch", vp)]
 
 
 class RasterArgs(C.Structure):

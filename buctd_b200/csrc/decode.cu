@@ -93,60 +93,63 @@ int launch_decode(const buctd_decode_args& a, cudaStream_t st) {
 // Head + decode fused (when the heat-maps themselves are not wanted): final_layer (1x1, C -> K, bias; pose_hrnet_coam.py:565)
 // evaluated on CUDA cores straight from the act16 feature map, running (max, first index) per joint, then the quarter-pixel
 // offset from the four re-evaluated neighbours and the crop transform -- the [B][K][H][W] float32 heat-maps (470 KB per
-// crop written and read back) never exist.  One block per crop; thread = pixel (all K joints), float32 accumulation in
-// channel order.  Same decode arithmetic as decode_kernel.  The tap-GEMM head accumulates the same 16-bit products in the
+// crop written and read back) never exist.  Two launches: a scan (thread = pixel, all K joints, float32 accumulation in
+// channel order, per-block partial arg-max) and a finish (thread = joint).  Same decode arithmetic as decode_kernel.  The tap-GEMM head accumulates the same 16-bit products in the
 // tensor core's own order, so values agree to float32 rounding, not bit for bit (documented at the entry point).
 // =================================================================================================
-constexpr int kHdMaxK = 32, kHdMaxC = 64;
+constexpr int kHdMaxK = 32;
+constexpr int kHdPix = 256;              // pixels per block of the scan kernel (one per thread)
 
-template <typename T>
-__global__ void __launch_bounds__(512) head_decode_kernel(buctd_head_decode_args a) {
-  __shared__ float s_w[kHdMaxK][kHdMaxC + 1];
+template <typename T, int CN>
+__device__ __forceinline__ void hd_load_row(const T* row, float (&x)[CN]) {
+#pragma unroll
+  for (int c0 = 0; c0 < CN; c0 += 8) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + c0);
+    float2 t;
+    t = T16<T>::unpack2(u.x); x[c0] = t.x; x[c0 + 1] = t.y;
+    t = T16<T>::unpack2(u.y); x[c0 + 2] = t.x; x[c0 + 3] = t.y;
+    t = T16<T>::unpack2(u.z); x[c0 + 4] = t.x; x[c0 + 5] = t.y;
+    t = T16<T>::unpack2(u.w); x[c0 + 6] = t.x; x[c0 + 7] = t.y;
+  }
+}
+template <int CN>
+__device__ __forceinline__ float hd_dot(const float (&x)[CN], const float* w, float bias) {
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < CN; c += 4) {
+    const float4 w4 = *reinterpret_cast<const float4*>(w + c);
+    acc = fmaf(x[c], w4.x, acc); acc = fmaf(x[c + 1], w4.y, acc);
+    acc = fmaf(x[c + 2], w4.z, acc); acc = fmaf(x[c + 3], w4.w, acc);
+  }
+  return acc + bias;
+}
+
+// pass 1: grid (ceil(HW / 256), B); thread = pixel; per joint the block's (max, first index) -> scratch[b][blk][k]
+template <typename T, int CN>
+__global__ void __launch_bounds__(kHdPix) head_scan_kernel(buctd_head_decode_args a) {
+  __shared__ __align__(16) float s_w[kHdMaxK][CN];
   __shared__ float s_b[kHdMaxK];
-  __shared__ float s_v[16][kHdMaxK];
-  __shared__ int s_i[16][kHdMaxK];
-  __shared__ int s_best[kHdMaxK];
-  __shared__ float s_bestv[kHdMaxK];
-  const int b = blockIdx.x;
-  const int K = a.k, Cn = a.c;
-  for (int i = threadIdx.x; i < K * Cn; i += blockDim.x) {
-    const int k = i / Cn, c = i - k * Cn;
+  __shared__ float s_v[kHdPix / 32][kHdMaxK];
+  __shared__ int s_i[kHdPix / 32][kHdMaxK];
+  const int b = blockIdx.y, K = a.k;
+  for (int i = threadIdx.x; i < K * CN; i += blockDim.x) {
+    const int k = i / CN, c = i - k * CN;
     s_w[k][c] = T16<T>::to_f(reinterpret_cast<const T*>(a.weight)[(long long)k * a.w_cs + c]);
   }
   if ((int)threadIdx.x < K) s_b[threadIdx.x] = a.bias ? a.bias[threadIdx.x] : 0.f;
   __syncthreads();
-  const T* feat = reinterpret_cast<const T*>(a.feat) + (long long)b * (a.h + 1) * (a.w + 1) * a.a_cs;
-  auto eval = [&](int py, int px, float* out) {
-    const T* row = feat + ((long long)py * (a.w + 1) + px) * a.a_cs;
-    float x[kHdMaxC];
-    for (int c0 = 0; c0 < Cn; c0 += 8) {
-      const uint4 u = *reinterpret_cast<const uint4*>(row + c0);
-      float2 t;
-      t = T16<T>::unpack2(u.x); x[c0] = t.x; x[c0 + 1] = t.y;
-      t = T16<T>::unpack2(u.y); x[c0 + 2] = t.x; x[c0 + 3] = t.y;
-      t = T16<T>::unpack2(u.z); x[c0 + 4] = t.x; x[c0 + 5] = t.y;
-      t = T16<T>::unpack2(u.w); x[c0 + 6] = t.x; x[c0 + 7] = t.y;
-    }
-    for (int k = 0; k < K; ++k) {
-      float acc = 0.f;
-      for (int c = 0; c < Cn; ++c) acc = fmaf(x[c], s_w[k][c], acc);
-      out[k] = acc + s_b[k];
-    }
-  };
-  float best[kHdMaxK];
-  int bidx[kHdMaxK];
-  for (int k = 0; k < K; ++k) { best[k] = -INFINITY; bidx[k] = 0x7fffffff; }
   const int hw = a.h * a.w;
-  for (int p = threadIdx.x; p < hw; p += blockDim.x) {
-    float v[kHdMaxK];
-    eval(p / a.w, p % a.w, v);
-    for (int k = 0; k < K; ++k)
-      if (v[k] > best[k]) { best[k] = v[k]; bidx[k] = p; }
+  const int p = blockIdx.x * kHdPix + threadIdx.x;
+  const bool live = p < hw;
+  float x[CN];
+  if (live) {
+    const int py = p / a.w, px = p - py * a.w;
+    hd_load_row<T, CN>(reinterpret_cast<const T*>(a.feat) + (((long long)b * (a.h + 1) + py) * (a.w + 1) + px) * a.a_cs, x);
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int k = 0; k < K; ++k) {
-    float bv = best[k];
-    int bi = bidx[k];
+    float bv = live ? hd_dot<CN>(x, s_w[k], s_b[k]) : -INFINITY;
+    int bi = live ? p : 0x7fffffff;
     for (int o = 16; o; o >>= 1) {
       const float ov = __shfl_xor_sync(0xffffffff, bv, o);
       const int oi = __shfl_xor_sync(0xffffffff, bi, o);
@@ -159,17 +162,28 @@ __global__ void __launch_bounds__(512) head_decode_kernel(buctd_head_decode_args
     const int k = threadIdx.x;
     float bv = s_v[0][k];
     int bi = s_i[0][k];
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+    for (int w = 1; w < kHdPix / 32; ++w)
       if (s_v[w][k] > bv || (s_v[w][k] == bv && s_i[w][k] < bi)) { bv = s_v[w][k]; bi = s_i[w][k]; }
-    if (bi == 0x7fffffff) bi = 0;
-    s_best[k] = bi; s_bestv[k] = bv;
+    float2* out = reinterpret_cast<float2*>(a.scratch) + ((long long)b * gridDim.x + blockIdx.x) * K + k;
+    *out = make_float2(bv, __int_as_float(bi));
   }
-  __syncthreads();
-  if ((int)threadIdx.x >= K) return;
-  const int k = threadIdx.x;
-  const int bk = b * K + k;
-  const int bi = s_best[k];
-  const float bv = s_bestv[k];
+}
+
+// pass 2: one block per crop, thread = joint: reduce the block partials in order, re-evaluate the four neighbours, decode
+template <typename T, int CN>
+__global__ void __launch_bounds__(32) head_finish_kernel(buctd_head_decode_args a, int nblk) {
+  const int b = blockIdx.x, k = threadIdx.x;
+  if (k >= a.k) return;
+  const float2* part = reinterpret_cast<const float2*>(a.scratch) + (long long)b * nblk * a.k + k;
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int j = 0; j < nblk; ++j) {
+    const float2 v = part[(long long)j * a.k];
+    const int oi = __float_as_int(v.y);
+    if (v.x > bv || (v.x == bv && oi < bi)) { bv = v.x; bi = oi; }
+  }
+  if (bi == 0x7fffffff) bi = 0;
+  const int bk = b * a.k + k;
   float cx = (float)(bi % a.w);
   float cy = floorf((float)bi / (float)a.w);
   if (!(bv > 0.0f)) { cx = 0.f; cy = 0.f; }
@@ -178,9 +192,21 @@ __global__ void __launch_bounds__(512) head_decode_kernel(buctd_head_decode_args
   if (a.post_process) {
     const int px = (int)floorf(cx + 0.5f), py = (int)floorf(cy + 0.5f);
     if (1 < px && px < a.w - 1 && 1 < py && py < a.h - 1) {
-      float r[kHdMaxK], l[kHdMaxK], d[kHdMaxK], u[kHdMaxK];
-      eval(py, px + 1, r); eval(py, px - 1, l); eval(py + 1, px, d); eval(py - 1, px, u);
-      const float dx = r[k] - l[k], dy = d[k] - u[k];
+      float w[CN];
+#pragma unroll
+      for (int c = 0; c < CN; ++c) w[c] = T16<T>::to_f(reinterpret_cast<const T*>(a.weight)[(long long)k * a.w_cs + c]);
+      const float bias = a.bias ? a.bias[k] : 0.f;
+      const T* feat = reinterpret_cast<const T*>(a.feat) + (long long)b * (a.h + 1) * (a.w + 1) * a.a_cs;
+      auto eval = [&](int yy, int xx) {
+        float x[CN];
+        hd_load_row<T, CN>(feat + ((long long)yy * (a.w + 1) + xx) * a.a_cs, x);
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < CN; ++c) acc = fmaf(x[c], w[c], acc);
+        return acc + bias;
+      };
+      const float dx = eval(py, px + 1) - eval(py, px - 1);
+      const float dy = eval(py + 1, px) - eval(py - 1, px);
       cx += (dx > 0.f ? 0.25f : (dx < 0.f ? -0.25f : 0.f));
       cy += (dy > 0.f ? 0.25f : (dy < 0.f ? -0.25f : 0.f));
     }
@@ -197,14 +223,26 @@ __global__ void __launch_bounds__(512) head_decode_kernel(buctd_head_decode_args
   }
 }
 
+template <typename T, int CN>
+static void head_decode_launch(const buctd_head_decode_args& a, cudaStream_t st) {
+  const int nblk = ceil_div(a.h * a.w, kHdPix);
+  head_scan_kernel<T, CN><<<dim3(nblk, a.batch), kHdPix, 0, st>>>(a);
+  head_finish_kernel<T, CN><<<a.batch, 32, 0, st>>>(a, nblk);
+}
+
 int launch_head_decode(const buctd_head_decode_args& a, cudaStream_t st) {
-  BUCTD_CHECK(a.batch >= 0 && a.k > 0 && a.k <= kHdMaxK && a.c > 0 && a.c <= kHdMaxC && a.c % 8 == 0 && a.h > 0 && a.w > 0, BUCTD_ERR_INVALID,
-              "head_decode: bad shape (K <= %d, C <= %d and a multiple of 8)", kHdMaxK, kHdMaxC);
+  BUCTD_CHECK(a.batch >= 0 && a.k > 0 && a.k <= kHdMaxK && (a.c == 32 || a.c == 48 || a.c == 64) && a.h > 0 && a.w > 0, BUCTD_ERR_INVALID,
+              "head_decode: K <= %d and C in {32, 48, 64} (got K %d, C %d)", kHdMaxK, a.k, a.c);
   if (a.batch == 0) return BUCTD_OK;
-  BUCTD_CHECK(a.feat && a.weight && a.preds && a.maxvals && a.a_cs % 8 == 0 && a.w_cs >= a.c, BUCTD_ERR_INVALID, "head_decode: bad pointers / strides");
+  BUCTD_CHECK(a.feat && a.weight && a.preds && a.maxvals && a.scratch && a.a_cs % 8 == 0 && a.w_cs >= a.c, BUCTD_ERR_INVALID,
+              "head_decode: bad pointers / strides");
   BUCTD_CHECK((a.center == nullptr) == (a.scale == nullptr), BUCTD_ERR_INVALID, "head_decode: center and scale go together");
-  if (a.dtype == BUCTD_F16) head_decode_kernel<__half><<<a.batch, 512, 0, st>>>(a);
-  else head_decode_kernel<__nv_bfloat16><<<a.batch, 512, 0, st>>>(a);
+  const bool h16 = a.dtype == BUCTD_F16;
+  switch (a.c) {
+    case 32: if (h16) head_decode_launch<__half, 32>(a, st); else head_decode_launch<__nv_bfloat16, 32>(a, st); break;
+    case 48: if (h16) head_decode_launch<__half, 48>(a, st); else head_decode_launch<__nv_bfloat16, 48>(a, st); break;
+    default: if (h16) head_decode_launch<__half, 64>(a, st); else head_decode_launch<__nv_bfloat16, 64>(a, st); break;
+  }
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;
 }

@@ -337,14 +337,40 @@ class PoseHighResolutionNet(nn.Module):
             else:
                 emit(L.OP_TAPGEMM, spec, cv.w)
 
+        # A chain whose live set (block input, intermediate, output: 3 tensors) exceeds the L2 streams every layer
+        # through HBM (branch 0 at B = 64: 3 x 43.5 MB against 126 MB, 530 MB of DRAM traffic per launch).  Crops are
+        # independent, so such a chain is cut into crop ranges that fit: same launches, same bits, L2-resident layers.
+        split_env = int(os.environ.get("BUCTD_CHAIN_SPLIT", "0"))
+        l2_budget = int(float(os.environ.get("BUCTD_CHAIN_L2_MB", "90")) * 2 ** 20)
+
+        def sub(a: Optional[Act], b0: int, nb_: int) -> Optional[Act]:
+            if a is None:
+                return None
+            return Act(a.ptr + b0 * (a.h + 1) * (a.w + 1) * a.cs * 2, nb_, a.h, a.w, a.c, a.cs)
+
         def flush_chain(label):
             items, collect[0] = collect[0], None
             for lo in range(0, len(items), L.MAX_CHAIN):
                 part = items[lo:lo + L.MAX_CHAIN]
                 if len(part) == 1:
                     emit(L.OP_TAPGEMM, part[0][0], part[0][1])
-                else:
+                    continue
+                src0 = part[0][0][2]
+                live = 3 * src0.b * (src0.h + 1) * (src0.w + 1) * src0.cs * 2
+                nsp = split_env if split_env > 0 else max(1, -(-live // l2_budget))
+                nsp = max(1, min(nsp, src0.b))
+                if nsp == 1:
                     emit(L.OP_CHAIN, ("chain", [sp for sp, _ in part], [lb for _, lb in part]), label)
+                    continue
+                bounds = [src0.b * i // nsp for i in range(nsp + 1)]
+                for i in range(nsp):
+                    b0, nb_ = bounds[i], bounds[i + 1] - bounds[i]
+                    sps = []
+                    for (tag, key, src, dst, kw), _ in part:
+                        kw2 = dict(kw)
+                        kw2["residual"] = sub(kw.get("residual"), b0, nb_)
+                        sps.append((tag, key, sub(src, b0, nb_), sub(dst, b0, nb_), kw2))
+                    emit(L.OP_CHAIN, ("chain", sps, [lb for _, lb in part]), label + (":crops%d" % i))
 
         # ---- stem ---------------------------------------------------------------------------
         s1 = act("stem1", arch.img_h // 2, arch.img_w // 2, 64)
@@ -670,7 +696,7 @@ class PoseHighResolutionNet(nn.Module):
         H, W = arch.img_h, arch.img_w
         direct = (arch.use_attention and arch.cond_stacked and self.antialias and H % 16 == 0 and W % 16 == 0 and kp.shape[1] <= 32
                   and max(len(v) for v in arch.coam.values()) <= 3 and arch.num_joints <= 32 and arch.final.k == 1
-                  and arch.final.cin <= 64 and arch.final.cin % 8 == 0)
+                  and arch.final.cin in (32, 48, 64))
         if not direct or rgb_d.dtype not in (torch.float32, torch.float16) or tuple(rgb_d.shape[1:]) != (3, H, W):
             from . import inference
             return inference.decode_device(self.forward_from_proposals(rgb, kpts), center, scale, post_process=post_process)
@@ -761,8 +787,10 @@ class PoseHighResolutionNet(nn.Module):
                 hd.feat, hd.weight, hd.bias = fs.ptr, wp, bp
                 hd.center, hd.scale = (center.data_ptr() if center is not None else None), (scale.data_ptr() if scale is not None else None)
                 hd.preds, hd.maxvals = preds.data_ptr(), maxvals.data_ptr()
+                scratch = torch.empty(B * ((fs.h * fs.w + 255) // 256) * K * 2, dtype=torch.float32, device=device)
+                hd.scratch = scratch.data_ptr()
                 ctx.call("buctd_head_decode", hd, stream)
-                self._keepalive = (x, stem_x, center, scale)
+                self._keepalive = (x, stem_x, center, scale, scratch)
                 return preds, maxvals
             out = torch.empty(B, arch.num_joints, fs.h, fs.w, dtype=torch.float32, device=device)
             fa = self._tapgemm("final_layer", fs, out.data_ptr(), 0, fs.h, fs.w, out_mode=L.OUT_NCHW32)

@@ -249,6 +249,7 @@ typedef struct {
   int32_t dtype, batch, k, h, w, c, a_cs, w_cs, post_process, reserved;
   const void* feat; const void* weight; const float* bias; const float* center; const float* scale;
   float* preds; float* maxvals; int32_t* idx;
+  void* scratch;        /* B * ceil(H W / 256) * K * 8 bytes */
 } buctd_head_decode_args;
 int buctd_head_decode(buctd_ctx* ctx, const buctd_head_decode_args* args, buctd_stream stream);
 
