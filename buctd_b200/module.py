@@ -337,10 +337,12 @@ class PoseHighResolutionNet(nn.Module):
             else:
                 emit(L.OP_TAPGEMM, spec, cv.w)
 
-        # A chain whose live set (block input, intermediate, output: 3 tensors) exceeds the L2 streams every layer
-        # through HBM (branch 0 at B = 64: 3 x 43.5 MB against 126 MB, 530 MB of DRAM traffic per launch).  Crops are
-        # independent, so such a chain is cut into crop ranges that fit: same launches, same bits, L2-resident layers.
-        split_env = int(os.environ.get("BUCTD_CHAIN_SPLIT", "0"))
+        # BUCTD_CHAIN_SPLIT=n cuts every chain into n crop ranges (0: as many as make the live set -- block input,
+        # intermediate, output -- fit BUCTD_CHAIN_L2_MB of L2).  Crops are independent, so the result is bit-identical.
+        # MEASURED (B = 64, round 2): branch 0 streams 530 MB of DRAM per launch unsplit (3 x 43.5 MB live against 126 MB),
+        # but two L2-resident halves take 358 us against 262 us unsplit -- the launch is bound by its pipeline ramp and the
+        # per-item dataflow, not by DRAM; whole forward 14.15 ms (auto) / 16.3 ms (2 everywhere) against 13.37.  Default 1.
+        split_env = int(os.environ.get("BUCTD_CHAIN_SPLIT", "1"))
         l2_budget = int(float(os.environ.get("BUCTD_CHAIN_L2_MB", "90")) * 2 ** 20)
 
         def sub(a: Optional[Act], b0: int, nb_: int) -> Optional[Act]:
