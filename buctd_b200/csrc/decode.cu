@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(256) raster_sum_kernel(buctd_raster_args a, un
 // resize to the three CoAM scales (ops.cu: triangle filter of 2S taps starting at S*o - S/2, weight 1 - |t - S + 0.5| / S,
 // normalised over the taps inside the image).  Both are separable, so per keypoint and scale there are two short
 // vectors ry[Y] = sum_y wY[Y][y] gy[y], rx[X] = sum_x wX[X][x] gx[x] (float64) and
-// out[b][Y][X][k] = (255 / (max gy max gx)) ry[Y] rx[X].  Grid (8 row slices, 3 scales, B); every CTA recomputes the
+// out[b][Y][X][k] = (255 / (max gy max gx)) ry[Y] rx[X].  Grid (2 row slices, 3 scales, B); every CTA recomputes the
 // vectors of its scale (a few thousand FMAs) and writes its slice of rows with 16-byte stores.
 // lib/dataset/JointsDataset.py:457-498 + lib/models/pose_hrnet_coam.py:750-757.
 // =================================================================================================
@@ -482,7 +482,7 @@ int launch_cond_from_kpts(const buctd_cond_kpts_args& a, cudaStream_t st) {
     BUCTD_CHECK(a.out_cs[i] % 8 == 0 && a.k <= a.out_cs[i] && (((uintptr_t)a.out[i]) & 15) == 0, BUCTD_ERR_INVALID,
                 "cond_from_kpts: K %d vs out_cs[%d] %d / alignment", a.k, i, a.out_cs[i]);
   if (a.batch == 0) return BUCTD_OK;
-  dim3 grid(8, 3, a.batch);
+  dim3 grid(2, 3, a.batch);      // every CTA recomputes the separable vectors of its (crop, scale): few row slices
   if (a.dtype == BUCTD_F16) cond_from_kpts_kernel<__half><<<grid, 256, 0, st>>>(a);
   else cond_from_kpts_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a);
   BUCTD_CUDA(cudaGetLastError());

@@ -94,33 +94,41 @@ template <typename T>
 __global__ void __launch_bounds__(256) fuse_kernel(buctd_fuse_args a) {
   pdl_launch_dependents();
   pdl_wait();
-  const int cv = a.c / 8;
-  const int Hp = a.h + 1, Wp = a.w + 1;
-  const long long total = (long long)a.batch * Hp * Wp * cv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % cv);
-    const long long r = i / cv;
-    const int x = (int)(r % Wp);
-    const long long ry = r / Wp;
-    const int y = (int)(ry % Hp);
-    const int b = (int)(ry / Hp);
+  // 32-bit index math (the launcher checks B (H+1) (W+1) C/8 < 2^31); one (row, 8-channel group) per thread and step
+  const unsigned cv = (unsigned)a.c / 8;
+  const unsigned Hp = a.h + 1, Wp = a.w + 1;
+  const unsigned total = (unsigned)a.batch * Hp * Wp * cv;
+  const int nt = a.nterms;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned r = i / cv;
+    const unsigned c8 = i - r * cv;
+    const unsigned ry = r / Wp;
+    const unsigned x = r - ry * Wp;
+    const unsigned b = ry / Hp;
+    const unsigned y = ry - b * Hp;
     uint4 u = make_uint4(0, 0, 0, 0);
-    if (x < a.w && y < a.h) {
+    if (x < (unsigned)a.w && y < (unsigned)a.h) {
+      uint4 t[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {                 // all loads first: the terms' latencies overlap
+        if (j < nt) {
+          const int sh = a.term_shift[j];
+          const unsigned sw = ((unsigned)a.w >> sh) + 1, shh = ((unsigned)a.h >> sh) + 1;
+          const size_t sr = (size_t)(b * shh + (y >> sh)) * sw + (x >> sh);
+          t[j] = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.term[j]) + sr * a.term_cs[j] + c8 * 8);
+        }
+      }
       float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (j >= a.nterms) break;
-        const int sh = a.term_shift[j];
-        const int sw = (a.w >> sh) + 1, shh = (a.h >> sh) + 1;
-        const long long sr = ((long long)b * shh + (y >> sh)) * sw + (x >> sh);
-        const uint4 t = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.term[j]) + sr * a.term_cs[j] + c8 * 8);
-        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+        if (j < nt) {
+          const uint32_t w[4] = {t[j].x, t[j].y, t[j].z, t[j].w};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float2 f = T16<T>::unpack2(w[q]);
-          acc[2 * q] += f.x;
-          acc[2 * q + 1] += f.y;
+          for (int q = 0; q < 4; ++q) {
+            float2 f = T16<T>::unpack2(w[q]);
+            acc[2 * q] += f.x;
+            acc[2 * q + 1] += f.y;
+          }
         }
       }
       if (a.relu) {
@@ -130,7 +138,7 @@ __global__ void __launch_bounds__(256) fuse_kernel(buctd_fuse_args a) {
       u.x = T16<T>::pack2(acc[0], acc[1]); u.y = T16<T>::pack2(acc[2], acc[3]);
       u.z = T16<T>::pack2(acc[4], acc[5]); u.w = T16<T>::pack2(acc[6], acc[7]);
     }
-    *reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.out) + r * a.out_cs + c8 * 8) = u;
+    *reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.out) + (size_t)r * a.out_cs + c8 * 8) = u;
   }
 }
 
@@ -143,6 +151,7 @@ int launch_fuse(const buctd_fuse_args& a, cudaStream_t st) {
                 "fuse: %dx%d not divisible by 2^%d", a.h, a.w, a.term_shift[j]);
   }
   const long long total = (long long)a.batch * (a.h + 1) * (a.w + 1) * (a.c / 8);
+  BUCTD_CHECK(total < (1ll << 31), BUCTD_ERR_INVALID, "fuse: tensor too large for 32-bit indexing (%lld groups)", total);
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   if (a.dtype == BUCTD_F16) launch_pdl(fuse_kernel<__half>, dim3(blocks), dim3(256), 0, st, a);
   else launch_pdl(fuse_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, a);
@@ -721,8 +730,66 @@ __global__ void __launch_bounds__(256) da_combine_kernel(buctd_da_combine_args a
   }
 }
 
+// Vector variant (C, channel strides multiples of 8): tile = 64 pixels x 32 channels; the planar c_out tile goes through
+// shared memory, x / p_out / out move as 16-byte groups of 8 channels.
+template <typename T>
+__global__ void __launch_bounds__(256) da_combine_vec_kernel(buctd_da_combine_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float s_c[32][65];
+  const int b = blockIdx.z;
+  const int hw = a.h * a.w;
+  const int p0 = blockIdx.x * 64, c0 = blockIdx.y * 32;
+  const int ps = a.c_stride > 0 ? a.c_stride : hw;
+  const T* cout = reinterpret_cast<const T*>(a.c_out) + (size_t)b * a.c * ps;
+  for (int i = threadIdx.x; i < 32 * 64; i += 256) {
+    const int cc = i >> 6, pp = i & 63;
+    const int c = c0 + cc, p = p0 + pp;
+    s_c[cc][pp] = (c < a.c && p < hw) ? T16<T>::to_f(cout[(size_t)c * ps + p]) : 0.f;
+  }
+  __syncthreads();
+  const int pp = threadIdx.x >> 2, cg = threadIdx.x & 3;
+  const int p = p0 + pp, c = c0 + cg * 8;
+  if (p >= hw || c >= a.c) return;
+  const int py = p / a.w, px = p - py * a.w;
+  const size_t r = ((size_t)b * (a.h + 1) + py) * (a.w + 1) + px;
+  const uint4 ux = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.x) + r * a.x_cs + c);
+  const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w};
+  float v[8];
+  if (a.channel_only) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = T16<T>::unpack2(wx[k]);
+      v[2 * k] = f.x * s_c[cg * 8 + 2 * k][pp];
+      v[2 * k + 1] = f.y * s_c[cg * 8 + 2 * k + 1][pp];
+    }
+  } else {
+    const uint4 up = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.p_out) + r * a.p_cs + c);
+    const uint32_t wp[4] = {up.x, up.y, up.z, up.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = T16<T>::unpack2(wx[k]), g = T16<T>::unpack2(wp[k]);
+      v[2 * k] = f.x + (g.x + s_c[cg * 8 + 2 * k][pp]);
+      v[2 * k + 1] = f.y + (g.y + s_c[cg * 8 + 2 * k + 1][pp]);
+    }
+  }
+  uint4 uo;
+  uo.x = T16<T>::pack2(v[0], v[1]); uo.y = T16<T>::pack2(v[2], v[3]);
+  uo.z = T16<T>::pack2(v[4], v[5]); uo.w = T16<T>::pack2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.out) + r * a.out_cs + c) = uo;
+}
+
 int launch_da_combine(const buctd_da_combine_args& a, cudaStream_t st) {
   BUCTD_CHECK(a.x && a.c_out && a.out && (a.channel_only || a.p_out), BUCTD_ERR_INVALID, "da_combine: null pointer");
+  const bool vec = a.c % 8 == 0 && a.x_cs % 8 == 0 && a.out_cs % 8 == 0 && (a.channel_only || a.p_cs % 8 == 0) &&
+                   ((((uintptr_t)a.x | (uintptr_t)a.out | (uintptr_t)a.p_out) & 15) == 0);
+  if (vec) {
+    dim3 grid(ceil_div(a.h * a.w, 64), ceil_div(a.c, 32), a.batch);
+    if (a.dtype == BUCTD_F16) launch_pdl(da_combine_vec_kernel<__half>, grid, dim3(256), 0, st, a);
+    else launch_pdl(da_combine_vec_kernel<__nv_bfloat16>, grid, dim3(256), 0, st, a);
+    BUCTD_CUDA(cudaGetLastError());
+    return BUCTD_OK;
+  }
   dim3 grid(ceil_div(a.h * a.w, 32), ceil_div(a.c, 32), a.batch);
   if (a.dtype == BUCTD_F16) launch_pdl(da_combine_kernel<__half>, grid, dim3(256), 0, st, a);
   else launch_pdl(da_combine_kernel<__nv_bfloat16>, grid, dim3(256), 0, st, a);

@@ -253,7 +253,9 @@ def test_channel_attention(dt, C, h, w):
 @pytest.mark.parametrize("C,h,w", [(48, 24, 18), (96, 12, 9), (192, 7, 5), (32, 16, 12), (64, 8, 6), (128, 4, 3),
                                    # every head dim runs on tcgen05: channel blocks of 64 (1..6), several key tiles, with and
                                    # without the ones column (C % 64 != 0 and <= 2 blocks)
-                                   (96, 48, 36), (192, 24, 18), (128, 16, 12), (256, 4, 3), (384, 12, 9), (16, 9, 7), (112, 20, 13)])
+                                   (96, 48, 36), (192, 24, 18), (128, 16, 12), (256, 4, 3), (384, 12, 9), (16, 9, 7), (112, 20, 13),
+                                   # two query tiles per CTA (C <= 64, >= 2 tiles): odd tile count, no ones column (C = 64)
+                                   (48, 28, 20), (64, 24, 18), (48, 48, 36)])
 def test_position_attention(dt, C, h, w):
     B = 2
     q = q16(_rand(B, C, h, w, seed=27, scale=1.5), dt)

@@ -22,8 +22,11 @@ for scale in (1.0, 6.0):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); ctx().run(L.OP_POS_ATT, a, stream()); e1.record(); torch.cuda.synchronize()
     buf = (ctypes.c_ulonglong * 16)()
+    if not hasattr(lib, "buctd_debug_pa_cycles"):            # product build: time only
+        print("q scale %.1f: %.1f us" % (scale, e0.elapsed_time(e1) * 1e3))
+        continue
     lib.buctd_debug_pa_cycles(buf)
     v = list(buf)
     nt = max(v[11], 1)
-    print("q scale %.1f: %.1f us | per tile: MMA thread total %d (wait K %d, wait P %d, wait V %d) | softmax total %d (bar %d, wait S %d, wait O %d, main pass %d, wait V %d), redo %d of %d tiles"
-          % (scale, e0.elapsed_time(e1) * 1e3, v[0] // nt, v[1] // nt, v[2] // nt, v[3] // nt, v[4] // nt, v[5] // nt, v[6] // nt, v[7] // nt, v[8] // nt, v[9] // nt, v[10], nt))
+    print("q scale %.1f: %.1f us | per tile: MMA thread total %d (wait K %d, wait P %d, wait V %d) | softmax total %d (bar %d, wait S %d, wait O %d, main pass %d [tmem ld wait %d, ld issue %d, chunks %d], wait V %d), redo %d of %d tiles"
+          % (scale, e0.elapsed_time(e1) * 1e3, v[0] // nt, v[1] // nt, v[2] // nt, v[3] // nt, v[4] // nt, v[5] // nt, v[6] // nt, v[7] // nt, v[8] // nt, v[12] // nt, v[13] // nt, v[14] // nt, v[9] // nt, v[10], nt))

@@ -25,13 +25,17 @@ net.load_state_dict(synth.synth_state_dict(net.arch, 0), strict=True)
 net = net.cuda().eval()
 dev = torch.device("cuda", 0)
 if args.variant == "coam":
-    x, c, s = make_inputs(torch, cfg, args.batch, dev, 1234)
+    rgb, kp, c, s = make_inputs(torch, cfg, args.batch, dev, 1234)
+    with torch.no_grad():
+        for _ in range(args.iters):
+            preds, maxvals = net.predict_from_proposals(rgb, kp, c, s, post_process=True)     # the bench step
+    torch.cuda.synchronize()
+    print("done", tuple(preds.shape))
 else:
     x = torch.randn(args.batch, 6, 384, 288, device=dev)
-    c = s = None
-with torch.no_grad():
-    for _ in range(args.iters):
-        hm = net(x)
-        inference.decode_device(hm, c, s, post_process=True)
-torch.cuda.synchronize()
-print("done", tuple(hm.shape))
+    with torch.no_grad():
+        for _ in range(args.iters):
+            hm = net(x)
+            inference.decode_device(hm, None, None, post_process=True)
+    torch.cuda.synchronize()
+    print("done", tuple(hm.shape))
