@@ -120,6 +120,7 @@ struct PaGroup {
   float* s_bias;                       // [2][128] additive key mask (double buffered)
   uint32_t* s_mask;                    // [2][4]
   uint64_t *s_full, *p_full, *o_done;  // this group's S-ready / P-ready / PV-done barriers
+  uint64_t* o_half;                    // first half of the PV MMAs done: keys 0..63 of the P tile may be overwritten
   uint64_t* kv_full;                   // the K/V ring
   uint8_t* s_kv;
   uint32_t tm_s, tm_o;                 // this group's S and O accumulators
@@ -147,8 +148,9 @@ __device__ __forceinline__ void pa_softmax_role(const PosAttTcParams& p, const P
   const uint32_t drop_thr = (TRAIN && p.drop_p > 0.f) ? drop_threshold(p.drop_p) : 0u;
   const uint32_t drop_seed = TRAIN ? (p.drop_seed ^ ((p.drop_p > 0.f && p.seed_xor) ? *p.seed_xor : 0u)) : 0u;
   float m_run = -INFINITY, l_run = 0.f;
-  uint8_t* const s_p = g.s_p; float* const s_bias = g.s_bias; uint32_t* const s_mask = g.s_mask;
+  uint8_t* const s_p = g.s_p; float* const s_bias = g.s_bias;
   uint64_t* const s_full = g.s_full; uint64_t* const p_full = g.p_full; uint64_t* const o_done = g.o_done;
+  uint64_t* const o_half = g.o_half;
   uint64_t* const kv_full = g.kv_full; uint8_t* const s_kv = g.s_kv;
   const uint32_t tm_s = g.tm_s, tm_o = g.tm_o;
   const int m0 = g.m0;
@@ -156,19 +158,23 @@ __device__ __forceinline__ void pa_softmax_role(const PosAttTcParams& p, const P
   const int sw = row & 7;
   PT_DECL(x_bar); PT_DECL(x_s); PT_DECL(x_o); PT_DECL(x_main); PT_DECL(x_v); PT_DECL(x_tot); PT_DECL(x_redo); PT_DECL(x_ld); PT_DECL(x_ldi); PT_DECL(x_ch);
   PT_BEGIN(x_start);
+  // key r of a crop is a pad iff r % (W + 1) == W (pad column) or r >= H (W + 1) (bottom pad row, rows beyond the crop);
+  // the two remainders are carried from tile to tile (no division per tile)
+  const int n_valid = p.H * Wp;
+  const int step = kTcTile % Wp;
+  int rem_e = etid % Wp;                       // (j * 128 + etid) % Wp: this thread's key of the tile
+  int rem_0 = 0;                               // (j * 128) % Wp
   for (int j = 0; j < ntiles; ++j) {
     float* bias = s_bias + (j & 1) * kTcTile;
-    {
-      const int r = j * kTcTile + etid;
-      const bool valid = r < p.nrows && (r % Wp) != p.W && (r / Wp) != p.H;
-      bias[etid] = valid ? 0.f : -INFINITY;
-      const uint32_t bal = __ballot_sync(0xffffffff, !valid);
-      if (lane == 0) s_mask[(j & 1) * 4 + (etid >> 5)] = bal;
-    }
+    bias[etid] = (j * kTcTile + etid < n_valid && rem_e != p.W) ? 0.f : -INFINITY;
+    const int c_pad = rem_0 <= p.W ? p.W - rem_0 : p.W - rem_0 + Wp;      // first pad column of the tile
+    rem_e += step; if (rem_e >= Wp) rem_e -= Wp;
+    rem_0 += step; if (rem_0 >= Wp) rem_0 -= Wp;
     { PT_BEGIN(t0); asm volatile("bar.sync %0, 128;" ::"r"(g.bar_id) : "memory"); PT_ADD(x_bar, t0); }
     { PT_BEGIN(t0); mbar_wait(s_full, j & 1); PT_ADD(x_s, t0); }
     tc_fence_after();
     bool first = true;
+    bool p_hi_busy = false;                                 // keys 64..127 of the P tile may still be read by the previous PV
     float ls = 0.f;
     for (;;) {
       // on the very first tile (or on a redo) the row maximum must be known before P can be formed
@@ -212,9 +218,10 @@ __device__ __forceinline__ void pa_softmax_role(const PosAttTcParams& p, const P
         m_run = m_new;
       } else if (j > 0) {
         PT_BEGIN(t0);
-        mbar_wait(o_done, (j - 1) & 1);                     // the P buffer is free once the previous PV has been issued+done
+        mbar_wait(o_half, (j - 1) & 1);                     // keys 0..63 of the P tile are free once the first four PV MMAs are done
         PT_ADD(x_o, t0);
         tc_fence_after();
+        p_hi_busy = true;
       }
       PT_BEGIN(t_main);
       const float m_use = m_run == -INFINITY ? 0.f : m_run;
@@ -296,32 +303,32 @@ __device__ __forceinline__ void pa_softmax_role(const PosAttTcParams& p, const P
         { PT_BEGIN(t0); if (ones) chunk_fast(32, vb); else chunk(32, vb); PT_ADD(x_ch, t0); }
         { PT_BEGIN(t0); tmem_ld_wait(); PT_ADD(x_ld, t0); }
         { PT_BEGIN(t0); PA_LD(96, vb); PT_ADD(x_ldi, t0); }
+        if (p_hi_busy) {
+          PT_BEGIN(t0);
+          mbar_wait(o_done, (j - 1) & 1);
+          PT_ADD(x_o, t0);
+          tc_fence_after();
+          p_hi_busy = false;
+        }
         { PT_BEGIN(t0); if (ones) chunk_fast(64, va); else chunk(64, va); PT_ADD(x_ch, t0); }
         { PT_BEGIN(t0); tmem_ld_wait(); PT_ADD(x_ld, t0); }
         { PT_BEGIN(t0); if (ones) chunk_fast(96, vb); else chunk(96, vb); PT_ADD(x_ch, t0); }
       }
       if (ones) {
         mx2 = rawmax * p.sc;
-        // zero the masked keys of this row's P
-        const int key0 = j * kTcTile;
-        if (key0 + kTcTile <= p.H * Wp) {
-          // interior tile (all keys above the bottom pad row): the pad keys are the x == W columns, key0 + c = W (mod W + 1)
-          int c = p.W - key0 % Wp;
-          if (c < 0) c += Wp;
+        // zero the masked keys of this row's P: the pad columns, and everything from the bottom pad row on
+        const int c_end = min(kTcTile, n_valid - j * kTcTile);           // keys [c_end, 128) of the tile are beyond the valid rows
 #pragma unroll 1
-          for (; c < kTcTile; c += Wp)
+        for (int c = c_pad; c < c_end; c += Wp)
+          *reinterpret_cast<T*>(prow + (c >> 6) * kTcBlk + ((((c & 63) >> 3) ^ sw) << 4) + (c & 7) * 2) = T16<T>::from_f(0.f);
+        if (c_end < kTcTile) {
+          int c = max(c_end, 0);
+#pragma unroll 1
+          for (; c < kTcTile && (c & 7); ++c)
             *reinterpret_cast<T*>(prow + (c >> 6) * kTcBlk + ((((c & 63) >> 3) ^ sw) << 4) + (c & 7) * 2) = T16<T>::from_f(0.f);
-        } else {                                              // the tail tiles: bottom pad row, rows beyond the crop
-          const uint32_t* mw = s_mask + (j & 1) * 4;
 #pragma unroll 1
-          for (int wd = 0; wd < 4; ++wd) {
-            uint32_t bits = mw[wd];
-            while (bits) {
-              const int c = wd * 32 + __ffs(bits) - 1;
-              bits &= bits - 1;
-              *reinterpret_cast<T*>(prow + (c >> 6) * kTcBlk + ((((c & 63) >> 3) ^ sw) << 4) + (c & 7) * 2) = T16<T>::from_f(0.f);
-            }
-          }
+          for (; c < kTcTile; c += 8)
+            *reinterpret_cast<uint4*>(prow + (c >> 6) * kTcBlk + ((((c & 63) >> 3) ^ sw) << 4)) = make_uint4(0, 0, 0, 0);
         }
       }
       // redo (warp-uniform decision) if some row of this warp saw a score more than 8 above its reference maximum
@@ -409,7 +416,8 @@ pos_att_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   uint64_t* s_full = kv_empty + 4;
   uint64_t* p_full = s_full + 1;
   uint64_t* o_done = p_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+  uint64_t* o_half = o_done + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_half + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
@@ -421,7 +429,7 @@ pos_att_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
     mbar_init(q_full, 1);
     for (int i = 0; i < 4; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_done, 1);
+    mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_done, 1); mbar_init(o_half, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -484,6 +492,7 @@ pos_att_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             // A: P block k/4 (64 keys each), 32 B per k-step inside the 128-byte row; B: 16 key rows = 2048 B further
             const uint64_t pa = pd + (uint64_t)((k >> 2) * (kTcBlk >> 4) + (k & 3) * 2);
             tc_mma_f16(tm_o + kc * 64, pa, vd + (uint64_t)(k * (2048 >> 4)), idesc_o, (j | k) != 0);
+            if (k == 3 && kc == NKC - 1) tc_commit(o_half);
           }
           tc_commit(&kv_empty[slot]);
           if (++slot == (uint32_t)NS) { slot = 0; ph ^= 1; }
@@ -498,7 +507,7 @@ pos_att_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     __syncwarp();
   } else {
     PaGroup g;
-    g.s_p = s_p; g.s_bias = s_bias; g.s_mask = s_mask; g.s_full = s_full; g.p_full = p_full; g.o_done = o_done;
+    g.s_p = s_p; g.s_bias = s_bias; g.s_mask = s_mask; g.s_full = s_full; g.p_full = p_full; g.o_done = o_done; g.o_half = o_half;
     g.kv_full = kv_full; g.s_kv = s_kv; g.tm_s = tm_s; g.tm_o = tm_o; g.m0 = m0; g.etid = threadIdx.x - 64; g.bar_id = 1; g.plant = true;
     pa_softmax_role<T, TRAIN>(p, g, b, row_base, ntiles, NKC, NS);
   }
@@ -535,7 +544,8 @@ pos_att_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   uint64_t* s_full = kv_empty + 4;           // [2]
   uint64_t* p_full = s_full + 2;             // [2]
   uint64_t* o_done = p_full + 2;             // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* o_half = o_done + 2;             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_half + 2);
 
   const int warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
@@ -547,7 +557,7 @@ pos_att_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
     mbar_init(q_full, 1);
     for (int i = 0; i < 4; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&o_done[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&o_done[i], 1); mbar_init(&o_half[i], 1); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512u);
@@ -603,6 +613,7 @@ pos_att_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         for (int k = 0; k < kTcTile / 16; ++k) {
           const uint64_t pa = pd + (uint64_t)((k >> 2) * (kTcBlk >> 4) + (k & 3) * 2);
           tc_mma_f16(tmem_base + 2 * kTcTile + g * 64, pa, vd + (uint64_t)(k * (2048 >> 4)), idesc_o, (j | k) != 0);
+          if (k == 3) tc_commit(&o_half[g]);
         }
         if (g == 1) tc_commit(&kv_empty[slot]);
         tc_commit(&o_done[g]);
@@ -632,7 +643,7 @@ pos_att_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const int grp = (warp - 2) >> 2;
     PaGroup g;
     g.s_p = s_p + grp * 2 * kTcBlk; g.s_bias = s_bias + grp * 2 * kTcTile; g.s_mask = s_mask + grp * 8;
-    g.s_full = &s_full[grp]; g.p_full = &p_full[grp]; g.o_done = &o_done[grp];
+    g.s_full = &s_full[grp]; g.p_full = &p_full[grp]; g.o_done = &o_done[grp]; g.o_half = &o_half[grp];
     g.kv_full = kv_full; g.s_kv = s_kv;
     g.tm_s = tmem_base + grp * kTcTile; g.tm_o = tmem_base + 2 * kTcTile + grp * 64;
     g.m0 = m0 + grp * kTcTile; g.etid = threadIdx.x - 64 - grp * 128; g.bar_id = 1 + grp; g.plant = grp == 0;
