@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(64) chan_scores_kernel(buctd_chan_att_args a, 
       S[(long long)(t1 * kCaTile + ty * PER + i) * a.c + t2 * kCaTile + tx * PER + j] = acc[i][j];
 }
 
-__global__ void chan_softmax_kernel(float* S, int c, float scale, int nrows, int nchunks) {
+__global__ void chan_softmax_kernel(float* S, int c, float scale, int nrows, int nchunks, int nsum) {
   pdl_launch_dependents();
   pdl_wait();
   // one warp per row (b, c1) of S; first reduce the row-chunk partials [b][chunk][c1][:] into chunk 0, in order
@@ -577,7 +577,7 @@ __global__ void chan_softmax_kernel(float* S, int c, float scale, int nrows, int
   float* p = S + ((long long)b * nchunks * c + c1) * c;
   for (int i = lane; i < c; i += 32) {
     float t = p[i];
-    for (int k = 1; k < nchunks; ++k) t += p[(long long)k * c * c + i];
+    for (int k = 1; k < nsum; ++k) t += p[(long long)k * c * c + i];        // the first nsum chunks hold partial scores
     p[i] = t;
   }
   __syncwarp();
@@ -679,8 +679,32 @@ static int chan_att_run(const buctd_chan_att_args& a, cudaStream_t st) {
   const size_t smem = sizeof(float) * ((size_t)TILE * a.c + (size_t)kCaPix * (a.c + 1));
   dim3 g3(ceil_div(a.h * a.w, kCaPix), tiles, a.batch);
   const float scale = 1.f / sqrtf((float)(a.h * a.w));
-  launch_pdl(chan_scores_kernel<T, TILE>, g1, dim3(64), 0, st, a, chunk);
-  launch_pdl(chan_softmax_kernel, dim3(ceil_div(a.batch * a.c, 8)), dim3(256), 0, st, a.scratch, a.c, scale, a.batch * a.c, (int)g1.x);
+  // scores: S[c1][c2] = sum over the pixel rows of yc[r][c1] y[r][c2] -- a contraction over the rows of two act16 tensors,
+  // i.e. buctd_gemm16 with both operands MN-major (tcgen05; the CUDA-core chan_scores_kernel took 75 us on branch 0).  The
+  // rows are split over nsplit CTAs per crop whose float32 partials land in the first chunks of the scratch and are summed
+  // in index order by the soft-max kernel (deterministic).  BUCTD_CHAN_SCORES_TC=0: the CUDA-core kernel.
+  static const bool use_tc = !(getenv("BUCTD_CHAN_SCORES_TC") && atoi(getenv("BUCTD_CHAN_SCORES_TC")) == 0);
+  int nsum = (int)g1.x;
+  if (use_tc && a.y_cs % 8 == 0 && a.yc_cs % 8 == 0 && ((((uintptr_t)a.y | (uintptr_t)a.yc)) & 15) == 0) {
+    int nsplit = 148 / a.batch;
+    nsplit = nsplit < 1 ? 1 : (nsplit > (int)g1.x ? (int)g1.x : nsplit);
+    buctd_gemm16_args g;
+    memset(&g, 0, sizeof(g));
+    g.dtype = a.dtype; g.a_mn_major = 1; g.b_mn_major = 1;
+    g.m = a.c; g.n = a.c; g.k = (int)rows;
+    g.nbatch = a.batch; g.nsplit = nsplit; g.ntaps = 1; g.b_rows = (int)rows;
+    g.lda = a.yc_cs; g.ldb = a.y_cs; g.ldd = a.c; g.out_f32 = 1; g.accumulate = 0;
+    g.a_batch_stride = rows * a.yc_cs; g.b_batch_stride = rows * a.y_cs;
+    g.d_t_stride = 0; g.d_s_stride = (long long)a.c * a.c; g.d_b_stride = (long long)g1.x * a.c * a.c;
+    g.alpha = 1.f;
+    g.a = a.yc; g.b = a.y; g.d = a.scratch;
+    const int rc = launch_gemm16(g, st);
+    if (rc) return rc;
+    nsum = nsplit;
+  } else {
+    launch_pdl(chan_scores_kernel<T, TILE>, g1, dim3(64), 0, st, a, chunk);
+  }
+  launch_pdl(chan_softmax_kernel, dim3(ceil_div(a.batch * a.c, 8)), dim3(256), 0, st, a.scratch, a.c, scale, a.batch * a.c, (int)g1.x, nsum);
   BUCTD_CUDA(cudaFuncSetAttribute(chan_apply_kernel<T, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   launch_pdl(chan_apply_kernel<T, TILE>, g3, dim3(128), smem, st, a);
   BUCTD_CUDA(cudaGetLastError());

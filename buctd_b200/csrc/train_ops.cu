@@ -103,6 +103,8 @@ __device__ __forceinline__ bool is_pad_row(unsigned r, int H, int W) {
 // =================================================================================================
 template <typename T>
 __global__ void __launch_bounds__(256) bn_stats_kernel(buctd_bn_stats_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long rows = (long long)a.batch * (a.h + 1) * (a.w + 1);
   col_reduce<2>(rows, a.c, a.scratch, [&](long long r, int c0, float (&acc)[2][8]) {
     float f[8];
@@ -126,6 +128,8 @@ __device__ __forceinline__ void warp_sum2(const double* partial, int nblocks, in
   *o0 = s; *o1 = ss;
 }
 __global__ void __launch_bounds__(256) bn_stats_finalize_kernel(buctd_bn_stats_args a, int nblocks) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (c >= a.c) return;
   double s, ss;
@@ -150,12 +154,12 @@ int launch_bn_stats(const buctd_bn_stats_args& a, cudaStream_t st) {
   const size_t smem = col_reduce_smem(a.c, 2);
   if (a.dtype == BUCTD_F16) {
     BUCTD_CUDA(cudaFuncSetAttribute(bn_stats_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bn_stats_kernel<__half><<<kRedBlocks, 256, smem, st>>>(a);
+    launch_pdl(bn_stats_kernel<__half>, dim3(kRedBlocks), dim3(256), smem, st, a);
   } else {
     BUCTD_CUDA(cudaFuncSetAttribute(bn_stats_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bn_stats_kernel<__nv_bfloat16><<<kRedBlocks, 256, smem, st>>>(a);
+    launch_pdl(bn_stats_kernel<__nv_bfloat16>, dim3(kRedBlocks), dim3(256), smem, st, a);
   }
-  bn_stats_finalize_kernel<<<ceil_div(a.c, 8), 256, 0, st>>>(a, kRedBlocks);
+  launch_pdl(bn_stats_finalize_kernel, dim3(ceil_div(a.c, 8)), dim3(256), 0, st, a, kRedBlocks);
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;
 }
@@ -165,6 +169,8 @@ int launch_bn_stats(const buctd_bn_stats_args& a, cudaStream_t st) {
 // =================================================================================================
 template <typename T>
 __global__ void __launch_bounds__(256) bn_apply_kernel(buctd_bn_apply_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const unsigned rows = (unsigned)a.batch * (a.h + 1) * (a.w + 1);
   const unsigned groups = a.out_cs / 8;
   const unsigned total = rows * groups;
@@ -198,8 +204,8 @@ int launch_bn_apply(const buctd_bn_apply_args& a, cudaStream_t st) {
   const long long total = (long long)a.batch * (a.h + 1) * (a.w + 1) * (a.out_cs / 8);
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   if (blocks == 0) return BUCTD_OK;
-  if (a.dtype == BUCTD_F16) bn_apply_kernel<__half><<<blocks, 256, 0, st>>>(a);
-  else bn_apply_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(a);
+  if (a.dtype == BUCTD_F16) launch_pdl(bn_apply_kernel<__half>, dim3(blocks), dim3(256), 0, st, a);
+  else launch_pdl(bn_apply_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, a);
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;
 }
@@ -209,6 +215,8 @@ int launch_bn_apply(const buctd_bn_apply_args& a, cudaStream_t st) {
 // =================================================================================================
 template <typename T>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(buctd_bn_bwd_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long rows = (long long)a.batch * (a.h + 1) * (a.w + 1);
   col_reduce<2>(rows, a.c, a.scratch, [&](long long r, int c0, float (&acc)[2][8]) {
     float g[8], z[8], y[8];
@@ -228,6 +236,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(buctd_bn_bwd_args a)
   });
 }
 __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(buctd_bn_bwd_args a, int nblocks) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (c >= a.c) return;
   double s1, s2;
@@ -243,6 +253,8 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(buctd_bn_bwd_args 
 }
 template <typename T>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(buctd_bn_bwd_args a, int nblocks) {
+  pdl_launch_dependents();
+  pdl_wait();
   const unsigned rows = (unsigned)a.batch * (a.h + 1) * (a.w + 1);
   const unsigned groups = a.dz_cs / 8;
   const unsigned total = rows * groups;
@@ -293,14 +305,14 @@ int launch_bn_bwd(const buctd_bn_bwd_args& a, cudaStream_t st) {
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   if (a.dtype == BUCTD_F16) {
     BUCTD_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bn_bwd_reduce_kernel<__half><<<kRedBlocks, 256, smem, st>>>(a);
-    bn_bwd_finalize_kernel<<<ceil_div(a.c, 8), 256, 0, st>>>(a, kRedBlocks);
-    bn_bwd_apply_kernel<__half><<<blocks, 256, 0, st>>>(a, kRedBlocks);
+    launch_pdl(bn_bwd_reduce_kernel<__half>, dim3(kRedBlocks), dim3(256), smem, st, a);
+    launch_pdl(bn_bwd_finalize_kernel, dim3(ceil_div(a.c, 8)), dim3(256), 0, st, a, kRedBlocks);
+    launch_pdl(bn_bwd_apply_kernel<__half>, dim3(blocks), dim3(256), 0, st, a, kRedBlocks);
   } else {
     BUCTD_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bn_bwd_reduce_kernel<__nv_bfloat16><<<kRedBlocks, 256, smem, st>>>(a);
-    bn_bwd_finalize_kernel<<<ceil_div(a.c, 8), 256, 0, st>>>(a, kRedBlocks);
-    bn_bwd_apply_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(a, kRedBlocks);
+    launch_pdl(bn_bwd_reduce_kernel<__nv_bfloat16>, dim3(kRedBlocks), dim3(256), smem, st, a);
+    launch_pdl(bn_bwd_finalize_kernel, dim3(ceil_div(a.c, 8)), dim3(256), 0, st, a, kRedBlocks);
+    launch_pdl(bn_bwd_apply_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, a, kRedBlocks);
   }
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;
@@ -311,6 +323,8 @@ int launch_bn_bwd(const buctd_bn_bwd_args& a, cudaStream_t st) {
 // =================================================================================================
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(buctd_colsum_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
   col_reduce<1>(a.rows, a.c, a.scratch, [&](long long r, int c0, float (&acc)[1][8]) {
     float f[8];
     unpack8<T>(ld8<T>(a.dy, r, a.cs, c0), f);
@@ -319,6 +333,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(buctd_colsum_args a) {
   });
 }
 __global__ void __launch_bounds__(256) colsum_finalize_kernel(buctd_colsum_args a, int nblocks) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (c >= a.c) return;
   double s, unused;
@@ -340,12 +356,12 @@ int launch_colsum(const buctd_colsum_args& a, cudaStream_t st) {
     const size_t smem = col_reduce_smem(b.c, 1);
     if (a.dtype == BUCTD_F16) {
       BUCTD_CUDA(cudaFuncSetAttribute(colsum_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      colsum_kernel<__half><<<kRedBlocks, 256, smem, st>>>(b);
+      launch_pdl(colsum_kernel<__half>, dim3(kRedBlocks), dim3(256), smem, st, b);
     } else {
       BUCTD_CUDA(cudaFuncSetAttribute(colsum_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      colsum_kernel<__nv_bfloat16><<<kRedBlocks, 256, smem, st>>>(b);
+      launch_pdl(colsum_kernel<__nv_bfloat16>, dim3(kRedBlocks), dim3(256), smem, st, b);
     }
-    colsum_finalize_kernel<<<ceil_div(b.c, 8), 256, 0, st>>>(b, kRedBlocks);
+    launch_pdl(colsum_finalize_kernel, dim3(ceil_div(b.c, 8)), dim3(256), 0, st, b, kRedBlocks);
   }
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;
@@ -356,6 +372,8 @@ int launch_colsum(const buctd_colsum_args& a, cudaStream_t st) {
 // =================================================================================================
 template <typename T>
 __global__ void __launch_bounds__(256) zero_stuff_kernel(buctd_zero_stuff_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int OH = 2 * a.h, OW = 2 * a.w;
   const unsigned groups = a.cs / 8;
   const unsigned total = (unsigned)a.batch * (OH + 1) * (OW + 1) * groups;
@@ -376,8 +394,8 @@ int launch_zero_stuff(const buctd_zero_stuff_args& a, cudaStream_t st) {
   const long long total = (long long)a.batch * (2 * a.h + 1) * (2 * a.w + 1) * (a.cs / 8);
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   if (blocks == 0) return BUCTD_OK;
-  if (a.dtype == BUCTD_F16) zero_stuff_kernel<__half><<<blocks, 256, 0, st>>>(a);
-  else zero_stuff_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(a);
+  if (a.dtype == BUCTD_F16) launch_pdl(zero_stuff_kernel<__half>, dim3(blocks), dim3(256), 0, st, a);
+  else launch_pdl(zero_stuff_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, a);
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;
 }
@@ -387,6 +405,8 @@ int launch_zero_stuff(const buctd_zero_stuff_args& a, cudaStream_t st) {
 // =================================================================================================
 template <typename T>
 __global__ void __launch_bounds__(256) fuse_bwd_kernel(buctd_fuse_bwd_args a, int j) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int sh = a.term_shift[j];
   const int th = a.h >> sh, tw = a.w >> sh;
   const int tcs = a.term_cs[j];
@@ -436,8 +456,8 @@ int launch_fuse_bwd(const buctd_fuse_bwd_args& a, cudaStream_t st) {
     const long long total = (long long)a.batch * ((a.h >> a.term_shift[j]) + 1) * ((a.w >> a.term_shift[j]) + 1) * (a.term_cs[j] / 8);
     const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
     if (blocks == 0) continue;
-    if (a.dtype == BUCTD_F16) fuse_bwd_kernel<__half><<<blocks, 256, 0, st>>>(a, j);
-    else fuse_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(a, j);
+    if (a.dtype == BUCTD_F16) launch_pdl(fuse_bwd_kernel<__half>, dim3(blocks), dim3(256), 0, st, a, j);
+    else launch_pdl(fuse_bwd_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, a, j);
   }
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;
@@ -448,6 +468,8 @@ int launch_fuse_bwd(const buctd_fuse_bwd_args& a, cudaStream_t st) {
 // =================================================================================================
 template <typename T>
 __global__ void __launch_bounds__(256) add16_kernel(buctd_add16_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int groups = (a.c + 7) / 8;
   const long long total = a.rows * groups;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -470,8 +492,8 @@ int launch_add16(const buctd_add16_args& a, cudaStream_t st) {
   const long long total = a.rows * ((a.c + 7) / 8);
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   if (blocks == 0) return BUCTD_OK;
-  if (a.dtype == BUCTD_F16) add16_kernel<__half><<<blocks, 256, 0, st>>>(a);
-  else add16_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(a);
+  if (a.dtype == BUCTD_F16) launch_pdl(add16_kernel<__half>, dim3(blocks), dim3(256), 0, st, a);
+  else launch_pdl(add16_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, a);
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;
 }
@@ -481,6 +503,8 @@ int launch_add16(const buctd_add16_args& a, cudaStream_t st) {
 // =================================================================================================
 template <typename T, bool TO_ACT>
 __global__ void __launch_bounds__(256) relayout_kernel(buctd_relayout_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_t[32][33];
   const int b = blockIdx.z;
   const int hw = a.h * a.w;
@@ -531,8 +555,8 @@ static int launch_relayout(const buctd_relayout_args& a, cudaStream_t st) {
     BUCTD_CUDA(cudaMemsetAsync(a.out, 0, (size_t)a.batch * (a.h + 1) * (a.w + 1) * a.cs * 2, st));
   }
   dim3 grid(ceil_div(a.h * a.w, 32), ceil_div(TO_ACT ? a.cs : a.c, 32), a.batch);
-  if (a.dtype == BUCTD_F16) relayout_kernel<__half, TO_ACT><<<grid, 256, 0, st>>>(a);
-  else relayout_kernel<__nv_bfloat16, TO_ACT><<<grid, 256, 0, st>>>(a);
+  if (a.dtype == BUCTD_F16) launch_pdl(relayout_kernel<__half, TO_ACT>, dim3(grid), dim3(256), 0, st, a);
+  else launch_pdl(relayout_kernel<__nv_bfloat16, TO_ACT>, dim3(grid), dim3(256), 0, st, a);
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;
 }
@@ -544,6 +568,8 @@ int launch_act16_to_planar(const buctd_relayout_args& a, cudaStream_t st) { retu
 // =================================================================================================
 template <typename T>
 __global__ void __launch_bounds__(256) chan_softmax_bwd_kernel(buctd_chan_softmax_bwd_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   const int lane = threadIdx.x & 31;
   if (row >= a.batch * a.c) return;
@@ -577,8 +603,8 @@ int launch_chan_softmax_bwd(const buctd_chan_softmax_bwd_args& a, cudaStream_t s
   BUCTD_CHECK(a.probs && a.da_d && a.ds && a.probs_d && a.ld >= a.c && a.ld % 8 == 0, BUCTD_ERR_INVALID, "chan_softmax_bwd: bad arguments");
   if (a.batch == 0) return BUCTD_OK;
   const int blocks = ceil_div(a.batch * a.c, 8);
-  if (a.dtype == BUCTD_F16) chan_softmax_bwd_kernel<__half><<<blocks, 256, 0, st>>>(a);
-  else chan_softmax_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(a);
+  if (a.dtype == BUCTD_F16) launch_pdl(chan_softmax_bwd_kernel<__half>, dim3(blocks), dim3(256), 0, st, a);
+  else launch_pdl(chan_softmax_bwd_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, a);
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;
 }
@@ -588,6 +614,8 @@ int launch_chan_softmax_bwd(const buctd_chan_softmax_bwd_args& a, cudaStream_t s
 // =================================================================================================
 template <typename T>
 __global__ void __launch_bounds__(256) pos_softmax_bwd_kernel(buctd_pos_softmax_bwd_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int rows = (a.h + 1) * (a.w + 1);
   const unsigned groups = a.ld / 8;
   const unsigned total = (unsigned)a.batch * rows * groups;            // < 2^32 (checked by the launcher)
@@ -632,8 +660,8 @@ int launch_pos_softmax_bwd(const buctd_pos_softmax_bwd_args& a, cudaStream_t st)
   BUCTD_CHECK(total < (1ll << 32), BUCTD_ERR_INVALID, "pos_softmax_bwd: %lld element groups exceed 32-bit indexing (split the batch)", total);
   const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
   if (blocks == 0) return BUCTD_OK;
-  if (a.dtype == BUCTD_F16) pos_softmax_bwd_kernel<__half><<<blocks, 256, 0, st>>>(a);
-  else pos_softmax_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(a);
+  if (a.dtype == BUCTD_F16) launch_pdl(pos_softmax_bwd_kernel<__half>, dim3(blocks), dim3(256), 0, st, a);
+  else launch_pdl(pos_softmax_bwd_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, a);
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;
 }
@@ -643,6 +671,8 @@ int launch_pos_softmax_bwd(const buctd_pos_softmax_bwd_args& a, cudaStream_t st)
 // =================================================================================================
 template <typename T>
 __global__ void __launch_bounds__(256) rowdot_kernel(buctd_rowdot_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int groups = (a.c + 7) / 8;
   for (long long r = (long long)blockIdx.x * 8 + threadIdx.x / 32; r < a.rows; r += (long long)gridDim.x * 8) {
@@ -663,8 +693,8 @@ int launch_rowdot(const buctd_rowdot_args& a, cudaStream_t st) {
   BUCTD_CHECK(a.a && a.b && a.out && a.a_cs % 8 == 0 && a.b_cs % 8 == 0, BUCTD_ERR_INVALID, "rowdot: bad arguments");
   const int blocks = (int)((a.rows + 7) / 8 < 148 * 16 ? (a.rows + 7) / 8 : 148 * 16);
   if (blocks == 0) return BUCTD_OK;
-  if (a.dtype == BUCTD_F16) rowdot_kernel<__half><<<blocks, 256, 0, st>>>(a);
-  else rowdot_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(a);
+  if (a.dtype == BUCTD_F16) launch_pdl(rowdot_kernel<__half>, dim3(blocks), dim3(256), 0, st, a);
+  else launch_pdl(rowdot_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, a);
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;
 }
@@ -675,6 +705,8 @@ int launch_rowdot(const buctd_rowdot_args& a, cudaStream_t st) {
 // =================================================================================================
 template <typename T>
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(buctd_stem_wgrad_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
   // one output row (b, oy) at a time: its three input rows of the three colour planes go through shared memory (coalesced
   // loads, broadcast reads), thread (co, lane) walks every fourth output column
   extern __shared__ float s_dyn[];
@@ -725,8 +757,8 @@ int launch_stem_wgrad(const buctd_stem_wgrad_args& a, cudaStream_t st) {
   BUCTD_CHECK(a.x && a.dz && a.partial && a.h % 2 == 0 && a.w % 2 == 0 && a.dz_cs >= 64, BUCTD_ERR_INVALID, "stem_wgrad: bad arguments");
   const size_t smem = sizeof(float) * (9 * (size_t)(a.w + 2) + 4 * 64 * 27);
   BUCTD_CHECK(smem <= 48 * 1024, BUCTD_ERR_INVALID, "stem_wgrad: width %d too large", a.w);
-  if (a.dtype == BUCTD_F16) stem_wgrad_kernel<__half><<<kRedBlocks, 256, smem, st>>>(a);
-  else stem_wgrad_kernel<__nv_bfloat16><<<kRedBlocks, 256, smem, st>>>(a);
+  if (a.dtype == BUCTD_F16) launch_pdl(stem_wgrad_kernel<__half>, dim3(kRedBlocks), dim3(256), smem, st, a);
+  else launch_pdl(stem_wgrad_kernel<__nv_bfloat16>, dim3(kRedBlocks), dim3(256), smem, st, a);
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;
 }
@@ -735,6 +767,8 @@ int launch_stem_wgrad(const buctd_stem_wgrad_args& a, cudaStream_t st) {
 // Split partials -> torch-layout float32 gradient
 // =================================================================================================
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(buctd_wgrad_reduce_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = (long long)a.n * a.k * a.ntaps;
   const long long per = (long long)a.ntaps * a.n * a.k;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -753,7 +787,7 @@ int launch_wgrad_reduce(const buctd_wgrad_reduce_args& a, cudaStream_t st) {
   BUCTD_CHECK(a.partial && a.grad && a.n >= 1 && a.k >= 1 && a.ntaps >= 1 && a.nsplit >= 1, BUCTD_ERR_INVALID, "wgrad_reduce: bad arguments");
   const long long total = (long long)a.n * a.k * a.ntaps;
   const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(a);
+  launch_pdl(wgrad_reduce_kernel, dim3(blocks), dim3(256), 0, st, a);
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;
 }
@@ -766,6 +800,8 @@ int launch_wgrad_reduce(const buctd_wgrad_reduce_args& a, cudaStream_t st) {
 // =================================================================================================
 template <typename T>
 __global__ void __launch_bounds__(256) repack_kernel(buctd_repack_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_w[32][32 * 9 + 1];
   const int* u = a.units + (long long)blockIdx.x * 4;
   const int64_t* e = a.table + (long long)u[0] * 8;
@@ -800,8 +836,8 @@ __global__ void __launch_bounds__(256) repack_kernel(buctd_repack_args a) {
 int launch_repack(const buctd_repack_args& a, cudaStream_t st) {
   BUCTD_CHECK(a.param && a.w16 && a.table && a.units && a.n_entries >= 0 && a.n_units >= 0, BUCTD_ERR_INVALID, "repack: bad arguments");
   if (a.n_units == 0) return BUCTD_OK;
-  if (a.dtype == BUCTD_F16) repack_kernel<__half><<<a.n_units, 256, 0, st>>>(a);
-  else repack_kernel<__nv_bfloat16><<<a.n_units, 256, 0, st>>>(a);
+  if (a.dtype == BUCTD_F16) launch_pdl(repack_kernel<__half>, dim3(a.n_units), dim3(256), 0, st, a);
+  else launch_pdl(repack_kernel<__nv_bfloat16>, dim3(a.n_units), dim3(256), 0, st, a);
   BUCTD_CUDA(cudaGetLastError());
   return BUCTD_OK;
 }

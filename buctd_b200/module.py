@@ -71,7 +71,16 @@ class PoseHighResolutionNet(nn.Module):
         self.compute_dtype = dtype
         self._dt = L.F16 if dtype == "fp16" else L.BF16
         self._torch_dt = torch.float16 if dtype == "fp16" else torch.bfloat16
-        self.antialias = bool(kwargs.get("antialias", True))   # torchvision>=0.17 TF.resize default for tensors
+        # TF.resize of the condition (lib/models/pose_hrnet_coam.py:755): torchvision >= 0.17 antialiases tensors by default,
+        # torchvision 0.9 (the authors' training environment) did not -- checkpoints trained there want antialias=False
+        # (kwarg, or cfg.MODEL.COND_RESIZE_ANTIALIAS)
+        aa = kwargs.get("antialias")
+        if aa is None:
+            try:
+                aa = cfg.MODEL.COND_RESIZE_ANTIALIAS
+            except (AttributeError, KeyError):
+                aa = True
+        self.antialias = bool(aa)
         for name, shape, kind in self.arch.param_specs():
             self._register(name, shape, kind)
         self._packed = None          # dict of device tensors
@@ -195,6 +204,10 @@ class PoseHighResolutionNet(nn.Module):
                     bk = self._get(da.fc_k.w + ".bias").detach().cpu().double()
                     bv = self._get(da.fc_v.w + ".bias").detach().cpu().double()
                     add_w(da.prefix + ":kv", torch.cat([wk, wv], 0).view(2 * da.c, da.c, 1, 1), torch.cat([bk, bv], 0))
+                    # the two 3x3 convolutions of a DAModule that read x (channel / position branch) likewise: N = 2C
+                    w1, b1 = self._fold(da.chan_cnn)
+                    w2, b2 = self._fold(da.pos_cnn)
+                    add_w(da.prefix + ":cnn2", torch.cat([w1, w2], 0), torch.cat([b1, b2], 0))
         # stem conv1 runs on CUDA cores in fp32: [64][27]
         w, b = self._fold(arch.stem[0])
         f32["conv1.w"] = w.reshape(64, 27).float().contiguous()
@@ -513,9 +526,17 @@ class PoseHighResolutionNet(nn.Module):
             head_ops.append(("resize", cond, cc))
             p = da.prefix
             # channel attention
-            y = act(p + ":y", h, w, C_)
+            fuse_cnn = not arch.att_channel_only and os.environ.get("BUCTD_COAM_CNN2", "1") != "0"
+            if fuse_cnn:
+                # channel_attention_module.cnn and position_attention_module.cnn read the same x: ONE 3x3 tap-GEMM with N = 2C;
+                # y / yp are the two channel halves of its output (row stride 2C)
+                yy = act(p + ":y|yp", h, w, 2 * C_)
+                y = Act(yy.ptr, yy.b, h, w, C_, yy.cs)
+                specs.append((L.OP_TAPGEMM, ("tg", p + ":cnn2", x, yy, dict(stride=1, relu=False, residual=None)), p + ":cnn2"))
+            else:
+                y = act(p + ":y", h, w, C_)
+                specs.append((L.OP_TAPGEMM, ("tg", da.chan_cnn.w, x, y, dict(stride=1, relu=False, residual=None)), da.chan_cnn.w))
             yc = act(p + ":yc", h, w, C_)
-            specs.append((L.OP_TAPGEMM, ("tg", da.chan_cnn.w, x, y, dict(stride=1, relu=False, residual=None)), da.chan_cnn.w))
             specs.append((L.OP_TAPGEMM, ("tg", da.chan_cnn_cond.w, cond, yc, dict(stride=1, relu=False, residual=None, k=cc)),
                           da.chan_cnn_cond.w))
             hws = _rup(h * w, 8)          # planar row stride: 16-byte multiples for TMA (H*W = 108 at the 1/32 scale of 384x288)
@@ -526,13 +547,14 @@ class PoseHighResolutionNet(nn.Module):
             specs.append((L.OP_TAPGEMM, ("lin_planar", da.chan_fc_o.w, planar, c_out, batch * C_, h * w, hws), da.chan_fc_o.w))
             p_out = None
             if not arch.att_channel_only:
-                yp = act(p + ":yp", h, w, C_)
+                yp = Act(yy.ptr + 2 * C_, yy.b, h, w, C_, yy.cs) if fuse_cnn else act(p + ":yp", h, w, C_)
                 ycp = act(p + ":ycp", h, w, cc, ccs)
                 q = act(p + ":q", h, w, C_)
                 kv = act(p + ":kv", h, w, 2 * C_)
                 o = act(p + ":o", h, w, C_)
                 p_out = act(p + ":p_out", h, w, C_)
-                specs.append((L.OP_TAPGEMM, ("tg", da.pos_cnn.w, x, yp, dict(stride=1, relu=False, residual=None)), da.pos_cnn.w))
+                if not fuse_cnn:
+                    specs.append((L.OP_TAPGEMM, ("tg", da.pos_cnn.w, x, yp, dict(stride=1, relu=False, residual=None)), da.pos_cnn.w))
                 specs.append((L.OP_TAPGEMM, ("tg", da.pos_cnn_cond.w, cond, ycp, dict(stride=1, relu=False, residual=None, k=cc)),
                               da.pos_cnn_cond.w))
                 specs.append((L.OP_TAPGEMM, ("tg", da.fc_q.w, ycp, q, dict(stride=1, relu=False, residual=None, k=cc)), da.fc_q.w))

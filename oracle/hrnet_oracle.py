@@ -192,6 +192,7 @@ def _da_module(sd, p, x, cond, channel_only: bool, act, wq, rec=None):
 def _coam_block(sd, name, xs, cond_hm, stacked: bool, colored: bool, channel_only: bool, act, wq,
                 resize: Callable = resize_aa, rec=None):
     # CoAMBlock.forward :750-757
+    resize = _CTX.get("resize") or resize        # tests: TF.resize without antialiasing (torchvision 0.9 behaviour)
     if not colored and not stacked:
         cond_hm = cond_hm[:, 0:1]
     out = []
