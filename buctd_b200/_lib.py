@@ -12,7 +12,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BUCTD_LIB") or os.path.join(_HERE, "libbuctd_b200.so")   # BUCTD_LIB: debug builds (role timers)
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 F16, BF16 = 0, 1
 TG_FLAT, TG_PATCH = 0, 1
 OUT_ACT16, OUT_ROWS16, OUT_NCHW32 = 0, 1, 2
@@ -72,7 +72,7 @@ class CondKptsArgs(C.Structure):
 
 class ChanAttArgs(C.Structure):
     _fields_ = [("dtype", i32), ("batch", i32), ("h", i32), ("w", i32), ("c", i32), ("y_cs", i32), ("yc_cs", i32),
-                ("out_stride", i32), ("drop_p", C.c_float), ("drop_seed", C.c_uint32),
+                ("out_stride", i32), ("drop_p", C.c_float), ("drop_seed", C.c_uint32), ("out_padded", i32), ("reserved", i32),
                 ("y", vp), ("yc", vp), ("scratch", fp), ("out", vp), ("seed_xor", vp)]
 
 

@@ -63,7 +63,7 @@ __device__ __forceinline__ void gm_tmem_ld32(uint32_t taddr, uint32_t* r) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kGmThreads, 1)
+__global__ void __launch_bounds__(kGmThreads)
 gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Gemm16Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -303,6 +303,10 @@ int launch_gemm16(const buctd_gemm16_args& a, cudaStream_t st) {
   const int stage_bytes = 128 * 128 + (group3 ? (p.bn_pad / 64) * 72 * 128 : p.bn_pad * 128);
   int stages = (227 * 1024 - 2048) / stage_bytes;
   p.stages = stages > 8 ? 8 : stages;
+  // a short K loop does not need the whole shared memory: fewer stages let several CTAs share an SM (the attention-sized
+  // products are thousands of one- to three-stage CTAs)
+  const int kstages = (p.k_per_split + kGmStageK - 1) / kGmStageK;
+  if (p.stages > kstages + 1) p.stages = kstages + 1 < 2 ? 2 : kstages + 1;
   // K-major: inner = K, rows = MN; MN-major: inner = MN, rows = K (+ tap offsets: signed coordinates, zero fill outside)
   CUtensorMap ma, mb;
   int rc;

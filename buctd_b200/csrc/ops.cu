@@ -566,7 +566,8 @@ __global__ void __launch_bounds__(64) chan_scores_kernel(buctd_chan_att_args a, 
       S[(long long)(t1 * kCaTile + ty * PER + i) * a.c + t2 * kCaTile + tx * PER + j] = acc[i][j];
 }
 
-__global__ void chan_softmax_kernel(float* S, int c, float scale, int nrows, int nchunks, int nsum) {
+template <typename T>
+__global__ void chan_softmax_kernel(float* S, int c, float scale, int nrows, int nchunks, int nsum, T* p16, int ld16, long long p16_bstride) {
   pdl_launch_dependents();
   pdl_wait();
   // one warp per row (b, c1) of S; first reduce the row-chunk partials [b][chunk][c1][:] into chunk 0, in order
@@ -588,7 +589,14 @@ __global__ void chan_softmax_kernel(float* S, int c, float scale, int nrows, int
   for (int i = lane; i < c; i += 32) s += expf(p[i] * scale - m);
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffff, s, o);
   const float inv = 1.f / s;
-  for (int i = lane; i < c; i += 32) p[i] = expf(p[i] * scale - m) * inv;
+  T* q = p16 ? p16 + (long long)b * p16_bstride + (long long)c1 * ld16 : nullptr;      // [b][c1][ld16]: the A operand of the tensor-core apply
+  for (int i = lane; i < c; i += 32) {
+    const float v = expf(p[i] * scale - m) * inv;
+    p[i] = v;
+    if (q) q[i] = T16<T>::from_f(v);
+  }
+  if (q)
+    for (int i = c + lane; i < ld16; i += 32) q[i] = T16<T>::from_f(0.f);
 }
 
 constexpr int kCaPix = 64;
@@ -657,7 +665,12 @@ __global__ void __launch_bounds__(128) chan_apply_kernel(buctd_chan_att_args a) 
   for (int j = 0; j < G; ++j) {
     const int p = p0 + pg * 4;
     T* o = reinterpret_cast<T*>(a.out) + ((long long)b * a.c + t1 * kCaTile + cg * G + j) * ps + p;
-    if (p + 4 <= hw && ((ps & 3) == 0)) {
+    if (a.out_padded) {                 // pixel p = (py, px) lands at py (W + 1) + px
+      T* ob = o - p;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (p + i < hw) ob[(p + i) / a.w * (a.w + 1) + (p + i) % a.w] = T16<T>::from_f(acc[i][j]);
+    } else if (p + 4 <= hw && ((ps & 3) == 0)) {
       uint2 u;
       u.x = T16<T>::pack2(acc[0][j], acc[1][j]);
       u.y = T16<T>::pack2(acc[2][j], acc[3][j]);
@@ -687,7 +700,8 @@ static int chan_att_run(const buctd_chan_att_args& a, cudaStream_t st) {
   int nsum = (int)g1.x;
   if (use_tc && a.y_cs % 8 == 0 && a.yc_cs % 8 == 0 && ((((uintptr_t)a.y | (uintptr_t)a.yc)) & 15) == 0) {
     int nsplit = 148 / a.batch;
-    nsplit = nsplit < 1 ? 1 : (nsplit > (int)g1.x ? (int)g1.x : nsplit);
+    const int cap = (int)g1.x > 1 ? (int)g1.x - 1 : 1;          // leave the last chunk free (16-bit probabilities of the apply)
+    nsplit = nsplit < 1 ? 1 : (nsplit > cap ? cap : nsplit);
     buctd_gemm16_args g;
     memset(&g, 0, sizeof(g));
     g.dtype = a.dtype; g.a_mn_major = 1; g.b_mn_major = 1;
@@ -704,7 +718,31 @@ static int chan_att_run(const buctd_chan_att_args& a, cudaStream_t st) {
   } else {
     launch_pdl(chan_scores_kernel<T, TILE>, g1, dim3(64), 0, st, a, chunk);
   }
-  launch_pdl(chan_softmax_kernel, dim3(ceil_div(a.batch * a.c, 8)), dim3(256), 0, st, a.scratch, a.c, scale, a.batch * a.c, (int)g1.x, nsum);
+  // apply: out[c1][r] = sum_c2 att[c1][c2] y[r][c2] over the PADDED pixel rows r -- a plain K-major x K-major product per crop
+  // (buctd_gemm16 again) once the probabilities exist in 16 bit; they go into the last scratch chunk (free: nsum < nchunks)
+  const int nchunks = (int)g1.x;
+  const int ld16 = (a.c + 7) / 8 * 8;
+  const bool tc_apply = a.out_padded && nsum < nchunks && a.drop_p <= 0.f && a.out_stride >= (int)rows && a.out_stride % 8 == 0 &&
+                        (((uintptr_t)a.out) & 15) == 0 && 2 * a.c >= ld16 && !(getenv("BUCTD_CHAN_APPLY_TC") && atoi(getenv("BUCTD_CHAN_APPLY_TC")) == 0);
+  T* p16 = tc_apply ? reinterpret_cast<T*>(a.scratch + (size_t)(nchunks - 1) * a.c * a.c) : nullptr;
+  launch_pdl(chan_softmax_kernel<T>, dim3(ceil_div(a.batch * a.c, 8)), dim3(256), 0, st, a.scratch, a.c, scale, a.batch * a.c, nchunks, nsum,
+             p16, ld16, (long long)2 * nchunks * a.c * a.c);
+  if (tc_apply) {
+    buctd_gemm16_args g;
+    memset(&g, 0, sizeof(g));
+    g.dtype = a.dtype; g.a_mn_major = 0; g.b_mn_major = 0;
+    g.m = a.c; g.n = (int)rows; g.k = a.c;
+    g.nbatch = a.batch; g.nsplit = 1; g.ntaps = 1;
+    g.lda = ld16; g.ldb = a.y_cs; g.ldd = a.out_stride; g.out_f32 = 0; g.accumulate = 0;
+    g.a_batch_stride = (long long)2 * nchunks * a.c * a.c; g.b_batch_stride = rows * a.y_cs;
+    g.d_b_stride = (long long)a.c * a.out_stride;
+    g.alpha = 1.f;
+    g.a = p16; g.b = a.y; g.d = a.out;
+    const int rc = launch_gemm16(g, st);
+    if (rc) return rc;
+    BUCTD_CUDA(cudaGetLastError());
+    return BUCTD_OK;
+  }
   BUCTD_CUDA(cudaFuncSetAttribute(chan_apply_kernel<T, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   launch_pdl(chan_apply_kernel<T, TILE>, g3, dim3(128), smem, st, a);
   BUCTD_CUDA(cudaGetLastError());
@@ -715,6 +753,7 @@ int launch_chan_att(const buctd_chan_att_args& a, cudaStream_t st, int* nlaunch)
   BUCTD_CHECK(a.c % 48 == 0 || a.c % 32 == 0, BUCTD_ERR_INVALID, "chan_att: C=%d must be a multiple of 48 or 32", a.c);
   BUCTD_CHECK(a.y && a.yc && a.scratch && a.out, BUCTD_ERR_INVALID, "chan_att: null pointer");
   BUCTD_CHECK(a.c <= 384, BUCTD_ERR_INVALID, "chan_att: C=%d too large for the shared-memory tile", a.c);
+  BUCTD_CHECK(!a.out_padded || a.out_stride >= (a.h + 1) * (a.w + 1), BUCTD_ERR_INVALID, "chan_att: out_padded needs out_stride >= (H+1)(W+1)");
   if (nlaunch) *nlaunch = 3;
   const bool t48 = a.c % 48 == 0;
   if (a.dtype == BUCTD_F16) return t48 ? chan_att_run<__half, 48>(a, st) : chan_att_run<__half, 32>(a, st);

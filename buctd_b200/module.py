@@ -197,6 +197,15 @@ class PoseHighResolutionNet(nn.Module):
             for da in arch.coam[s]:
                 for lin in ([da.fc_q, da.fc_o] if not arch.att_channel_only else []) + [da.chan_fc_o]:
                     w = self._get(lin.w + ".weight").detach().cpu().double()
+                    if lin is da.chan_fc_o:
+                        # the HW x HW projection reads the channel-attention output in PADDED pixel order (buctd_coam_channel_att,
+                        # out_padded): its weight matrix gets zero columns at the pad positions, K = (H+1)(W+1)
+                        rows1 = (da.h + 1) * (da.w + 1)
+                        valid = (torch.arange(da.h).view(-1, 1) * (da.w + 1) + torch.arange(da.w).view(1, -1)).reshape(-1)
+                        wp = torch.zeros(lin.fout, rows1, dtype=torch.float64)
+                        wp[:, valid] = w
+                        add_w(lin.w, wp.view(lin.fout, rows1, 1, 1), self._get(lin.w + ".bias").detach().cpu().double())
+                        continue
                     add_w(lin.w, w.view(lin.fout, lin.fin, 1, 1), self._get(lin.w + ".bias").detach().cpu().double())
                 if not arch.att_channel_only:
                     wk = self._get(da.fc_k.w + ".weight").detach().cpu().double()
@@ -540,11 +549,12 @@ class PoseHighResolutionNet(nn.Module):
             specs.append((L.OP_TAPGEMM, ("tg", da.chan_cnn_cond.w, cond, yc, dict(stride=1, relu=False, residual=None, k=cc)),
                           da.chan_cnn_cond.w))
             hws = _rup(h * w, 8)          # planar row stride: 16-byte multiples for TMA (H*W = 108 at the 1/32 scale of 384x288)
-            planar = raw(batch * C_ * hws * 2)
+            rows1, ldp = (h + 1) * (w + 1), _rup((h + 1) * (w + 1), 8)     # channel-attention output in padded pixel order
+            planar = raw(batch * C_ * ldp * 2)
             scratch = raw(L.chan_att_scratch_floats(batch, h, w, C_) * 4)
             c_out = raw(batch * C_ * hws * 2)
-            specs.append((L.OP_CHAN_ATT, ("chan", y, yc, scratch, planar, hws), p + ":chan_att"))
-            specs.append((L.OP_TAPGEMM, ("lin_planar", da.chan_fc_o.w, planar, c_out, batch * C_, h * w, hws), da.chan_fc_o.w))
+            specs.append((L.OP_CHAN_ATT, ("chan", y, yc, scratch, planar, ldp), p + ":chan_att"))
+            specs.append((L.OP_TAPGEMM, ("lin_planar", da.chan_fc_o.w, planar, c_out, batch * C_, rows1, ldp, hws), da.chan_fc_o.w))
             p_out = None
             if not arch.att_channel_only:
                 yp = Act(yy.ptr + 2 * C_, yy.b, h, w, C_, yy.cs) if fuse_cnn else act(p + ":yp", h, w, C_)
@@ -599,9 +609,9 @@ class PoseHighResolutionNet(nn.Module):
                     args.layer[li] = self._tapgemm(key, fix(src), base + dst.ptr, dst.cs, dst.h, dst.w,
                                                    residual=fix(res) if res is not None else None, **kw)
             elif tag == "lin_planar":
-                _, key, src_off, dst_off, rows, hw, hws = spec
-                a = Act(base + src_off, 1, 0, 0, hw, hws)
-                args = self._tapgemm(key, a, base + dst_off, hws, 0, 0, out_mode=L.OUT_ROWS16, m_rows=rows, a_cs=hws)
+                _, key, src_off, dst_off, rows, k_in, ld_in, hws = spec
+                a = Act(base + src_off, 1, 0, 0, k_in, ld_in)
+                args = self._tapgemm(key, a, base + dst_off, hws, 0, 0, out_mode=L.OUT_ROWS16, m_rows=rows, a_cs=ld_in)
                 args.batch = 1
             elif tag == "fuse":
                 _, terms, out = spec
@@ -617,7 +627,7 @@ class PoseHighResolutionNet(nn.Module):
                 _, y, yc, scratch, planar, hws = spec
                 args = L.ChanAttArgs()
                 args.dtype, args.batch, args.h, args.w, args.c = self._dt, batch, y.h, y.w, y.c
-                args.y_cs, args.yc_cs, args.out_stride = y.cs, yc.cs, hws
+                args.y_cs, args.yc_cs, args.out_stride, args.out_padded = y.cs, yc.cs, hws, 1
                 args.y, args.yc, args.scratch, args.out = base + y.ptr, base + yc.ptr, base + scratch, base + planar
             elif tag == "pos":
                 _, q, kv, o, c = spec

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BUCTD_ABI_VERSION 2
+#define BUCTD_ABI_VERSION 3
 
 #define BUCTD_OK 0
 #define BUCTD_ERR_INVALID (-1)   /* bad argument / unsupported shape */
@@ -172,6 +172,10 @@ int buctd_cond_from_kpts(buctd_ctx* ctx, const buctd_cond_kpts_args* args, buctd
  * HW x HW fc_o tap-GEMM).  y, yc: act16 [B][H+1][W+1][cs].  scratch: float32 [B][nchunks][C][C] with
  * nchunks = ceil((H+1)(W+1) / BUCTD_CHAN_ATT_ROWS_PER_CHUNK) (per-chunk partial sums, reduced in a fixed order:
  * the result is bit-reproducible); after the call [b][0][:][:] holds the soft-max probabilities.
+ * out_padded != 0: out is written in PADDED pixel order, out[b][c1][y (W+1) + x] with row stride out_stride >=
+ * (H+1)(W+1) (pad positions: zeros on the tensor-core path, left untouched by the CUDA-core kernels -- allocate zeroed): the consumer is a fc_o whose weight matrix carries zero columns at the pad
+ * positions.  In that form (no dropout, >= 2 scratch chunks) both contractions run on the tensor cores (buctd_gemm16's
+ * kernel: scores over the pixel rows with MN-major operands, then att (16 bit) x y^T); otherwise CUDA-core kernels.
  * Replaces SimplifiedScaledDotProductAttention.forward up to fc_o,
  * lib/models/self_attention.py:146-158 as called from ChannelAttentionModule.forward,
  * lib/models/pose_hrnet_coam.py:673-689. */
@@ -180,6 +184,7 @@ typedef struct {
   int32_t dtype, batch, h, w, c, y_cs, yc_cs;
   int32_t out_stride;   /* planar row stride of out in elements (0 = H*W); a multiple of 8 lets the HW x HW fc_o read it by TMA */
   float drop_p; uint32_t drop_seed;   /* training: dropout of the probabilities (see "Dropout" below); 0: none */
+  int32_t out_padded, reserved;
   const void* y; const void* yc; float* scratch; void* out;
   const uint32_t* seed_xor;           /* optional device word XOR-ed into drop_seed (the step counter of a replayed CUDA graph) */
 } buctd_chan_att_args;

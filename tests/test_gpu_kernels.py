@@ -247,6 +247,19 @@ def test_channel_attention(dt, C, h, w):
     att = torch.softmax(torch.matmul(ycf, yf.transpose(1, 2)) / math.sqrt(h * w), -1)
     assert_close(scratch[:, 0], att, 1e-4, "chan att probs")
     assert_close(out, torch.matmul(att, yf), TOL[dt], "chan att out")
+    # padded pixel order (what the plan uses): out[b][c1][y (w + 1) + x], tensor-core apply when there are >= 2 scratch chunks
+    # (probabilities rounded to 16 bit before the product), CUDA-core kernels otherwise -- same layout either way
+    rows1 = (h + 1) * (w + 1)
+    ld = (rows1 + 7) // 8 * 8
+    outp = torch.zeros(B, C, ld, dtype=TDT[dt], device="cuda")
+    scratch.zero_()
+    a.out, a.out_stride, a.out_padded = outp.data_ptr(), ld, 1
+    ctx().run(L.OP_CHAN_ATT, a, stream())
+    torch.cuda.synchronize()
+    assert_close(scratch[:, 0], att, 1e-4, "chan att probs (padded run)")
+    got = outp[:, :, :rows1].view(B, C, h + 1, w + 1)
+    assert got[:, :, h].float().abs().max() == 0 and got[:, :, :, w].float().abs().max() == 0
+    assert_close(got[:, :, :h, :w].reshape(B, C, h * w), torch.matmul(att, yf), 2 * TOL[dt], "chan att out (padded order)")
 
 
 @pytest.mark.parametrize("dt", DTS)
