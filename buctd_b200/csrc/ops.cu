@@ -90,55 +90,66 @@ int launch_stem(const buctd_stem_args& a, cudaStream_t st) {
 // Exchange/fuse: out = ReLU(sum_j nearest_up(term_j)), 8 channels (16 B) per thread.
 // lib/models/pose_hrnet_coam.py:257-266.
 // =================================================================================================
+// One block = one padded row (b, y) of the output; thread = (pixel lane, 8-channel group), fixed for the whole row, so
+// there is no index division per element and the terms' row bases are computed once (the round-2 ncu capture showed the
+// flat-index version issue-bound: 73 % issue slots busy at 30 % of the DRAM bandwidth).
 template <typename T>
 __global__ void __launch_bounds__(256) fuse_kernel(buctd_fuse_args a) {
   pdl_launch_dependents();
   pdl_wait();
-  // 32-bit index math (the launcher checks B (H+1) (W+1) C/8 < 2^31); one (row, 8-channel group) per thread and step
   const unsigned cv = (unsigned)a.c / 8;
   const unsigned Hp = a.h + 1, Wp = a.w + 1;
-  const unsigned total = (unsigned)a.batch * Hp * Wp * cv;
+  const unsigned px_lanes = blockDim.x / cv;              // pixels per step
+  const unsigned pl = threadIdx.x / cv, c8 = threadIdx.x - pl * cv;
+  if (pl >= px_lanes) return;
   const int nt = a.nterms;
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const unsigned r = i / cv;
-    const unsigned c8 = i - r * cv;
-    const unsigned ry = r / Wp;
-    const unsigned x = r - ry * Wp;
-    const unsigned b = ry / Hp;
-    const unsigned y = ry - b * Hp;
-    uint4 u = make_uint4(0, 0, 0, 0);
-    if (x < (unsigned)a.w && y < (unsigned)a.h) {
-      uint4 t[4];
+  for (unsigned row = blockIdx.x; row < (unsigned)a.batch * Hp; row += gridDim.x) {
+    const unsigned b = row / Hp, y = row - b * Hp;
+    T* out = reinterpret_cast<T*>(a.out) + (size_t)row * Wp * a.out_cs + c8 * 8;
+    if (y == (unsigned)a.h) {                               // bottom pad row
+      for (unsigned x = pl; x < Wp; x += px_lanes) *reinterpret_cast<uint4*>(out + (size_t)x * a.out_cs) = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    const T* tb[4];
+    int tcs[4], tsh[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {                 // all loads first: the terms' latencies overlap
-        if (j < nt) {
-          const int sh = a.term_shift[j];
-          const unsigned sw = ((unsigned)a.w >> sh) + 1, shh = ((unsigned)a.h >> sh) + 1;
-          const size_t sr = (size_t)(b * shh + (y >> sh)) * sw + (x >> sh);
-          t[j] = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.term[j]) + sr * a.term_cs[j] + c8 * 8);
-        }
+    for (int j = 0; j < 4; ++j) {
+      if (j < nt) {
+        const int sh = a.term_shift[j];
+        const unsigned sw = ((unsigned)a.w >> sh) + 1, shh = ((unsigned)a.h >> sh) + 1;
+        tb[j] = reinterpret_cast<const T*>(a.term[j]) + (size_t)(b * shh + (y >> sh)) * sw * a.term_cs[j] + c8 * 8;
+        tcs[j] = a.term_cs[j]; tsh[j] = sh;
       }
-      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    }
+    for (unsigned x = pl; x < Wp; x += px_lanes) {
+      uint4 u = make_uint4(0, 0, 0, 0);
+      if (x < (unsigned)a.w) {
+        uint4 t[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (j < nt) {
-          const uint32_t w[4] = {t[j].x, t[j].y, t[j].z, t[j].w};
+        for (int j = 0; j < 4; ++j)                         // all loads first: the terms' latencies overlap
+          if (j < nt) t[j] = *reinterpret_cast<const uint4*>(tb[j] + (size_t)(x >> tsh[j]) * tcs[j]);
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float2 f = T16<T>::unpack2(w[q]);
-            acc[2 * q] += f.x;
-            acc[2 * q + 1] += f.y;
+        for (int j = 0; j < 4; ++j) {
+          if (j < nt) {
+            const uint32_t w[4] = {t[j].x, t[j].y, t[j].z, t[j].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float2 f = T16<T>::unpack2(w[q]);
+              acc[2 * q] += f.x;
+              acc[2 * q + 1] += f.y;
+            }
           }
         }
-      }
-      if (a.relu) {
+        if (a.relu) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) acc[q] = fmaxf(acc[q], 0.f);
+          for (int q = 0; q < 8; ++q) acc[q] = fmaxf(acc[q], 0.f);
+        }
+        u.x = T16<T>::pack2(acc[0], acc[1]); u.y = T16<T>::pack2(acc[2], acc[3]);
+        u.z = T16<T>::pack2(acc[4], acc[5]); u.w = T16<T>::pack2(acc[6], acc[7]);
       }
-      u.x = T16<T>::pack2(acc[0], acc[1]); u.y = T16<T>::pack2(acc[2], acc[3]);
-      u.z = T16<T>::pack2(acc[4], acc[5]); u.w = T16<T>::pack2(acc[6], acc[7]);
+      *reinterpret_cast<uint4*>(out + (size_t)x * a.out_cs) = u;
     }
-    *reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.out) + (size_t)r * a.out_cs + c8 * 8) = u;
   }
 }
 
@@ -150,9 +161,9 @@ int launch_fuse(const buctd_fuse_args& a, cudaStream_t st) {
     BUCTD_CHECK((a.h % (1 << a.term_shift[j])) == 0 && (a.w % (1 << a.term_shift[j])) == 0, BUCTD_ERR_INVALID,
                 "fuse: %dx%d not divisible by 2^%d", a.h, a.w, a.term_shift[j]);
   }
-  const long long total = (long long)a.batch * (a.h + 1) * (a.w + 1) * (a.c / 8);
-  BUCTD_CHECK(total < (1ll << 31), BUCTD_ERR_INVALID, "fuse: tensor too large for 32-bit indexing (%lld groups)", total);
-  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  BUCTD_CHECK(a.c / 8 <= 256 && (long long)a.batch * (a.h + 1) < (1ll << 31), BUCTD_ERR_INVALID, "fuse: C <= 2048 and B (H+1) < 2^31");
+  const long long rows_total = (long long)a.batch * (a.h + 1);
+  const int blocks = (int)(rows_total < 148 * 16 ? rows_total : 148 * 16);
   if (a.dtype == BUCTD_F16) launch_pdl(fuse_kernel<__half>, dim3(blocks), dim3(256), 0, st, a);
   else launch_pdl(fuse_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, a);
   BUCTD_CUDA(cudaGetLastError());

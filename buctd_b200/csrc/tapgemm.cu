@@ -46,7 +46,13 @@ __device__ unsigned long long g_role_cycles[160 * 16];
 constexpr int kATileBytes = kBlockM * 128;
 constexpr int kThreads = 192;          // patch kernel: producer + MMA + 4 epilogue warps
 
-template <int BN> __host__ __device__ constexpr int patch_stages() { return BN <= 128 ? 4 : 3; }
+// Stages of the (tap, K chunk) ring.  One tile per CTA means prologue (barriers, TMEM allocation), the nine taps and the
+// epilogue of a tile run back to back; with a 2-deep ring (BUCTD_PATCH_STAGES, default) two or three CTAs fit an SM and
+// one's epilogue overlaps the other's loads -- measured against the 4-deep ring that fills the SM with one CTA.
+#ifndef BUCTD_PATCH_STAGES
+#define BUCTD_PATCH_STAGES 2
+#endif
+template <int BN> __host__ __device__ constexpr int patch_stages() { return BN <= 128 ? BUCTD_PATCH_STAGES : (BUCTD_PATCH_STAGES < 3 ? BUCTD_PATCH_STAGES : 3); }
 
 // =================================================================================================
 // PATCH kernel (stride-2 3x3): one tile per CTA
@@ -530,7 +536,7 @@ tapgemm_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 // ---- host side --------------------------------------------------------------------------------
 static int stage_bytes(int bn) { return (bn + 63) / 64 * kEpiBlockBytes; }
 static size_t patch_smem_bytes(int bn) {
-  const int s = bn <= 128 ? 4 : 3;
+  const int s = bn <= 128 ? BUCTD_PATCH_STAGES : (BUCTD_PATCH_STAGES < 3 ? BUCTD_PATCH_STAGES : 3);
   return 1024 + (size_t)s * (kATileBytes + bn * 128) + stage_bytes(bn) + bn * 4 + 256;
 }
 
