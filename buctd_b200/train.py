@@ -69,6 +69,8 @@ class TrainStep:
     ``nn.Parameter`` views: ``state_dict()`` / checkpoints work as before) and its BatchNorm running statistics are
     updated in place."""
 
+    NLANES = 4        # side streams: one per branch of a HighResolutionModule
+
     def __init__(self, model, batch: int, lr: float = 1e-3, dtype: str = "bf16", loss_scale: float = 1.0, drop_p: float = 0.1,
                  seed: int = 0, use_target_weight: bool = True, optimizer: Optional[Adam] = None, graph: Optional[bool] = None):
         if not torch.cuda.is_available():
@@ -99,9 +101,12 @@ class TrainStep:
         self.buffers = dict(model.named_buffers())
         self.steps_done = 0
         self.antialias = bool(getattr(model, "antialias", True))
+        self.use_lanes = os.environ.get("BUCTD_TRAIN_LANES", "1") != "0"
+        with torch.cuda.device(self.device):
+            self._side = [torch.cuda.Stream(device=self.device) for _ in range(self.NLANES)]
         # ---- two-pass build: measure the workspace, allocate, build with absolute pointers ----------
         self._build(dry=True)
-        self.ws = torch.zeros(self._ws_bytes + self._wg_need_final + 4096, dtype=torch.uint8, device=self.device)
+        self.ws = torch.zeros(self._ws_bytes + (1 + self.NLANES) * (self._wg_need_final + 1024) + 4096, dtype=torch.uint8, device=self.device)
         self.w16 = torch.zeros(self._w16_elems + 64, dtype=self.tdt, device=self.device)
         self._build(dry=False)
         self.table = torch.tensor(self._table, dtype=torch.int64, device=self.device)
@@ -158,7 +163,26 @@ class TrainStep:
         return self._grad_ptr + 4 * self.poff[pname]
 
     def _call(self, lst: List, name: str, args):
-        lst.append((name, args))
+        lst.append((name, args, self._cur_lane))
+
+    # Lanes: the BasicBlocks of the branches of one HighResolutionModule are independent between two exchange / fuse steps, in
+    # the forward and in the backward, and at 32 crops per GPU the low-resolution branches are rows of small, latency-bound
+    # launches.  An op recorded while ``_cur_lane`` is i runs on side stream i; ops recorded with lane None run on the step's
+    # stream and first join every active lane, and a lane forks from the step's stream when its first op arrives.  A backward
+    # op inherits the lane its forward op was recorded on.  Reduction / split-K scratch is per lane.
+    def _tape_add(self, fn):
+        lane = self._cur_lane
+
+        def wrapped():
+            prev, self._cur_lane = self._cur_lane, lane
+            try:
+                fn()
+            finally:
+                self._cur_lane = prev
+        self.tape.append(wrapped)
+
+    def _lane_slot(self) -> int:
+        return 0 if self._cur_lane is None else 1 + self._cur_lane
 
     # ------------------------------------------------------------------------------------------------------
     # op builders: each emits forward launches now and registers a backward builder on the tape
@@ -200,18 +224,18 @@ class TrainStep:
             for t in range(9):
                 g.tap_off[t] = (t // 3 - 1) * (x.w + 1) + (t % 3 - 1)
         g.alpha = 1.0
-        g.a, g.b, g.d = dz.ptr, x.ptr, self._wg_scratch
+        g.a, g.b, g.d = dz.ptr, x.ptr, self._wg_scratch[self._lane_slot()]
         self._wg_need = max(self._wg_need, nsplit * taps * cout * cin * 4)
         self._call(ops, "buctd_gemm16", g)
         r = L.WgradReduceArgs()
         r.n, r.k, r.ntaps, r.nsplit, r.accumulate, r.inv_scale = cout, cin, taps, nsplit, 0, self.inv_scale
-        r.partial, r.grad = self._wg_scratch, self._gptr(pname)
+        r.partial, r.grad = self._wg_scratch[self._lane_slot()], self._gptr(pname)
         self._call(ops, "buctd_wgrad_reduce", r)
 
     def _colsum(self, ops: List, ptr: int, c: int, cs: int, rows: int, pname: str):
         a = L.ColsumArgs()
         a.dtype, a.c, a.cs, a.accumulate, a.rows, a.inv_scale = self.dt, c, cs, 0, rows, self.inv_scale
-        a.dy, a.dbias, a.scratch = ptr, self._gptr(pname), self._red_scratch
+        a.dy, a.dbias, a.scratch = ptr, self._gptr(pname), self._red_scratch[self._lane_slot()]
         self._call(ops, "buctd_colsum", a)
 
     def _conv_core(self, cv: Conv, x: _T, name=""):
@@ -250,7 +274,7 @@ class TrainStep:
         mr = self._take(2 * C_ * 4)
         s = L.BnStatsArgs()
         s.dtype, s.batch, s.h, s.w, s.c, s.z_cs, s.eps, s.momentum = self.dt, self.B, z.h, z.w, C_, z.cs, BN_EPS, BN_MOMENTUM
-        s.z, s.mean_rstd, s.scratch = z.ptr, mr, self._red_scratch
+        s.z, s.mean_rstd, s.scratch = z.ptr, mr, self._red_scratch[self._lane_slot()]
         s.running_mean, s.running_var = self.buffers[bn + ".running_mean"].data_ptr(), self.buffers[bn + ".running_var"].data_ptr()
         self._call(self.fwd, "buctd_bn_stats", s)
         a = L.BnApplyArgs()
@@ -270,13 +294,13 @@ class TrainStep:
             b.dy_cs, b.y_cs, b.z_cs, b.dz_cs = y.grad.cs, y.cs, z.cs, dz.cs
             b.relu, b.inv_scale = int(relu), self.inv_scale
             b.dy, b.y, b.z, b.mean_rstd, b.gamma = y.grad.ptr, y.ptr, z.ptr, mr, self._pptr(bn + ".weight")
-            b.dgamma, b.dbeta, b.scratch, b.dz = self._gptr(bn + ".weight"), self._gptr(bn + ".bias"), self._red_scratch, dz.ptr
+            b.dgamma, b.dbeta, b.scratch, b.dz = self._gptr(bn + ".weight"), self._gptr(bn + ".bias"), self._red_scratch[self._lane_slot()], dz.ptr
             if residual is not None and residual.needs_grad:
                 dr, acc = self._grad(residual)
                 b.dres, b.dres_cs, b.res_accumulate = dr.ptr, dr.cs, acc
             self._call(self.bwd, "buctd_bn_bwd", b)
             conv_backward(dz)
-        self.tape.append(backward)
+        self._tape_add(backward)
         return y
 
     def conv_bn(self, cv: Conv, x: _T, residual: Optional[_T] = None, relu: Optional[bool] = None) -> _T:
@@ -290,7 +314,7 @@ class TrainStep:
         def backward():
             if z.grad is not None:
                 cb(z.grad)
-        self.tape.append(backward)
+        self._tape_add(backward)
         return z
 
     def linear(self, lin: Linear, x: _T, name="") -> _T:
@@ -323,7 +347,7 @@ class TrainStep:
             b.nterms = n
             if n:
                 self._call(self.bwd, "buctd_hr_fuse_bwd", b)
-        self.tape.append(backward)
+        self._tape_add(backward)
         return out
 
     # ---- CoAM --------------------------------------------------------------------------------------------
@@ -422,7 +446,7 @@ class TrainStep:
             self._gemm(ops, ds, k.ptr, dq.ptr, rows1, C_, rows1, a_mn=0, b_mn=1, lda=ld, ldb=k.cs, ldd=dq.cs, nbatch=B, a_bs=rows1 * ld,
                        b_bs=rows1 * k.cs, d_bs=rows1 * dq.cs)
         self._call(self.fwd, "buctd_coam_position_att", pa)
-        self.tape.append(pos_backward)
+        self._tape_add(pos_backward)
         p_out = self.linear(da.fc_o, o)
         # ---------------- combine ----------------
         out = self._act(h, w, C_, name=da.prefix + ":out")
@@ -490,7 +514,7 @@ class TrainStep:
                        a_bs=rows1 * y.cs, b_bs=C_ * ldc, d_bs=rows1 * dyc.cs)
         # the combine backward must run BEFORE the backward of p_out's linear layer (it sets p_out.grad): p_out's layer was
         # taped earlier, so append this one last -- the tape is walked in reverse
-        self.tape.append(combine_backward)
+        self._tape_add(combine_backward)
         return out
 
     # ------------------------------------------------------------------------------------------------------
@@ -508,9 +532,10 @@ class TrainStep:
         self.seeds: Dict[str, int] = {}
         H, W = arch.img_h, arch.img_w
         H4, W4 = H // 4, W // 4
-        self._red_scratch = self._take(8 * 2 * 2048 * (L.BN_BLOCKS + 1))
+        self._cur_lane = None
+        self._red_scratch = [self._take(8 * 2 * 2048 * (L.BN_BLOCKS + 1)) for _ in range(1 + self.NLANES)]
         self._wg_need = getattr(self, "_wg_need", 0) if not dry else 0
-        self._wg_scratch = self._take(self._wg_need_final if not dry else 0)
+        self._wg_scratch = [self._take(self._wg_need_final if not dry else 0) for _ in range(1 + self.NLANES)]
         self.seed_dev = torch.zeros(1, dtype=torch.int32, device=self.device) if dry or not hasattr(self, "seed_dev") else self.seed_dev
         self.seed_dev_ptr = self.seed_dev.data_ptr()
         Cx = 3 + arch.in_cond
@@ -583,9 +608,11 @@ class TrainStep:
                 xs = new
             for m in mods:
                 for i in range(nb):
+                    self._cur_lane = i if (self.use_lanes and nb > 1) else None
                     for blk in m.branches[i]:
                         t = self.conv_bn(blk.convs[0], xs[i])
                         xs[i] = self.conv_bn(blk.convs[1], t, residual=xs[i], relu=True)
+                self._cur_lane = None
                 if not m.fuse:
                     continue
                 outs = []
@@ -624,7 +651,7 @@ class TrainStep:
         self._call(self.fwd, "buctd_joints_mse", ms)
         # backward of the head: dhm (nchw32) -> act16, bias / weight / data gradient
         dhm = self._act(H4, W4, K, cs=_rup(K, 8), needs_grad=False, name="dhm")
-        self.bwd.append(("nchw32_to_act16", (dhm32, B, K, 0, K, H4, W4, dhm.cs, dhm.ptr)))
+        self.bwd.append(("nchw32_to_act16", (dhm32, B, K, 0, K, H4, W4, dhm.cs, dhm.ptr), None))
         self._colsum(self.bwd, dhm.ptr, K, dhm.cs, dhm.rows, "final_layer.bias")
         self._wgrad(self.bwd, dhm, fs, "final_layer.weight", K, fl.cin, fl.k)
         dfs, acc = self._grad(fs)
@@ -642,12 +669,36 @@ class TrainStep:
     # execution
     # ------------------------------------------------------------------------------------------------------
     def _run_ops(self, ops, stream):
+        """``stream``: the torch stream of the step.  Ops with a lane run on that lane's side stream (forked from / joined into
+        ``stream`` with events: inside a CUDA-graph capture these become the graph's dependency edges)."""
         lib, h = self.ctx.lib, self.ctx.handle
-        for name, args in ops:
-            if name == "nchw32_to_act16":
-                self.ctx.nchw32_to_act16(self.dt, *args, stream)
+        main = stream.cuda_stream
+        active = []
+
+        def join():
+            for l in active:
+                ev = torch.cuda.Event()
+                ev.record(self._side[l])
+                stream.wait_event(ev)
+            del active[:]
+
+        for name, args, lane in ops:
+            if lane is None:
+                if active:
+                    join()
+                st = main
             else:
-                L.check(getattr(lib, name)(h, C.byref(args), C.c_void_p(stream)), name)
+                if lane not in active:
+                    ev = torch.cuda.Event()
+                    ev.record(stream)
+                    self._side[lane].wait_event(ev)
+                    active.append(lane)
+                st = self._side[lane].cuda_stream
+            if name == "nchw32_to_act16":
+                self.ctx.nchw32_to_act16(self.dt, *args, st)
+            else:
+                L.check(getattr(lib, name)(h, C.byref(args), C.c_void_p(st)), name)
+        join()
 
     def _repack(self):
         a = L.RepackArgs()
@@ -681,6 +732,7 @@ class TrainStep:
         return self._views
 
     def _fwd_bwd(self, stream):
+        """stream: the (current) torch stream of the step"""
         self.seed_dev.copy_(self.seed_host, non_blocking=True)
         self._run_ops(self.fwd, stream)
         self._run_ops(self.bwd, stream)
@@ -693,14 +745,14 @@ class TrainStep:
             self._copy_in(input, target, target_weight)
             stream = torch.cuda.current_stream(self.device)
             if not self._use_graph:
-                self._fwd_bwd(stream.cuda_stream)
+                self._fwd_bwd(stream)
             else:
                 if self._graph is None:
-                    self._fwd_bwd(stream.cuda_stream)              # eager warm-up run (also validates every launch)
+                    self._fwd_bwd(stream)                          # eager warm-up run (also validates every launch)
                     stream.synchronize()
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
-                        self._fwd_bwd(torch.cuda.current_stream(self.device).cuda_stream)
+                        self._fwd_bwd(torch.cuda.current_stream(self.device))
                     self._graph = g
                 else:
                     self._graph.replay()
