@@ -293,6 +293,7 @@ BUCTD_API int buctd_create(int device, buctd_ctx** out) {
   if (!rc) rc = pos_att_tc_init_device();
   if (!rc) rc = gemm16_init_device();
   if (!rc) rc = pos_att_bwd_init_device();
+  if (!rc) rc = pairgemm_init_device();
   if (!rc && get_encode_tiled() == nullptr) {
     set_error("buctd_create: cuTensorMapEncodeTiled driver entry point not found");
     rc = BUCTD_ERR_NO_DEVICE;

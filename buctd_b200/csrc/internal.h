@@ -59,6 +59,15 @@ inline void fastdiv_make(uint32_t d, uint32_t* mul, uint32_t* shift) {
   *shift = s;
 }
 
+// CTA-pair GEMM (pairgemm.cu): the plan of a large nn.Linear
+struct PairGemmParams {
+  int k16, num_kc;
+  int n, n_store;            // true output columns (bias range) / columns that exist in an output row
+  int m_tiles, num_tiles;    // 256 x 256 tiles, m fastest
+  int relu;
+  const float* bias;
+};
+
 // everything a tap-GEMM launch needs, computed (tensor maps encoded) once
 struct TapGemmLaunch {
   alignas(64) CUtensorMap map_a;
@@ -70,6 +79,8 @@ struct TapGemmLaunch {
   dim3 grid;
   int bn;
   int dtype;
+  int pair;                          // the launch is a pairgemm (cta_group::2) launch: map_a / map_b / map_out + pp
+  PairGemmParams pp;
 };
 
 int tapgemm_prepare(const buctd_tapgemm_args& a, TapGemmLaunch* L, int sm_count);
@@ -77,6 +88,10 @@ int tapgemm_launch(const TapGemmLaunch& L, cudaStream_t st);
 // [rows][cs] 16-bit matrix seen through SWIZZLE_128B boxes of 64 channels x box_rows rows (inner = channels that exist)
 int tapgemm_encode_rows_map(CUtensorMap* m, int dtype, const void* base, int inner, int cs, long long rows, int box_rows);
 int tapgemm_init_device();
+bool pairgemm_wanted(const buctd_tapgemm_args& a, int num_kc);
+int pairgemm_prepare(const buctd_tapgemm_args& a, TapGemmLaunch* L, int ctas);
+int pairgemm_launch(const TapGemmLaunch& L, cudaStream_t st);
+int pairgemm_init_device();
 
 // immediate launchers of the CUDA-core kernels (each returns a BUCTD_* code)
 int launch_stem(const buctd_stem_args& a, cudaStream_t st);

@@ -787,6 +787,12 @@ int tapgemm_prepare(const buctd_tapgemm_args& a, TapGemmLaunch* L, int sm_count)
   CUresult cr;
   dim3 grid;
   memset(&L->sp, 0, sizeof(L->sp));
+  L->pair = 0;
+  if (pairgemm_wanted(a, kp.num_kc)) {
+    BUCTD_CHECK(a.m_rows > 0 && a.m_rows < (1ll << 31), BUCTD_ERR_INVALID, "tapgemm: bad m_rows %lld", (long long)a.m_rows);
+    L->kp = kp;
+    return pairgemm_prepare(a, L, sm_count);
+  }
   if (a.mode == BUCTD_TG_FLAT) {
     BUCTD_CHECK(a.m_rows > 0 && a.m_rows < (1ll << 31), BUCTD_ERR_INVALID, "tapgemm: bad m_rows %lld", (long long)a.m_rows);
     if (a.out_mode != BUCTD_OUT_ROWS16 || a.ntaps == 9)
@@ -885,6 +891,7 @@ extern "C" __attribute__((visibility("default"))) int buctd_debug_role_cycles(un
 #endif
 
 int tapgemm_launch(const TapGemmLaunch& L, cudaStream_t st) {
+  if (L.pair) return pairgemm_launch(L, st);
   if (L.dtype == BUCTD_F16) return dispatch_bn<__half>(L, st);
   return dispatch_bn<__nv_bfloat16>(L, st);
 }

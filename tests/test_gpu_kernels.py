@@ -388,3 +388,38 @@ def test_tapgemm_chain_basic_blocks(dt, c, B, h, w, nblocks, dxf, monkeypatch):
     torch.cuda.synchronize()
     assert_close(from_act16(bufs[cur], c), ref, 4 * TOL[dt], "chain of %d blocks C=%d" % (nblocks, c))
     assert pads_are_zero(bufs[cur])
+
+
+def _linear_rows_case(dt, rows, k, n, relu, seed=40):
+    """large nn.Linear on a [rows, k] matrix with padded row strides (the channel attention's fc_o on the planar matrix)"""
+    lda, ldo = rup(k, 8), rup(n, 8)
+    x = q16(_rand(rows, k, seed=seed), dt)
+    wt = q16(_rand(n, k, seed=seed + 1, scale=1.0 / math.sqrt(k)), dt)
+    bias = _rand(n, seed=seed + 2, scale=0.1)
+    a16 = torch.zeros(rows, lda, dtype=TDT[dt], device="cuda")
+    a16[:, :k] = x.to(TDT[dt])
+    out = torch.full((rows, ldo), 7.0, dtype=TDT[dt], device="cuda")
+    tapgemm(dt, a16, wt.view(n, k, 1, 1), bias, out, H=0, W=0, out_mode=L.OUT_ROWS16, m_rows=rows, batch=1, k=k, relu=relu)
+    ref = F.linear(x.cuda(), wt.cuda(), bias.cuda())          # fp32 on the GPU (the big case is 150 GFLOP)
+    if relu:
+        ref = ref.relu()
+    return out, ref
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("rows,k,n,relu", [(512, 481, 432, False), (300, 1825, 1728, True), (256, 256, 256, False),
+                                           (1000, 7081, 1000, False)])
+def test_pairgemm_linear_rows(dt, rows, k, n, relu, monkeypatch):
+    """CTA-pair (cta_group::2) GEMM: M / N / K tails, bias, ReLU, and the same numbers as the one-CTA slab plan"""
+    out, ref = _linear_rows_case(dt, rows, k, n, relu)
+    assert_close(out[:, :n], ref, TOL[dt], "pairgemm")
+    monkeypatch.setenv("BUCTD_PAIRGEMM", "0")
+    out1, _ = _linear_rows_case(dt, rows, k, n, relu)
+    # both plans accumulate the same fp32 products in the same k order on the tensor core
+    assert_close(out[:, :n], out1[:, :n], 2e-3, "pairgemm vs slab plan")
+
+
+def test_pairgemm_fc_o_w48():
+    """the real shape: Linear(6912, 6912) over 64 x 48 planar rows of padded-pixel length 7081"""
+    out, ref = _linear_rows_case(L.F16, 3072, 7081, 6912, False)
+    assert_close(out[:, :6912], ref, TOL[L.F16], "pairgemm fc_o")
