@@ -92,6 +92,10 @@ bool pairgemm_wanted(const buctd_tapgemm_args& a, int num_kc);
 int pairgemm_prepare(const buctd_tapgemm_args& a, TapGemmLaunch* L, int ctas);
 int pairgemm_launch(const TapGemmLaunch& L, cudaStream_t st);
 int pairgemm_init_device();
+int pair_max_clusters(int* out);       // CTA pairs of a one-CTA-per-SM kernel that can be co-resident on the device
+// set around tapgemm_prepare by a caller that plans for a CTA pair: every weight tile is split between the two CTAs
+// (shared-memory carve-up and the weight tensor map's box use bn / 2 rows)
+extern thread_local int tl_slab_pair;
 
 // immediate launchers of the CUDA-core kernels (each returns a BUCTD_* code)
 int launch_stem(const buctd_stem_args& a, cudaStream_t st);

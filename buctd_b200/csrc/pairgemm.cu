@@ -27,64 +27,6 @@ constexpr int kPgHalfBytes = 128 * 128;                 // one operand half of a
 constexpr int kPgStageBytes = 2 * kPgHalfBytes;        // A half + W half
 constexpr int kPgSmemBytes = 1024 + kPgStages * kPgStageBytes + 2 * kEpiBlockBytes + 256 * 4 + 256;
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of `p` (a shared-memory pointer of THIS CTA) in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-// TMA load of one box into THIS CTA's shared memory; the bytes are counted on the barrier at `bar_cluster_addr`
-// (the leader CTA's full barrier)
-__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(m), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
-}
-__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
-}
-// arrives (count 1) on the barrier at the same shared-memory offset in BOTH CTAs once every MMA issued so far is done
-__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"((uint16_t)3)
-               : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 __device__ __forceinline__ void pg_tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
@@ -247,12 +189,6 @@ bool pairgemm_wanted(const buctd_tapgemm_args& a, int num_kc) {
          num_kc >= 4 && a.m_rows >= 256;
 }
 
-int pairgemm_init_device() {
-  BUCTD_CUDA(cudaFuncSetAttribute(pairgemm_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPgSmemBytes));
-  BUCTD_CUDA(cudaFuncSetAttribute(pairgemm_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPgSmemBytes));
-  return BUCTD_OK;
-}
-
 template <typename T>
 static int pairgemm_max_clusters(int* out) {
   cudaLaunchConfig_t cfg = {};
@@ -264,6 +200,23 @@ static int pairgemm_max_clusters(int* out) {
   int n = 0;
   BUCTD_CUDA(cudaOccupancyMaxActiveClusters(&n, pairgemm_kernel<T>, &cfg));
   *out = n;
+  return BUCTD_OK;
+}
+
+int pair_max_clusters(int* out) {
+  static int cached = 0;
+  if (cached == 0) {
+    int rc = pairgemm_max_clusters<__half>(&cached);
+    if (rc) return rc;
+    BUCTD_CHECK(cached > 0, BUCTD_ERR_CUDA, "no CTA pair fits this device");
+  }
+  *out = cached;
+  return BUCTD_OK;
+}
+
+int pairgemm_init_device() {
+  BUCTD_CUDA(cudaFuncSetAttribute(pairgemm_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPgSmemBytes));
+  BUCTD_CUDA(cudaFuncSetAttribute(pairgemm_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPgSmemBytes));
   return BUCTD_OK;
 }
 
@@ -286,13 +239,8 @@ int pairgemm_prepare(const buctd_tapgemm_args& a, TapGemmLaunch* L, int ctas) {
   if (rc) return rc;
   rc = tapgemm_encode_rows_map(&L->map_out, a.dtype, a.out, a.out_cs, a.out_cs, a.m_rows, 128);
   if (rc) return rc;
-  static int max_clusters[2] = {0, 0};
-  int& mc = max_clusters[a.dtype == BUCTD_F16 ? 0 : 1];
-  if (mc == 0) {
-    rc = a.dtype == BUCTD_F16 ? pairgemm_max_clusters<__half>(&mc) : pairgemm_max_clusters<__nv_bfloat16>(&mc);
-    if (rc) return rc;
-    BUCTD_CHECK(mc > 0, BUCTD_ERR_CUDA, "pairgemm: no CTA pair fits this device");
-  }
+  int mc = 0;
+  if ((rc = pair_max_clusters(&mc))) return rc;
   int clusters = ctas / 2 < mc ? ctas / 2 : mc;
   if (clusters < 1) clusters = 1;
   if (clusters > p.num_tiles) clusters = p.num_tiles;

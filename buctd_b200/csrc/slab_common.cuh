@@ -30,6 +30,13 @@ struct SubIter {
     ds = (int)gridDim.x % num_super; dn = (int)gridDim.x / num_super;
     j = 0;
   }
+  // the same walk for a virtual CTA `vb` of `vg` over `num_units` units per N tile (CTA pairs: a unit = two super-tiles)
+  __device__ __forceinline__ void init2(int num_units, int vb, int vg) {
+    num_super = num_units;
+    s = vb % num_units; nt = vb / num_units;
+    ds = vg % num_units; dn = vg / num_units;
+    j = 0;
+  }
   __device__ __forceinline__ void next_item() {
     s += ds; nt += dn;
     if (s >= num_super) { s -= num_super; ++nt; }
@@ -43,18 +50,21 @@ struct SubIter {
 };
 
 // all k-steps of one (sub-tile, tap, chunk): fully unrolled, every descriptor is base + immediate
-template <int BN, int KS>
+template <int BN, int KS, bool PAIR = false>
 __device__ __forceinline__ void mma_ksteps(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t first) {
 #pragma unroll
-  for (int k = 0; k < KS; ++k) tc_mma_f16(d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k == 0 ? first : 1u);
+  for (int k = 0; k < KS; ++k) {
+    if constexpr (PAIR) tc_mma_f16_pair(d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k == 0 ? first : 1u);
+    else tc_mma_f16(d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k == 0 ? first : 1u);
+  }
 }
-template <int BN>
+template <int BN, bool PAIR = false>
 __device__ __forceinline__ void mma_ksteps_rt(int ksteps, uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t first) {
   switch (ksteps) {
-    case 1: mma_ksteps<BN, 1>(d, adesc, bdesc, idesc, first); break;
-    case 2: mma_ksteps<BN, 2>(d, adesc, bdesc, idesc, first); break;
-    case 3: mma_ksteps<BN, 3>(d, adesc, bdesc, idesc, first); break;
-    default: mma_ksteps<BN, 4>(d, adesc, bdesc, idesc, first); break;
+    case 1: mma_ksteps<BN, 1, PAIR>(d, adesc, bdesc, idesc, first); break;
+    case 2: mma_ksteps<BN, 2, PAIR>(d, adesc, bdesc, idesc, first); break;
+    case 3: mma_ksteps<BN, 3, PAIR>(d, adesc, bdesc, idesc, first); break;
+    default: mma_ksteps<BN, 4, PAIR>(d, adesc, bdesc, idesc, first); break;
   }
 }
 

@@ -574,6 +574,8 @@ int tapgemm_init_device() {
   return rc ? rc : set_attrs<__nv_bfloat16>();
 }
 
+thread_local int tl_slab_pair = 0;
+
 static int pick_bn(int n_alloc) {
   static const int cand[] = {32, 48, 64, 96, 128, 192, 256};
   if (n_alloc <= 256) {
@@ -616,7 +618,7 @@ static bool plan_slab_one(const buctd_tapgemm_args& a, int bn, int num_kc, int k
   if (msub > nacc) return false;
   const int n_tiles = ceil_div(a.n_alloc, bn);
   const int halo = a.ntaps == 9 ? a.out_w + 2 : 0;        // (W+1) + 1 rows on each side
-  const int wtile = bn * 128;
+  const int wtile = (tl_slab_pair ? bn / 2 : bn) * 128;
   // direct epilogue: 16-bit rows, every N tile full (no channel tail), 16-byte aligned rows
   static const bool no_direct = getenv("BUCTD_NO_DIRECT") != nullptr;       // debug knob
   // (measured: a win for rows of <= 128 bytes, a loss for wide tiles whose rows are many partial-sector writes)
@@ -629,7 +631,11 @@ static bool plan_slab_one(const buctd_tapgemm_args& a, int bn, int num_kc, int k
   const int stage = stage_needed ? stage_bytes(bn) : 0;
   const int fixed = 1024 + 2 * bn * 4 + 512;              // alignment slack + two bias tiles + barriers
   const long long total_w = (long long)a.ntaps * num_kc * wtile;
-  const bool resident = n_tiles == 1 && total_w <= 80 * 1024;
+  // A CTA pair holds half of every weight tile per CTA: the 9 x 2 half tiles of a C = 96 layer (108 KB) stay resident
+  // beside one slab set and one stage buffer, and nothing is streamed per work item (BUCTD_PAIR_RESIDENT=0: stream)
+  const char* epr = getenv("BUCTD_PAIR_RESIDENT");
+  const long long res_cap = tl_slab_pair && !(epr != nullptr && atoi(epr) == 0) ? 112 * 1024 : 80 * 1024;
+  bool resident = n_tiles == 1 && total_w <= res_cap;
   const int rows = msub * 128 + 2 * halo;
   const int nboxes = ceil_div(rows, 256);
   const int box_rows = (ceil_div(rows, nboxes) + 7) / 8 * 8;   // every box starts on a 1024-byte swizzle atom
@@ -638,12 +644,26 @@ static bool plan_slab_one(const buctd_tapgemm_args& a, int bn, int num_kc, int k
   int sa = 0, sw = 0, se = 0;
   long long need = 0;
   const int sa_max = num_kc > 1 ? 3 : 2;
-  for (int cse = 2; cse >= 1 && sa == 0; --cse)
-    for (int csw = resident ? 0 : 4; (resident ? csw == 0 : csw >= 2) && sa == 0; --csw)
-      for (int csa = sa_max; csa >= 2; --csa) {
-        need = fixed + (long long)cse * stage + csa * slab + (resident ? total_w : (long long)csw * wtile);
-        if (need <= kSmemBudget) { sa = csa; sw = csw; se = cse; break; }
-      }
+  const char* esw = getenv("BUCTD_SW_MAX");               // experiment knobs: weight-ring depth (<= 8), stage buffers
+  const char* ese = getenv("BUCTD_SE_MAX");
+  // the weight ring is latency-bound (ring depth tiles per ~0.9 us TMA round trip: chain_bench with BUCTD_CHAIN_DEBUG=5);
+  // a pair's half tiles leave room for 8 of them
+  const int sw_max = esw ? (atoi(esw) < 2 ? 2 : atoi(esw) > 8 ? 8 : atoi(esw)) : (tl_slab_pair ? 8 : 4);
+  const int se_max = ese ? (atoi(ese) <= 1 ? 1 : 2) : 2;
+  for (int pass = 0; pass < 2 && sa == 0; ++pass) {
+    if (pass == 1) {
+      // only the weight sets the pair rule newly admits fall back to streaming at the same super-tile; for the others
+      // the caller tries a smaller super-tile first (resident weights are worth more than a long slab)
+      if (!resident || total_w <= 80 * 1024) break;
+      resident = false;
+    }
+    for (int cse = se_max; cse >= 1 && sa == 0; --cse)
+      for (int csw = resident ? 0 : sw_max; (resident ? csw == 0 : csw >= 2) && sa == 0; --csw)
+        for (int csa = sa_max; csa >= 2; --csa) {
+          need = fixed + (long long)cse * stage + csa * slab + (resident ? total_w : (long long)csw * wtile);
+          if (need <= kSmemBudget) { sa = csa; sw = csw; se = cse; break; }
+        }
+  }
   if (sa == 0) return false;
   if (direct && a.residual != nullptr && se != 2) direct = false;  // direct + residual needs one stage buffer per epilogue group
   SlabParams c;
@@ -832,7 +852,7 @@ int tapgemm_prepare(const buctd_tapgemm_args& a, TapGemmLaunch* L, int sm_count)
   {
     cuuint64_t dims[2] = {(cuuint64_t)a.w_cs, (cuuint64_t)a.ntaps * a.n_alloc};
     cuuint64_t strides[1] = {(cuuint64_t)a.w_cs * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)bn};
+    cuuint32_t box[2] = {64, (cuuint32_t)(tl_slab_pair ? bn / 2 : bn)};
     cuuint32_t es[2] = {1, 1};
     cr = enc(&L->map_b, dt, 2, const_cast<void*>(a.w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

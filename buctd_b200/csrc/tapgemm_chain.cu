@@ -219,12 +219,19 @@ __device__ __forceinline__ void dxf_compute(const TapGemmKParams& p, long long m
   }
 }
 
-template <typename T, int BN, int MSUB, bool DXF>
+// PAIR: the grid is launched in clusters of two CTAs that work as ONE tcgen05 CTA pair (cta_group::2, M = 256): CTA r of
+// pair v processes super-tile 2 su + r of unit su (both with the same N tile), each CTA loads its own slab but only HALF
+// of every weight tile (BN / 2 rows), and the leader (rank 0) issues the MMAs of both.  The layers this is chosen for
+// (C >= 96) stream 166 KB .. 1.3 MB of weights per work item against <= 64 KB of activations: at C >= 192 the one-CTA
+// kernel is bound by that stream (TMA fill of one SM ~ 36 B/clk: 10 us per 128-row item against 6.4 us of MMAs).
+// Everything behind the accumulator (epilogue, stage buffers, DMA, dataflow flags, publisher) stays per CTA.
+template <typename T, int BN, int MSUB, bool DXF, bool PAIR = false>
 __global__ void __launch_bounds__(kChainThreads, 1)
 tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParams p0, const SlabParams sp) {
+  static_assert(!(PAIR && DXF), "the dx-fused plan is a one-CTA plan");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int kWTileBytes = BN * 128;
+  constexpr int kWTileBytes = (PAIR ? BN / 2 : BN) * 128;            // this CTA's rows of one weight tile
   constexpr int TR = DXF ? kDxfRows : kBlockM;                       // output rows per accumulator tile
   constexpr int ASTRIDE = DXF ? dxf_acc_stride<BN>() : acc_stride<BN>();
   constexpr int NACC = DXF ? dxf_nacc<BN>() : slab_nacc<BN>();
@@ -251,6 +258,12 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
   const int lane = threadIdx.x & 31;
   const bool split = sp.stage_bufs == 1;
   const int NL = cp.n_layers;
+  // virtual CTA / grid and the units of one N tile: a CTA and a super-tile, or a CTA pair and two super-tiles
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int vb = PAIR ? (int)blockIdx.x >> 1 : (int)blockIdx.x;
+  const int vg = PAIR ? (int)gridDim.x >> 1 : (int)gridDim.x;
+  const int units = PAIR ? (sp.num_super + 1) >> 1 : sp.num_super;
+  auto real_s = [&](int su) { return PAIR ? 2 * su + rank : su; };     // may be == num_super (odd count): a dummy tile
 
   if (warp == 0 && lane == 0) {
     for (int l = 0; l < NL; ++l) {
@@ -259,22 +272,28 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
     }
     for (int s = 0; s < 4; ++s) { mbar_init(&slab_full[s], 1); mbar_init(&slab_empty[s], 1); }
     for (int s = 0; s < 8; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    for (int s = 0; s < kMaxAcc; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], split ? 8 : 4); }
+    // PAIR: the leader's acc_empty collects the epilogue warps of both CTAs
+    for (int s = 0; s < kMaxAcc; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], (split ? 8 : 4) * (PAIR ? 2 : 1)); }
     for (int s = 0; s < 4; ++s) { mbar_init(&st_ready[s], 1); mbar_init(&st_done[s], split ? 8 : 4); }
     mbar_init(w_free, 1);
     pub->head = 0;
     pub->tail = 0;
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, sp.tmem_cols);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_pair(tmem_slot, sp.tmem_cols);
+    else tmem_alloc(tmem_slot, sp.tmem_cols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();      // the barriers of both CTAs exist before either signals the other's
+  else __syncthreads();
   tc_fence_after();
   pdl_launch_dependents();
   pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
   constexpr int R = MSUB * TR;
-  const int my_items = (sp.num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int num_items_v = units * cp.n_tiles;
+  const int my_items = (num_items_v - vb + vg - 1) / vg;
   const int total_u = my_items * MSUB;
 
   if (warp == 0) {
@@ -283,6 +302,12 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
     // (flags only grow).  With a single polling thread the serial latency per item (three dependent acquire loads) was
     // longer than a dx-fused tile takes to compute.
     uint32_t slot = 0, slot_ph = 1, ws = 0, ws_ph = 1;
+    // full barriers: this CTA's, or (PAIR) the leader's -- which counts the bytes of both CTAs
+    const uint32_t slab_full_a = PAIR ? mapa_u32(&slab_full[0], 0) : smem_u32(&slab_full[0]);
+    const uint32_t w_full_a = PAIR ? mapa_u32(&w_full[0], 0) : smem_u32(&w_full[0]);
+    const bool expects = !PAIR || rank == 0;
+    constexpr uint32_t kTx = PAIR ? 2u : 1u;
+    const int w_row0 = PAIR ? rank * (BN / 2) : 0;
     const int reach = (sp.halo + R - 1) / R;
     const int per = 2 * reach + 1, look = 32 / per;
     const unsigned full = (1u << per) - 1u;
@@ -291,13 +316,13 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
       const CUtensorMap* map_b = &cp.m[l].b;
       if (lane == 0 && sp.w_resident) {
         if (l > 0) mbar_wait(w_free, (uint32_t)(l - 1) & 1u);
-        mbar_expect_tx(&w_full[0], (uint32_t)(sp.w_tiles * kWTileBytes));
+        if (expects) mbar_expect_tx(&w_full[0], kTx * (uint32_t)(sp.w_tiles * kWTileBytes));
         for (int kc = 0; kc < p0.num_kc; ++kc)
           for (int t = 0; t < p0.ntaps; ++t)
-            tma_load_2d(wbuf + (size_t)(kc * p0.ntaps + t) * kWTileBytes, map_b, &w_full[0], kc * 64, t * p0.n_alloc);
+            tma_load_2d_to<PAIR>(wbuf + (size_t)(kc * p0.ntaps + t) * kWTileBytes, map_b, w_full_a, kc * 64, t * p0.n_alloc + w_row0);
       }
       SubIter it;
-      it.init(sp.num_super);
+      it.init2(units, vb, vg);
       int ready_upto = (l == 0 || (cp.debug & 1)) ? my_items : 0;       // items [k, ready_upto) have their inputs
       for (int k = 0; k < my_items; ++k, it.next_item()) {
         if (k >= ready_upto) {
@@ -306,8 +331,8 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
           const unsigned int* row = cp.flags + (size_t)(l - 1) * sp.num_super;
           int fidx = -1;
           if (o < look && k + o < my_items) {
-            const long long item = (long long)blockIdx.x + (long long)(k + o) * gridDim.x;
-            const int f = (int)(item % sp.num_super) - reach + j;
+            const long long item = (long long)vb + (long long)(k + o) * vg;
+            const int f = real_s((int)(item % units)) - reach + j;
             if (f >= 0 && f < sp.num_super) fidx = f;
           }
           const long long t0 = clock64();
@@ -325,19 +350,20 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
           if (lane == 0) fence_proxy_async_all();            // ... and lane 0's TMA (async proxy) reads after that
         }
         if (lane == 0) {
-          const long long r0 = (long long)it.s * R - sp.halo;
+          const long long r0 = (long long)real_s(it.s) * R - sp.halo;      // a dummy tile lies past the last row: zero fill
           for (int kc = 0; kc < p0.num_kc; ++kc) {
             mbar_wait(&slab_empty[slot], slot_ph);
-            mbar_expect_tx(&slab_full[slot], (uint32_t)sp.slab_bytes);
+            if (expects) mbar_expect_tx(&slab_full[slot], kTx * (uint32_t)sp.slab_bytes);
             for (int i = 0; i < sp.nboxes; ++i)
-              tma_load_2d(slabs + (size_t)slot * sp.slab_bytes + (size_t)i * sp.box_rows * 128, map_a, &slab_full[slot], kc * 64,
-                          (int)(r0 + (long long)i * sp.box_rows));
+              tma_load_2d_to<PAIR>(slabs + (size_t)slot * sp.slab_bytes + (size_t)i * sp.box_rows * 128, map_a, slab_full_a + slot * 8,
+                                   kc * 64, (int)(r0 + (long long)i * sp.box_rows));
             if (++slot == (uint32_t)sp.sa) { slot = 0; slot_ph ^= 1; }
             if (!sp.w_resident) {
               for (int t = 0; t < p0.ntaps; ++t) {
                 mbar_wait(&w_empty[ws], ws_ph);
-                mbar_expect_tx(&w_full[ws], kWTileBytes);
-                tma_load_2d(wbuf + (size_t)ws * kWTileBytes, map_b, &w_full[ws], kc * 64, t * p0.n_alloc + it.nt * BN);
+                if (expects) mbar_expect_tx(&w_full[ws], kTx * kWTileBytes);
+                tma_load_2d_to<PAIR>(wbuf + (size_t)ws * kWTileBytes, map_b, w_full_a + ws * 8, kc * 64,
+                                     t * p0.n_alloc + it.nt * BN + w_row0);
                 if (++ws == (uint32_t)sp.sw) { ws = 0; ws_ph ^= 1; }
               }
             }
@@ -347,8 +373,8 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
       }
     }
   } else if (warp == 1) {
-    if (elect_one()) {
-      const uint32_t idesc = umma_idesc_f16(T16<T>::kFmt, kBlockM, DXF ? 3 * BN : BN);
+    if ((!PAIR || rank == 0) && elect_one()) {
+      const uint32_t idesc = umma_idesc_f16(T16<T>::kFmt, PAIR ? 2 * kBlockM : kBlockM, DXF ? 3 * BN : BN);
       uint32_t slot = 0, slot_ph = 0, ws = 0, ws_ph = 0, aslot = 0, aph = 1;
       const uint32_t slab0_addr = smem_u32(slabs);
       const uint32_t wbuf_addr = smem_u32(wbuf);
@@ -393,7 +419,8 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
           uint32_t d[MSUB], dslot[MSUB];
 #pragma unroll
           for (int j = 0; j < MSUB; ++j) {
-            mbar_wait(&acc_empty[aslot], aph);
+            if constexpr (PAIR) mbar_wait_cluster(&acc_empty[aslot], aph);      // arrivals come from both CTAs
+            else mbar_wait(&acc_empty[aslot], aph);
             dslot[j] = aslot;
             d[j] = tmem_base + aslot * ASTRIDE;
             if (++aslot == NACC) { aslot = 0; aph ^= 1; }
@@ -422,20 +449,20 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
                 const uint32_t first = (kc | t) == 0 ? 0u : 1u;
 #pragma unroll
                 for (int j = 0; j < MSUB; ++j)
-                  mma_ksteps_rt<BN>(ksteps, d[j], adesc0 + (uint64_t)(j * (kBlockM * 128 / 16)), bdesc, idesc, first);
+                  mma_ksteps_rt<BN, PAIR>(ksteps, d[j], adesc0 + (uint64_t)(j * (kBlockM * 128 / 16)), bdesc, idesc, first);
                 if (!sp.w_resident) {
-                  tc_commit(&w_empty[ws]);
+                  tc_commit_x<PAIR>(&w_empty[ws]);
                   if (++ws == (uint32_t)sp.sw) { ws = 0; ws_ph ^= 1; }
                 }
               }
             }
-            tc_commit(&slab_empty[slot]);
+            tc_commit_x<PAIR>(&slab_empty[slot]);
             if (++slot == (uint32_t)sp.sa) { slot = 0; slot_ph ^= 1; }
           }
 #pragma unroll
-          for (int j = 0; j < MSUB; ++j) tc_commit(&acc_full[dslot[j]]);
+          for (int j = 0; j < MSUB; ++j) tc_commit_x<PAIR>(&acc_full[dslot[j]]);
         }
-        if (sp.w_resident) tc_commit(w_free);
+        if (sp.w_resident) tc_commit_x<PAIR>(w_free);
       }
     }
     __syncwarp();
@@ -475,7 +502,7 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
         // C >= 192, where a CTA has one or two items per layer and a late flag stalls the neighbours for a whole item.
         constexpr int kLagMax = 4;
         const int lag = cp.lag;
-        const bool drain = sp.num_items / (int)gridDim.x <= lag + 1;      // otherwise the FIFO runs across the layer boundary
+        const bool drain = num_items_v / vg <= lag + 1;      // otherwise the FIFO runs across the layer boundary
         int pend[kLagMax + 1];
         int npend = 0;
         for (int l = 0; l < NL; ++l, ubase += total_u) {
@@ -487,14 +514,14 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
           // the residual tile of super-tile s is an earlier layer's output of super-tile s: written, completed and
           // published by THIS thread (same super-tile -> CTA assignment in every layer)
           SubIter st_it, pr_it;
-          st_it.init(sp.num_super);
-          pr_it.init(sp.num_super);
+          st_it.init2(units, vb, vg);
+          pr_it.init2(units, vb, vg);
           auto prepare = [&](int u) {
             const int ug = ubase + u;
             const int e = ug & se_mask;
             if (has_res) {
               EpiTile t;
-              t.m0 = (long long)pr_it.s * R + (long long)pr_it.j * TR;
+              t.m0 = (long long)real_s(pr_it.s) * R + (long long)pr_it.j * TR;
               t.tb = t.ty0 = t.tx0 = 0;
               if constexpr (DXF) dxf_load_residual<BN>(p, map_res, t.m0, stage + (size_t)e * epi_stage_bytes<BN>(), &st_ready[e]);
               else epi_load_residual<BN>(p, map_res, t, pr_it.nt * BN, stage + (size_t)e * epi_stage_bytes<BN>(), &st_ready[e]);
@@ -510,17 +537,17 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
             const int e = ug & se_mask;
             mbar_wait(&st_done[e], (uint32_t)(ug >> se_sh) & 1u);
             EpiTile t;
-            t.m0 = (long long)st_it.s * R + (long long)st_it.j * TR;
+            t.m0 = (long long)real_s(st_it.s) * R + (long long)st_it.j * TR;
             t.tb = t.ty0 = t.tx0 = 0;
             if constexpr (DXF) dxf_store<BN>(p, map_out, t.m0, stage + (size_t)e * epi_stage_bytes<BN>());
             else epi_store<BN>(p, map_out, t, st_it.nt * BN, stage + (size_t)e * epi_stage_bytes<BN>());
-            const int s_now = st_it.s;
+            const int s_now = real_s(st_it.s);
             const bool item_end = st_it.j == MSUB - 1;
             st_it.template next<MSUB>();
             if (item_end && l + 1 < NL && !(cp.debug & 1)) {
 #pragma unroll
               for (int i = 0; i <= kLagMax; ++i)
-                if (i == npend) pend[i] = l * sp.num_super + s_now;
+                if (i == npend) pend[i] = s_now < sp.num_super ? l * sp.num_super + s_now : -1;      // -1: a pair's dummy tile
               ++npend;
               // publish the oldest pending item: its MSUB store groups precede the lag * MSUB most recent ones, which
               // stay in flight (waiting for the newest stores would stall this thread, and with it the stage buffers)
@@ -531,7 +558,7 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
                   case 2: tma_store_wait_complete<2 * MSUB>(); break;
                   default: tma_store_wait_complete<kLagMax * MSUB>(); break;
                 }
-                pub_push(pub, pushed, (unsigned)pend[0]);
+                if (pend[0] >= 0) pub_push(pub, pushed, (unsigned)pend[0]);
 #pragma unroll
                 for (int i = 0; i < kLagMax; ++i) pend[i] = pend[i + 1];
                 --npend;
@@ -551,7 +578,7 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
             tma_store_wait_all();                 // this CTA's tiles so far are in global memory
 #pragma unroll
             for (int i = 0; i <= kLagMax; ++i)
-              if (i < npend) pub_push(pub, pushed, (unsigned)pend[i]);
+              if (i < npend && pend[i] >= 0) pub_push(pub, pushed, (unsigned)pend[i]);
             npend = 0;
           }
         }
@@ -568,20 +595,21 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
       uint32_t aslot = (uint32_t)ug, aph = 0;
       uint32_t xpar = 0;
       int ubase = 0;
+      const uint32_t acc_empty_a = PAIR ? mapa_u32(&acc_empty[0], 0) : 0u;      // the leader's accumulator-free barriers
       for (int l = 0; l < NL; ++l, ubase += total_u) {
         TapGemmKParams p = p0;
         p.relu = cp.relu[l];
         p.bias = cp.bias[l];
         const bool has_res = cp.has_res[l] != 0;
         SubIter it;
-        it.init(sp.num_super);
+        it.init2(units, vb, vg);
         int u = ug - ubase;                     // 0 or 1 at a layer start
         if (u == 1) it.template next<MSUB>();
         int cur_nt = -1;
         for (; u < total_u; u += step, ug += step) {
           const int nt = it.nt;
           EpiTile tile;
-          tile.m0 = (long long)it.s * R + (long long)it.j * TR;
+          tile.m0 = (long long)real_s(it.s) * R + (long long)it.j * TR;
           tile.tb = tile.ty0 = tile.tx0 = 0;
           if (nt != cur_nt) {
             if (split) { epi_sync<256>(); epi_load_bias<BN, 256>(p, nt * BN, my_bias, gtid); epi_sync<256>(); }
@@ -610,7 +638,10 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
           if (lane == 0) mbar_arrive(&st_done[e]);
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[aslot]);
+          if (lane == 0) {
+            if constexpr (PAIR) mbar_arrive_cluster(acc_empty_a + aslot * 8);
+            else mbar_arrive(&acc_empty[aslot]);
+          }
           it.template next<MSUB>();
           if (step == 2) it.template next<MSUB>();
           aslot += step;
@@ -620,8 +651,13 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, sp.tmem_cols);
+  if constexpr (PAIR) {
+    cluster_sync_all();                   // neither CTA leaves (or frees TMEM) while the other may still touch it
+    if (warp == 1) tmem_dealloc_pair(tmem_base, sp.tmem_cols);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, sp.tmem_cols);
+  }
 }
 
 // ---- host side --------------------------------------------------------------------------------
@@ -632,6 +668,7 @@ struct ChainLaunch {
   dim3 grid;
   int bn, dtype;
   int dxf;
+  int pair;        // CTA-pair plan (cta_group::2): grid = 2 x pairs, launched in clusters of two
 };
 
 template <typename T, int BN, int MSUB>
@@ -641,6 +678,9 @@ static int chain_set_attr() {
   }
   if constexpr (BN <= 64) {
     BUCTD_CUDA(cudaFuncSetAttribute(tapgemm_chain_kernel<T, BN, MSUB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+  }
+  if constexpr (BN >= 96 && MSUB <= slab_nacc<BN>()) {
+    BUCTD_CUDA(cudaFuncSetAttribute(tapgemm_chain_kernel<T, BN, MSUB, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
   }
   return BUCTD_OK;
 }
@@ -736,6 +776,20 @@ int tapgemm_chain_prepare(const buctd_tapgemm_chain_args& a, ChainLaunch* C, int
   SlabParams dxf_sp;
   dim3 dxf_grid;
   C->dxf = 0;
+  // CTA-pair plan for the wide layers: the one-CTA kernel streams the whole weight set per work item through a ring
+  // that is bound by the TMA round trip (4 tiles per ~0.9 us).  Measured per convolution at B = 64 (tools/chain_bench.py,
+  // profiles/r3_chain_pair.txt): C = 192 @24x18 22.1 -> 17.1 us, C = 384 @12x9 22.4 -> 19.8 us; C = 96 @48x36 28.3 -> 27.9
+  // (its floor is the activation traffic, not the weights), so pairs start at 192 channels.  BUCTD_CHAIN_PAIR=0 keeps
+  // the one-CTA plan everywhere, =2 pairs from 96 channels on (tests).
+  {
+    const char* e = getenv("BUCTD_CHAIN_PAIR");
+    const int mode = e != nullptr ? atoi(e) : 1;
+    C->pair = mode != 0 && f.n_alloc >= (mode == 2 ? 96 : 192) && sm_count >= 2;
+  }
+  struct PairScope {       // tapgemm_prepare plans half weight tiles while this is alive
+    explicit PairScope(int on) { tl_slab_pair = on; }
+    ~PairScope() { tl_slab_pair = 0; }
+  } pair_scope(C->pair);
   for (int l = 0; l < a.n_layers; ++l) {
     const buctd_tapgemm_args& g = a.layer[l];
     BUCTD_CHECK(g.mode == BUCTD_TG_FLAT && g.out_mode == BUCTD_OUT_ACT16, BUCTD_ERR_INVALID,
@@ -755,7 +809,16 @@ int tapgemm_chain_prepare(const buctd_tapgemm_chain_args& a, ChainLaunch* C, int
     if (l == 0) {
       C->kp = L.kp; C->sp = L.sp; C->grid = L.grid; C->bn = L.bn; C->dtype = L.dtype;
       C->sp.direct = 0; C->sp.jmajor = 0;
-      C->dxf = chain_plan_dxf(g, L, sm_count, &dxf_sp, &dxf_grid) ? 1 : 0;
+      C->dxf = C->pair ? 0 : (chain_plan_dxf(g, L, sm_count, &dxf_sp, &dxf_grid) ? 1 : 0);
+      if (C->pair) {
+        BUCTD_CHECK(L.bn >= 96 && L.bn % 32 == 0, BUCTD_ERR_INVALID, "tapgemm_chain: pair plan with N tile %d", L.bn);
+        int mc = 0;
+        if ((rc = pair_max_clusters(&mc))) return rc;
+        const int units = (L.sp.num_super + 1) / 2, items_v = units * (L.sp.num_items / L.sp.num_super);
+        int pairs = sm_count / 2 < mc ? sm_count / 2 : mc;
+        if (pairs > items_v) pairs = items_v;
+        C->grid = dim3((unsigned)(2 * pairs), 1);
+      }
     } else {
       BUCTD_CHECK(L.bn == C->bn && L.sp.msub == C->sp.msub && L.sp.sa == C->sp.sa && L.sp.sw == C->sp.sw &&
                       L.sp.stage_bufs == C->sp.stage_bufs && L.sp.smem_bytes == C->sp.smem_bytes,
@@ -793,8 +856,8 @@ int tapgemm_chain_prepare(const buctd_tapgemm_chain_args& a, ChainLaunch* C, int
   }
   C->cp.debug = getenv("BUCTD_CHAIN_DEBUG") ? atoi(getenv("BUCTD_CHAIN_DEBUG")) : 0;
   if (getenv("BUCTD_PLAN_DEBUG") != nullptr)
-    fprintf(stderr, "[buctd] chain plan: %d layers bn %d dxf %d lag %d msub %d sa %d stage_bufs %d slab %d B supers %d grid %u smem %d\n", a.n_layers, C->bn,
-            C->dxf, C->cp.lag, C->sp.msub, C->sp.sa, C->sp.stage_bufs, C->sp.slab_bytes, C->sp.num_super, C->grid.x, C->sp.smem_bytes);
+    fprintf(stderr, "[buctd] chain plan: %d layers bn %d dxf %d pair %d lag %d msub %d sa %d stage_bufs %d slab %d B supers %d grid %u smem %d\n", a.n_layers, C->bn,
+            C->dxf, C->pair, C->cp.lag, C->sp.msub, C->sp.sa, C->sp.stage_bufs, C->sp.slab_bytes, C->sp.num_super, C->grid.x, C->sp.smem_bytes);
   return BUCTD_OK;
 }
 
@@ -803,6 +866,13 @@ static void chain_launch_one(const ChainLaunch& C, cudaStream_t st) {
   if (C.dxf) {
     if constexpr (BN <= 64) {
       launch_pdl(tapgemm_chain_kernel<T, BN, MSUB, true>, C.grid, dim3(kChainThreads), C.sp.smem_bytes, st, C.cp, C.kp, C.sp);
+    }
+    return;
+  }
+  if (C.pair) {
+    if constexpr (BN >= 96 && MSUB <= slab_nacc<BN>()) {
+      launch_pdl_cluster(tapgemm_chain_kernel<T, BN, MSUB, false, true>, C.grid, dim3(kChainThreads), C.sp.smem_bytes, st, 2u, C.cp, C.kp,
+                         C.sp);
     }
     return;
   }

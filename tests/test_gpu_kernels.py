@@ -357,6 +357,27 @@ def test_tapgemm_chain_basic_blocks(dt, c, B, h, w, nblocks, dxf, monkeypatch):
         monkeypatch.setenv("BUCTD_DXF_MSUB", dxf.split(":")[1])
     else:
         monkeypatch.delenv("BUCTD_DXF_MSUB", raising=False)
+    _chain_case(dt, c, B, h, w, nblocks)
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("pair", ["2", "0"])
+@pytest.mark.parametrize("c,B,h,w,nblocks", [
+    (96, 5, 12, 9, 4), (192, 30, 24, 18, 4), (96, 33, 48, 36, 3),
+    (192, 9, 12, 9, 2),            # 10 tiles: 5 pairs
+    (192, 7, 12, 9, 2),            # 910 rows = 8 tiles (7.1): last tile partial
+    (384, 5, 12, 9, 2),            # two N tiles of 192; 650 rows = 6 tiles (5.1)
+    (384, 9, 12, 9, 1),            # 1170 rows = 10 tiles x 2 N tiles
+    (384, 64, 12, 9, 4),           # branch 3 of W48 at 384x288, B = 64: 65 tiles -> 33 units, the last one half dummy
+    (128, 3, 24, 18, 2), (256, 11, 12, 9, 2)])
+def test_tapgemm_chain_pair(dt, pair, c, B, h, w, nblocks, monkeypatch):
+    """the wide chains as CTA pairs (cta_group::2, half weight tiles per CTA; odd tile counts leave a dummy tile) and,
+    with BUCTD_CHAIN_PAIR=0, as the one-CTA plan (=2: pairs from C = 96 on; the default starts at 192)"""
+    monkeypatch.setenv("BUCTD_CHAIN_PAIR", pair)
+    _chain_case(dt, c, B, h, w, nblocks)
+
+
+def _chain_case(dt, c, B, h, w, nblocks):
     x = q16(_rand(B, c, h, w, seed=61), dt)
     ws = [q16(_rand(c, c, 3, 3, seed=62 + i, scale=1.0 / math.sqrt(9 * c)), dt) for i in range(2 * nblocks)]
     bs = [_rand(c, seed=80 + i, scale=0.1).float().contiguous() for i in range(2 * nblocks)]

@@ -25,6 +25,7 @@ dt = L.F16
 # variant = "<BUCTD_DXF>[:<BUCTD_DXF_MSUB>][/<BUCTD_CHAIN_DEBUG>][@<BUCTD_FORCE_MSUB>]"
 CASES = [(48, 96, 72, ["0", "0@2", "0@1", "0/1", "1:1", "1:2", "1:2/1", "1:2/2", "1:2/4", "1:2/6", "1:2/7", "1:1/1", "1:1/2", "1:1/4", "1:1/7"]),
          (64, 96, 72, ["0", "0@1", "1:1", "1:1/1", "1:1/2", "1:1/4", "1:1/7"])]
+EXTRA_KEYS = set()
 if os.environ.get("CHAIN_BENCH_CASES"):
     CASES = eval(os.environ["CHAIN_BENCH_CASES"])
 for (c, h, w, variants) in CASES:
@@ -34,7 +35,13 @@ for (c, h, w, variants) in CASES:
     bs = [torch.randn(c, device="cuda").float().contiguous() * 0.1 for _ in range(8)]
     results = {}
     for var in variants:
-        v0 = var
+        v0, *extra = var.split("+")              # "...+KEY=VAL": any other plan knob (BUCTD_CHAIN_PAIR, BUCTD_SW_MAX, ...)
+        for key in [k for k in os.environ if k in EXTRA_KEYS]:
+            del os.environ[key]
+        for kv in extra:
+            key, val = kv.split("=")
+            EXTRA_KEYS.add(key)
+            os.environ[key] = val
         for key, sep in (("BUCTD_CHAIN_LAG", "g"), ("BUCTD_FORCE_MSUB", "@"), ("BUCTD_CHAIN_DEBUG", "/"), ("BUCTD_DXF_MSUB", ":")):
             if sep in v0:
                 v0, val = v0.split(sep)
