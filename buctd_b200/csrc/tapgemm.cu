@@ -646,9 +646,10 @@ static bool plan_slab_one(const buctd_tapgemm_args& a, int bn, int num_kc, int k
   const int sa_max = num_kc > 1 ? 3 : 2;
   const char* esw = getenv("BUCTD_SW_MAX");               // experiment knobs: weight-ring depth (<= 8), stage buffers
   const char* ese = getenv("BUCTD_SE_MAX");
-  // the weight ring is latency-bound (ring depth tiles per ~0.9 us TMA round trip: chain_bench with BUCTD_CHAIN_DEBUG=5);
-  // a pair's half tiles leave room for 8 of them
-  const int sw_max = esw ? (atoi(esw) < 2 ? 2 : atoi(esw) > 8 ? 8 : atoi(esw)) : (tl_slab_pair ? 8 : 4);
+  // the weight ring is latency-bound (ring depth tiles per ~0.9 us TMA round trip: chain_bench with BUCTD_CHAIN_DEBUG=1):
+  // as deep as fits beside two stage buffers and the slabs, up to 8 tiles (C = 96 chains: 4 -> 6 tiles, 25.8 -> 24.0 us
+  // per convolution; whole forward 11.39 -> 11.25 ms)
+  const int sw_max = esw ? (atoi(esw) < 2 ? 2 : atoi(esw) > 8 ? 8 : atoi(esw)) : 8;
   const int se_max = ese ? (atoi(ese) <= 1 ? 1 : 2) : 2;
   for (int pass = 0; pass < 2 && sa == 0; ++pass) {
     if (pass == 1) {

@@ -51,21 +51,28 @@ __device__ __forceinline__ void col_reduce(long long rows, int c, double* partia
 #pragma unroll
     for (int j = 0; j < 8; ++j) dacc[v][j] = 0.0;
   if (rl < nrl) {
-    int cnt = 0;
-    for (long long r = (long long)blockIdx.x * nrl + rl; r < rows; r += (long long)gridDim.x * nrl) {
-      load(r, g * 8, acc);
-      if (++cnt == 64) {                              // flush the float accumulators into float64 every 64 rows
-#pragma unroll
-        for (int v = 0; v < NV; ++v)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { dacc[v][j] += (double)acc[v][j]; acc[v][j] = 0.f; }
-        cnt = 0;
+    // A thread walks its rows in runs of <= 64 (then the float accumulators are flushed into float64), four rows per
+    // trip: the four rows' loads are independent of the accumulators, so they are in flight together -- with one 16-byte
+    // load per thread and trip the wide layers (256 channels: 8 row lanes per block, ~100 trips) ran at DRAM latency,
+    // 0.2 TB/s.  Same additions in the same order as the one-row loop.
+    const long long step = (long long)gridDim.x * nrl;
+    long long r = (long long)blockIdx.x * nrl + rl;
+    while (r < rows) {
+      const long long left = (rows - r + step - 1) / step;
+      const int n = left < 64 ? (int)left : 64;
+      int i = 0;
+      for (; i + 4 <= n; i += 4, r += 4 * step) {
+        load(r, g * 8, acc);
+        load(r + step, g * 8, acc);
+        load(r + 2 * step, g * 8, acc);
+        load(r + 3 * step, g * 8, acc);
       }
+      for (; i < n; ++i, r += step) load(r, g * 8, acc);
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { dacc[v][j] += (double)acc[v][j]; acc[v][j] = 0.f; }
     }
-#pragma unroll
-    for (int v = 0; v < NV; ++v)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) dacc[v][j] += (double)acc[v][j];
     const int cw = groups * 8;
 #pragma unroll
     for (int v = 0; v < NV; ++v)
