@@ -68,6 +68,7 @@ pairgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   }
   if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
   tc_fence_before();
+  __syncthreads();                      // the allocator's shared-memory write, CTA-wide (also what racecheck understands)
   cluster_sync_all();                   // barriers of both CTAs are initialised, TMEM of both is allocated
   tc_fence_after();
   pdl_launch_dependents();

@@ -285,8 +285,8 @@ tapgemm_chain_kernel(const __grid_constant__ ChainParams cp, const TapGemmKParam
     else tmem_alloc(tmem_slot, sp.tmem_cols);
   }
   tc_fence_before();
+  __syncthreads();
   if constexpr (PAIR) cluster_sync_all();      // the barriers of both CTAs exist before either signals the other's
-  else __syncthreads();
   tc_fence_after();
   pdl_launch_dependents();
   pdl_wait();
