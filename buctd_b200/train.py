@@ -123,6 +123,12 @@ class TrainStep:
         self._use_graph = (os.environ.get("BUCTD_TRAIN_GRAPH", "1") != "0") if graph is None else bool(graph)
         self._static_in = None
         self.on_grads_ready: Optional[Callable[[], None]] = None      # multi-GPU: the all-reduce of self.opt.flat_grad goes here
+        # Bucketed overlap of that all-reduce with the backward (set_bucket_split): the backward is recorded in two parts;
+        # after the first, the gradients of the flat buffer's range [lo, hi) are final and ``on_bucket_ready(lo, hi)`` may
+        # start their (asynchronous) reduction while the second part runs; ``on_grads_ready`` then reduces the rest and waits.
+        self.on_bucket_ready: Optional[Callable[[int, int], None]] = None
+        self._split = None                  # (index into self.bwd, lo, hi): the early bucket is flat_grad[lo:hi]
+        self._graph2 = None
 
     # ------------------------------------------------------------------------------------------------------
     # allocation helpers
@@ -731,11 +737,58 @@ class TrainStep:
                            view(self.hm, self.heatmap_shape))
         return self._views
 
-    def _fwd_bwd(self, stream):
-        """stream: the (current) torch stream of the step"""
-        self.seed_dev.copy_(self.seed_host, non_blocking=True)
-        self._run_ops(self.fwd, stream)
-        self._run_ops(self.bwd, stream)
+    def _fwd_bwd(self, stream, part=None):
+        """stream: the (current) torch stream of the step.  part: None = the whole step; 0 = forward + the backward up to the
+        bucket split; 1 = the rest of the backward"""
+        if part in (None, 0):
+            self.seed_dev.copy_(self.seed_host, non_blocking=True)
+            self._run_ops(self.fwd, stream)
+        if part is None:
+            self._run_ops(self.bwd, stream)
+        elif part == 0:
+            self._run_ops(self.bwd[:self._split[0]], stream)
+        else:
+            self._run_ops(self.bwd[self._split[0]:], stream)
+
+    def grad_last_writes(self) -> Dict[str, int]:
+        """{parameter name -> index of the LAST backward op that writes its gradient}: every pointer-valued field of every
+        recorded backward op that points into the flat gradient buffer (found by value, not by bookkeeping)"""
+        lo = self._grad_ptr
+        hi = lo + 4 * self.opt.flat_grad.numel()
+        names = sorted(self.poff, key=self.poff.get)
+        starts = [self.poff[n] for n in names]
+        import bisect
+        last: Dict[str, int] = {}
+        for i, (_, args, _) in enumerate(self.bwd):
+            vals = args if isinstance(args, tuple) else [getattr(args, f[0]) for f in args._fields_]
+            for v in vals:
+                if isinstance(v, int) and lo <= v < hi:
+                    last[names[bisect.bisect_right(starts, (v - lo) // 4) - 1]] = i
+        return last
+
+    def set_bucket_split(self, frac: float = 0.5):
+        """Cut the recorded backward after ``frac`` of its ops and return ``(lo, hi)``: the longest contiguous range of the
+        flat gradient buffer whose parameters all have their FINAL gradient once the first part has run (the backward walks
+        the network from the head to the stem and the buffer is in module-registration order: the range is the late stages).
+        Call before the first step."""
+        if self._graph is not None:
+            raise RuntimeError("set_bucket_split() must be called before the step is recorded as a graph")
+        s = max(1, min(len(self.bwd) - 1, int(len(self.bwd) * frac)))
+        last = self.grad_last_writes()
+        names = sorted(self.poff, key=self.poff.get)
+        n = self.opt.flat_grad.numel()
+        ends = [self.poff[k] for k in names[1:]] + [n]
+        best, run_lo = (0, 0), None
+        for k, end in zip(names, ends):
+            if k in last and last[k] < s:
+                if run_lo is None:
+                    run_lo = self.poff[k]
+                if end - run_lo > best[1] - best[0]:
+                    best = (run_lo, end)
+            else:
+                run_lo = None
+        self._split = (s, best[0], best[1])
+        return best
 
     def forward_backward(self, input, target, target_weight) -> torch.Tensor:
         """forward + loss + backward: fills ``self.opt.flat_grad`` (every parameter's ``.grad`` is a view of it)"""
@@ -744,7 +797,9 @@ class TrainStep:
         with torch.cuda.device(self.device):
             self._copy_in(input, target, target_weight)
             stream = torch.cuda.current_stream(self.device)
-            if not self._use_graph:
+            if self._split is not None:
+                self._fwd_bwd_split(stream)
+            elif not self._use_graph:
                 self._fwd_bwd(stream)
             else:
                 if self._graph is None:
@@ -758,6 +813,28 @@ class TrainStep:
                     self._graph.replay()
             torch._foreach_add_([self.buffers[n] for n in self._nbt], 1)
         return self.loss_t
+
+    def _fwd_bwd_split(self, stream):
+        """the step in two parts with ``on_bucket_ready(lo)`` between them (two CUDA graphs when graphs are on)"""
+        def hook():
+            if self.on_bucket_ready is not None:
+                self.on_bucket_ready(self._split[1], self._split[2])
+        if not self._use_graph or self._graph is None:
+            self._fwd_bwd(stream, 0)                               # eager (first step: also validates every launch)
+            hook()
+            self._fwd_bwd(stream, 1)
+            if self._use_graph:
+                stream.synchronize()
+                g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1):
+                    self._fwd_bwd(torch.cuda.current_stream(self.device), 0)
+                with torch.cuda.graph(g2):
+                    self._fwd_bwd(torch.cuda.current_stream(self.device), 1)
+                self._graph, self._graph2 = g1, g2
+        else:
+            self._graph.replay()
+            hook()
+            self._graph2.replay()
 
     def step(self, input, target, target_weight) -> torch.Tensor:
         loss = self.forward_backward(input, target, target_weight)

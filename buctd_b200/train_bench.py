@@ -55,10 +55,29 @@ def run(args, ClockSampler, load_peaks):
     if world > 1:
         ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
 
+        # ONE logical all-reduce of the flat gradient buffer, issued as buckets: the range of the buffer the backward finishes
+        # first (the late stages) is reduced asynchronously under the second half of the backward, the rest after it.
+        # ev[0] .. ev[1] = what the step still waits for (the exposed part).  BUCTD_TRAIN_BUCKETS=0: one blocking call.
+        bucketed = os.environ.get("BUCTD_TRAIN_BUCKETS", "1") != "0"
+        lo, hi = ts.set_bucket_split(0.5) if bucketed else (0, 0)
+        work = [None]
+
+        def bucket(lo_, hi_):
+            work[0] = dist.all_reduce(ts.opt.flat_grad[lo_:hi_], op=dist.ReduceOp.AVG, async_op=True)
+
         def allreduce():
             ev[0].record()
-            dist.all_reduce(ts.opt.flat_grad, op=dist.ReduceOp.AVG)
+            if bucketed:
+                if lo > 0:
+                    dist.all_reduce(ts.opt.flat_grad[:lo], op=dist.ReduceOp.AVG)
+                if hi < ts.opt.flat_grad.numel():
+                    dist.all_reduce(ts.opt.flat_grad[hi:], op=dist.ReduceOp.AVG)
+                work[0].wait()
+            else:
+                dist.all_reduce(ts.opt.flat_grad, op=dist.ReduceOp.AVG)
             ev[1].record()
+        if bucketed:
+            ts.on_bucket_ready = bucket
         ts.on_grads_ready = allreduce
 
     def barrier():
@@ -126,7 +145,10 @@ def run(args, ClockSampler, load_peaks):
             "config": {"workload": "BUCTD-CoAM-W48 384x288 training step, batch=%d/GPU, JointsMSELoss(use_target_weight) + backward + Adam lr 1e-3, "
                                    "attention dropout 0.1, train-mode BatchNorm (per-GPU statistics)" % B,
                        "name": "train", "global_batch": B * world, "parallelism": "data parallel dp%d, one NCCL all-reduce (AVG) of the flat "
-                       "%.1f M-element float32 gradient buffer per step" % (world, ts.opt.flat_grad.numel() / 1e6),
+                       "%.1f M-element float32 gradient buffer per step%s" % (
+                           world, ts.opt.flat_grad.numel() / 1e6,
+                           ", issued as buckets: the late stages' range of the buffer (%.1f M elements, final after the first half of the backward) "
+                           "reduced under the second half" % ((ts._split[2] - ts._split[1]) / 1e6) if ts._split else ""),
                        "weights": "random-init (buctd_b200.synth, seed 0)", "l2": "two resident batches alternate (2 x %d MB)" % (B * 20 * H * W * 4 >> 20),
                        "loss_first_last": [round(first, 6), round(last, 6)], "workspace_gb": round(ts.ws.numel() / 2 ** 30, 2)},
             "roofline": {"bound": "tensor", "unit": "TFLOP/s", "peak": peaks["tflops_sustained"],
@@ -136,6 +158,8 @@ def run(args, ClockSampler, load_peaks):
                     "h2d_bytes_per_step": int(sum(t.numel() * 4 for t in host[0])), "d2h_bytes_per_step": 4,
                     "ms_per_step": round(ms_e2e / args.steps, 3), "api": "TrainStep.step(input_host, target_host, target_weight_host).item()"},
             "allreduce_ms": round(ar_ms[0], 3) if world > 1 else None,
+            "allreduce_note": ("exposed time: from the end of the backward to the end of the reduction (the early bucket overlaps the backward)"
+                               if world > 1 and ts._split else None),
             "gpu_launches": int(args.steps * ts.launches_per_step()), "launches_per_step": ts.launches_per_step(),
             "launch_note": "C-ABI launches recorded per step (replayed as one CUDA graph + Adam + re-pack); %d immediate launches counted by the handle" % launches,
             "clocks": clocks,

@@ -162,6 +162,42 @@ def test_graph_replay_equals_eager_and_steps_train():
     assert torch.isfinite(hm).all()
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_bucket_split_is_the_same_step(graph):
+    """the backward cut in two for the bucketed all-reduce (set_bucket_split): identical gradients; when the hook fires, the
+    early bucket -- the tail of the flat buffer -- already holds its FINAL values and the second part never touches it"""
+    name = "train_step_coam_w32_128x96"
+    cfg, net, sd, ts, x, tgt, tw = _setup(name, "bf16", drop_p=0.1, graph=graph)
+    ts.forward_backward(x, tgt, tw)
+    ts.forward_backward(x, tgt, tw)
+    torch.cuda.synchronize()
+    whole = ts.opt.flat_grad.clone()
+
+    cfg, net, sd, ts, x, tgt, tw = _setup(name, "bf16", drop_p=0.1, graph=graph)
+    lo, hi = ts.set_bucket_split(0.5)
+    n = ts.opt.flat_grad.numel()
+    assert 0 <= lo < hi <= n, (lo, hi, n)
+    assert hi - lo > n // 10, "the early bucket should be a real share of the gradient (%d of %d)" % (hi - lo, n)
+    seen = []
+
+    def hook(lo_, hi_):
+        assert (lo_, hi_) == (lo, hi)
+        seen.append(ts.opt.flat_grad[lo_:hi_].clone())             # stream-ordered: what an all-reduce launched here would read
+        ts.opt.flat_grad[lo_:hi_].mul_(1.0)                        # ... and write, while the second part runs
+    ts.on_bucket_ready = hook
+    ts.forward_backward(x, tgt, tw)
+    ts.forward_backward(x, tgt, tw)
+    torch.cuda.synchronize()
+    assert len(seen) == 2
+    assert torch.equal(ts.opt.flat_grad, whole)
+    assert torch.equal(seen[1], whole[lo:hi])
+    # every parameter of the early bucket is written for the last time before the cut
+    last = ts.grad_last_writes()
+    s = ts._split[0]
+    assert all(last[k] < s for k, off in ts.poff.items() if lo <= off < hi)
+    assert set(last) == set(ts.poff), "every parameter's gradient is written by some backward op"
+
+
 def test_adam_is_a_torch_optimizer():
     from buctd_b200.optim import Adam
     ps = [torch.nn.Parameter(torch.randn(7, 5, device="cuda")), torch.nn.Parameter(torch.randn(11, device="cuda"))]
