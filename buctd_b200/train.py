@@ -63,6 +63,24 @@ class _T:
         return self.rows * self.cs * 2
 
 
+def longest_final_range(poff: Dict[str, int], n: int, last: Dict[str, int], s: int):
+    """(lo, hi): the longest contiguous element range of a flat buffer of ``n`` elements -- parameters ``poff`` = {name ->
+    first element}, laid out back to back -- in which every parameter's last writer ``last[name]`` comes before op ``s``
+    (a parameter without a writer never qualifies).  (0, 0) when there is none."""
+    names = sorted(poff, key=poff.get)
+    ends = [poff[k] for k in names[1:]] + [n]
+    best, run_lo = (0, 0), None
+    for k, end in zip(names, ends):
+        if k in last and last[k] < s:
+            if run_lo is None:
+                run_lo = poff[k]
+            if end - run_lo > best[1] - best[0]:
+                best = (run_lo, end)
+        else:
+            run_lo = None
+    return best
+
+
 class TrainStep:
     """One recorded training step for a fixed batch size.  ``step(input, target, target_weight)`` returns the loss
     (a 0-d CUDA float32 tensor).  The model's parameters are re-homed into the optimizer's flat buffer (they stay
@@ -775,18 +793,7 @@ class TrainStep:
             raise RuntimeError("set_bucket_split() must be called before the step is recorded as a graph")
         s = max(1, min(len(self.bwd) - 1, int(len(self.bwd) * frac)))
         last = self.grad_last_writes()
-        names = sorted(self.poff, key=self.poff.get)
-        n = self.opt.flat_grad.numel()
-        ends = [self.poff[k] for k in names[1:]] + [n]
-        best, run_lo = (0, 0), None
-        for k, end in zip(names, ends):
-            if k in last and last[k] < s:
-                if run_lo is None:
-                    run_lo = self.poff[k]
-                if end - run_lo > best[1] - best[0]:
-                    best = (run_lo, end)
-            else:
-                run_lo = None
+        best = longest_final_range(self.poff, self.opt.flat_grad.numel(), last, s)
         self._split = (s, best[0], best[1])
         return best
 

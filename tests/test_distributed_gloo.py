@@ -94,3 +94,53 @@ def test_allreduce_mean_matches_global_batch_gradient_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(err < 1e-6 for _, err in res), res
+
+
+def test_longest_final_range():
+    """the early bucket of the bucketed gradient all-reduce: longest contiguous run of parameters whose last writer precedes
+    the cut (buctd_b200.train.longest_final_range; the GPU test checks it against the recorded step)"""
+    from buctd_b200.train import longest_final_range
+    poff = {"a": 0, "b": 10, "c": 30, "d": 35, "e": 60}
+    n = 100
+    last = {"a": 90, "b": 5, "c": 7, "d": 80, "e": 3}
+    assert longest_final_range(poff, n, last, 50) == (60, 100)            # e alone (40) beats b + c (25)
+    assert longest_final_range(poff, n, last, 85) == (10, 100)            # b .. e
+    assert longest_final_range(poff, n, last, 4) == (60, 100)
+    assert longest_final_range(poff, n, last, 3) == (0, 0)
+    assert longest_final_range(poff, n, {"b": 1, "c": 1}, 50) == (10, 35)  # parameters without a writer never qualify
+    assert longest_final_range(poff, n, last, 1000) == (0, 100)
+
+
+def _bucket_worker(rank, world, port, q):
+    """ONE logical all-reduce issued as buckets (an asynchronous early range + the rest) == the single call"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(11 + rank)
+        flat = torch.randn(1000, generator=g)
+        whole = flat.clone()
+        dist.all_reduce(whole, op=dist.ReduceOp.SUM)
+        whole /= world
+        lo, hi = 333, 801
+        work = dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True)       # gloo has no AVG: sum, then scale
+        dist.all_reduce(flat[:lo], op=dist.ReduceOp.SUM)
+        dist.all_reduce(flat[hi:], op=dist.ReduceOp.SUM)
+        work.wait()
+        flat /= world
+        q.put((rank, bool(torch.equal(flat, whole))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_equals_single_call_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res), res
