@@ -239,9 +239,9 @@ def run_native(args):
                 sink.add_(res[0])                               # the host consumes every result
 
         e2e_loop(3)
-        # three timed passes of exactly K steps each, the fastest one is reported (all are in the line): the host side of
-        # this loop (pinned copies under the previous batch's forward) is exposed to the box's other host activity, and a
-        # pass whose copies lose their overlap costs +3.4 .. 5.5 ms per step (one pass in four, profiles/README.md)
+        # three timed passes of exactly K steps each, the fastest one is reported (all are in the line).  (Until the end of
+        # round 2 every predict_stream call allocated its device slots on a fresh side stream -- two 85 MB cudaMallocs,
+        # ~0.25 s -- which made a 50-step pass read up to 9 ms per step slower; the stream is now cached, profiles/README.md.)
         e2e_passes = [timed(e2e_loop, args.steps) for _ in range(3)]
         ms_e2e = min(e2e_passes)
         h2d = sum(int(t.numel() * t.element_size()) for t in host[0])
